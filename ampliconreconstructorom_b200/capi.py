@@ -1,0 +1,222 @@
+"""ctypes binding of libsegaligner_b200.so (C ABI in include/segaligner_b200.h).
+
+There is no CPU fallback: importing works without a GPU (so the symbol table can be checked), but creating a
+Context raises if the shared library is missing or no sm_100 device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "lib" / "libsegaligner_b200.so"
+BIN_PATH = PKG_DIR / "bin" / "SegAligner"
+
+SA_INIT_SEMIGLOBAL, SA_INIT_LOCAL, SA_INIT_FITTING = 0, 1, 2
+SA_START_SEMIGLOBAL, SA_START_LOCAL, SA_START_END = 0, 1, 2
+SA_SIDE_CONTIG, SA_SIDE_SEG = 0, 1
+
+problem_dtype = np.dtype([("contig", "<i4"), ("seg", "<i4"), ("used_slot", "<i4"), ("reserved", "<i4")])
+result_dtype = np.dtype([("score", "<f4"), ("j", "<i4"), ("q", "<i4"), ("path_len", "<i4")])
+
+
+class Mode(C.Structure):
+    _fields_ = [("init_mode", C.c_int32), ("start_mode", C.c_int32), ("fitting", C.c_int32),
+                ("lookback", C.c_int32), ("swap_b_x", C.c_int32)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("fill_ms", C.c_float), ("post_ms", C.c_float), ("n_launches", C.c_int32), ("reserved", C.c_int32)]
+
+
+# every symbol include/segaligner_b200.h declares (tests check the library exports exactly these)
+EXPORTS = [
+    "sa_device_count", "sa_ctx_create", "sa_ctx_destroy", "sa_last_error", "sa_set_maps", "sa_score_batch",
+    "sa_score_batch_device", "sa_sync", "sa_align_batch", "sa_detect_batch", "sa_fill_one", "sa_powf12",
+    "sa_powf12_range", "sa_get_timing", "sa_measure_fp64_peak",
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree shared library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback for the SegAligner DP path)")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.sa_device_count.restype = C.c_int
+    lib.sa_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.sa_ctx_destroy.argtypes = [vp]
+    lib.sa_ctx_destroy.restype = None
+    lib.sa_last_error.argtypes = [vp]
+    lib.sa_last_error.restype = C.c_char_p
+    lib.sa_set_maps.argtypes = [vp, C.c_int, i32, vp, vp, vp]
+    lib.sa_score_batch.argtypes = [vp, C.POINTER(Mode), vp, i64, vp]
+    lib.sa_score_batch_device.argtypes = [vp, C.POINTER(Mode), vp, vp, i64, vp]
+    lib.sa_sync.argtypes = [vp]
+    lib.sa_align_batch.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, i64, i64, vp, vp, vp, vp, vp]
+    lib.sa_detect_batch.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, vp, vp, vp]
+    lib.sa_fill_one.argtypes = [vp, C.POINTER(Mode), vp, vp, i64, vp, vp, vp]
+    lib.sa_powf12.argtypes = [vp, vp, i64, vp, C.c_int]
+    lib.sa_powf12_range.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp]
+    lib.sa_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    lib.sa_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class SegAlignerError(RuntimeError):
+    pass
+
+
+class Context:
+    """One GPU context (sa_ctx). Not thread-safe; use one per host thread / device."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.sa_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise SegAlignerError(f"sa_ctx_create(device={device}) failed with {rc}: no usable sm_100 GPU "
+                                  "(the DP path has no CPU fallback)")
+        self.h = h
+        self.n_labels = [None, None]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sa_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise SegAlignerError(f"{what} failed ({rc}): {self.lib.sa_last_error(self.h).decode()}")
+
+    def set_maps(self, side: int, off: np.ndarray, pos: np.ndarray, prob: np.ndarray):
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        prob = np.ascontiguousarray(prob, dtype=np.float32)
+        n_maps = len(off) - 1
+        assert pos.size == off[-1] and prob.size == off[-1] - n_maps
+        self._check(self.lib.sa_set_maps(self.h, side, n_maps, _ptr(off), _ptr(pos), _ptr(prob)), "sa_set_maps")
+        self.n_labels[side] = (np.diff(off) - 1).astype(np.int64)
+
+    @staticmethod
+    def mode(init_mode=SA_INIT_SEMIGLOBAL, start_mode=SA_START_SEMIGLOBAL, fitting=0, lookback=6, swap_b_x=0):
+        return Mode(init_mode, start_mode, fitting, lookback, swap_b_x)
+
+    @staticmethod
+    def problems(contig, seg, used_slot=None):
+        contig = np.asarray(contig, dtype=np.int32)
+        pr = np.zeros(contig.size, dtype=problem_dtype)
+        pr["contig"] = contig
+        pr["seg"] = np.asarray(seg, dtype=np.int32)
+        pr["used_slot"] = -1 if used_slot is None else np.asarray(used_slot, dtype=np.int32)
+        return pr
+
+    def score_batch(self, mode: Mode, problems: np.ndarray) -> np.ndarray:
+        problems = np.ascontiguousarray(problems, dtype=problem_dtype)
+        res = np.zeros(problems.size, dtype=result_dtype)
+        self._check(self.lib.sa_score_batch(self.h, C.byref(mode), _ptr(problems), problems.size, _ptr(res)),
+                    "sa_score_batch")
+        return res
+
+    def score_batch_device(self, mode: Mode, d_problems: int, d_order: int, n: int, d_results: int):
+        self._check(self.lib.sa_score_batch_device(self.h, C.byref(mode), C.c_void_p(d_problems),
+                                                   C.c_void_p(d_order) if d_order else None, n,
+                                                   C.c_void_p(d_results)), "sa_score_batch_device")
+
+    def sync(self):
+        self._check(self.lib.sa_sync(self.h), "sa_sync")
+
+    def align_batch(self, mode: Mode, problems: np.ndarray, used_bits: np.ndarray | None = None,
+                    used_words_per_slot: int = 0):
+        """Returns (results, path_off, path_j, path_q, path_s); paths are end->start like get_aln_list."""
+        problems = np.ascontiguousarray(problems, dtype=problem_dtype)
+        n = problems.size
+        nb = self.n_labels[0][problems["contig"]]
+        nx = self.n_labels[1][problems["seg"]]
+        path_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.minimum(nb, nx), out=path_off[1:])
+        tot = max(int(path_off[-1]), 1)
+        pj = np.full(tot, -1, dtype=np.int32)
+        pq = np.full(tot, -1, dtype=np.int32)
+        ps = np.zeros(tot, dtype=np.float32)
+        res = np.zeros(n, dtype=result_dtype)
+        n_slots = 0
+        if used_bits is not None:
+            used_bits = np.ascontiguousarray(used_bits, dtype=np.uint32)
+            n_slots = used_bits.size // max(used_words_per_slot, 1)
+        self._check(self.lib.sa_align_batch(self.h, C.byref(mode), _ptr(problems), n, _ptr(used_bits),
+                                            used_words_per_slot, n_slots, _ptr(path_off), _ptr(res), _ptr(pj),
+                                            _ptr(pq), _ptr(ps)), "sa_align_batch")
+        return res, path_off, pj, pq, ps
+
+    def detect_batch(self, mode: Mode, problems: np.ndarray, n_want: np.ndarray):
+        problems = np.ascontiguousarray(problems, dtype=problem_dtype)
+        n = problems.size
+        n_want = np.ascontiguousarray(n_want, dtype=np.int32)
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(n_want, out=off[1:])
+        scores = np.zeros(max(int(off[-1]), 1), dtype=np.float32)
+        got = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.sa_detect_batch(self.h, C.byref(mode), _ptr(problems), n, _ptr(n_want), _ptr(off),
+                                             _ptr(scores), _ptr(got)), "sa_detect_batch")
+        return scores, off, got
+
+    def fill_one(self, mode: Mode, contig: int, seg: int, used_rows=None):
+        nb = int(self.n_labels[0][contig])
+        nx = int(self.n_labels[1][seg])
+        pr = self.problems([contig], [seg])
+        S = np.zeros((nb, nx), dtype=np.float32)
+        prev = np.zeros((nb, nx, 2), dtype=np.int32)
+        res = np.zeros(1, dtype=result_dtype)
+        used_bits, words = None, 0
+        if used_rows is not None:
+            words = (nb + 31) // 32
+            used_bits = np.zeros(words, dtype=np.uint32)
+            for j in used_rows:
+                used_bits[j >> 5] |= np.uint32(1 << (j & 31))
+        self._check(self.lib.sa_fill_one(self.h, C.byref(mode), _ptr(pr), _ptr(used_bits), words, _ptr(S),
+                                         _ptr(prev), _ptr(res)), "sa_fill_one")
+        return S, prev, res[0]
+
+    def powf12(self, x: np.ndarray, fast: bool = True) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.zeros_like(x)
+        self._check(self.lib.sa_powf12(self.h, _ptr(x), x.size, _ptr(out), 1 if fast else 0), "sa_powf12")
+        return out
+
+    def powf12_range(self, lo_bits: int, hi_bits: int):
+        n = hi_bits - lo_bits
+        a = np.zeros(n, dtype=np.float32)
+        b = np.zeros(n, dtype=np.float32)
+        self._check(self.lib.sa_powf12_range(self.h, lo_bits, hi_bits, _ptr(a), _ptr(b)), "sa_powf12_range")
+        return a, b
+
+    def timing(self) -> Timing:
+        t = Timing()
+        self._check(self.lib.sa_get_timing(self.h, C.byref(t)), "sa_get_timing")
+        return t
+
+    def fp64_peak(self) -> float:
+        v = C.c_double()
+        self._check(self.lib.sa_measure_fp64_peak(self.h, C.byref(v)), "sa_measure_fp64_peak")
+        return v.value

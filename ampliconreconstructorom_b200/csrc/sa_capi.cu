@@ -1,0 +1,516 @@
+// C-ABI host layer of libsegaligner_b200.so (declared in include/segaligner_b200.h).
+// Owns device memory, the stream, batching/chunking and the largest-first problem order; all arithmetic that
+// decides results runs in the kernels of sa_kernels.cu, except the per-label operand tables built here on the
+// host in exact fp32 (same operations, same order as score_f, /root/reference/SegAligner/SegAligner.cpp:86-90).
+// There is NO CPU fallback: every entry point fails with SA_ENODEV / SA_ECUDA when no sm_100 GPU is usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "sa_kernels.cuh"
+
+using namespace sa;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+struct MapSetHost {
+    std::vector<int64_t> off;  // n_maps+1
+    DevBuf d_pos, d_prob, d_ops, d_off;
+    int n_maps = 0;
+    int max_labels = 0;
+    MapSetDev dev() const {
+        MapSetDev m;
+        m.pos = d_pos.as<float>();
+        m.prob = d_prob.as<float>();
+        m.ops = d_ops.as<LabelOps>();
+        m.pos_off = d_off.as<int64_t>();
+        m.n_maps = n_maps;
+        m.max_labels = max_labels;
+        return m;
+    }
+    int labels(int m) const { return (int)(off[m + 1] - off[m]) - 1; }
+};
+
+}  // namespace
+
+struct sa_ctx {
+    int device = 0;
+    int n_sms = 0;
+    int ctas_per_sm = 1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    MapSetHost sides[2];
+    DevBuf d_problems, d_order, d_results, d_halo, d_counter, d_cell_off, d_S, d_code, d_used, d_path_off, d_path_j,
+        d_path_q, d_path_s, d_tmp0, d_tmp1, d_tmp2;
+    sa_timing timing = {0, 0, 0, 0};
+    size_t store_budget_cells = 0;  // max cells of stored matrices per chunk
+};
+
+namespace {
+
+int fail(sa_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    return code;
+}
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? SA_ENOMEM : SA_ECUDA,                   \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                           \
+    } while (0)
+
+// score_f's operands per label, exact fp32, reference operation order.
+void build_label_ops(const float *pos, const float *prob, int n, LabelOps *out) {
+    for (int l = 0; l < n; l++) {
+        for (int k = 1; k <= LB; k++) {
+            float d = 0.0f, f = 0.0f;
+            if (l - k >= 0) {
+                volatile float dd = pos[l] - pos[l - k];  // b_posns[j] - b_posns[i]  (SegAligner.cpp:87)
+                d = dd;
+                volatile float acc = 0.0f;  // std::accumulate(probs+p+1, probs+q, 0.0f)  (:86)
+                for (int t = l - k + 1; t < l; t++) acc = acc + prob[t];
+                volatile float ff = 5000.0f * acc;  // fp_t (:90)
+                f = ff;
+            }
+            out[l].d[k - 1] = d;
+            out[l].f[k - 1] = f;
+        }
+    }
+}
+
+// Largest-first processing order (LPT): counting sort on a 1/8-octave log2 size class, O(n).
+void build_order(const sa_ctx *c, const sa_problem *pr, int64_t n, std::vector<int32_t> &order) {
+    order.resize((size_t)n);
+    const int NB = 8 * 40;
+    std::vector<int64_t> cnt(NB + 1, 0);
+    std::vector<uint16_t> cls((size_t)n);
+    for (int64_t k = 0; k < n; k++) {
+        const double cells = (double)c->sides[0].labels(pr[k].contig) * (double)c->sides[1].labels(pr[k].seg);
+        int b = cells > 1.0 ? (int)(std::log2(cells) * 8.0) : 0;
+        if (b >= NB) b = NB - 1;
+        cls[(size_t)k] = (uint16_t)(NB - 1 - b);  // descending
+        cnt[NB - 1 - b + 1]++;
+    }
+    for (int b = 0; b < NB; b++) cnt[b + 1] += cnt[b];
+    for (int64_t k = 0; k < n; k++) order[(size_t)cnt[cls[(size_t)k]]++] = (int32_t)k;
+}
+
+int check_problems(sa_ctx *ctx, const sa_problem *pr, int64_t n, int64_t n_used_slots) {
+    const int nc = ctx->sides[0].n_maps, ns = ctx->sides[1].n_maps;
+    for (int64_t k = 0; k < n; k++) {
+        if (pr[k].contig < 0 || pr[k].contig >= nc || pr[k].seg < 0 || pr[k].seg >= ns)
+            return fail(ctx, SA_EINVAL, "problem " + std::to_string(k) + ": map index out of range");
+        if (pr[k].used_slot >= n_used_slots) return fail(ctx, SA_EINVAL, "problem: used_slot out of range");
+        if (ctx->sides[0].labels(pr[k].contig) < 1 || ctx->sides[1].labels(pr[k].seg) < 1)
+            return fail(ctx, SA_EINVAL, "problem " + std::to_string(k) + ": map without labels");
+    }
+    return SA_OK;
+}
+
+int n_fill_ctas(const sa_ctx *ctx) { return ctx->n_sms * ctx->ctas_per_sm; }
+
+int prepare_fill(sa_ctx *ctx, FillParams &P, const sa_mode *mode) {
+    if (!mode) return fail(ctx, SA_EINVAL, "mode is NULL");
+    if (ctx->sides[0].n_maps == 0 || ctx->sides[1].n_maps == 0) return fail(ctx, SA_EINVAL, "maps not uploaded");
+    if (mode->lookback != LB) return fail(ctx, SA_EINVAL, "banded kernels need lookback == 6");
+    memset(&P, 0, sizeof(P));
+    P.contigs = ctx->sides[0].dev();
+    P.segs = ctx->sides[1].dev();
+    P.init_mode = mode->init_mode;
+    P.start_mode = mode->start_mode;
+    P.fitting = mode->fitting;
+    const long long n_warps = (long long)n_fill_ctas(ctx) * FILL_WARPS;
+    P.halo_stride = (long long)std::max(ctx->sides[1].max_labels, 1) * 8;
+    CU(ctx->d_halo.reserve(sizeof(float) * (size_t)(n_warps * 2 * P.halo_stride)));
+    P.halo = ctx->d_halo.as<float>();
+    CU(ctx->d_counter.reserve(sizeof(unsigned long long)));
+    P.counter = ctx->d_counter.as<unsigned long long>();
+    return SA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sa_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int sa_ctx_create(int device, sa_ctx **out) {
+    if (!out) return SA_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return SA_ENODEV;
+    if (cudaSetDevice(device) != cudaSuccess) return SA_ENODEV;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SA_ENODEV;
+    if (prop.major != 10) {
+        fprintf(stderr, "segaligner_b200: device %d is sm_%d%d; this library contains sm_100a code only\n", device,
+                prop.major, prop.minor);
+        return SA_ENODEV;
+    }
+    sa_ctx *ctx = new sa_ctx();
+    ctx->device = device;
+    ctx->n_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return SA_ECUDA;
+    }
+    for (auto &e : ctx->ev) cudaEventCreate(&e);
+    ctx->ctas_per_sm = fill_ctas_per_sm();
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    // stored matrices cost 5 bytes per cell; keep a chunk below a quarter of free memory and below 2^31 cells
+    ctx->store_budget_cells = std::min<size_t>(free_b / 4 / 5, (size_t)1 << 31);
+    if (const char *e = getenv("SA_STORE_BUDGET_CELLS")) ctx->store_budget_cells = (size_t)atoll(e);
+    *out = ctx;
+    return SA_OK;
+}
+
+void sa_ctx_destroy(sa_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &s : ctx->sides) {
+        s.d_pos.release();
+        s.d_prob.release();
+        s.d_ops.release();
+        s.d_off.release();
+    }
+    DevBuf *bufs[] = {&ctx->d_problems, &ctx->d_order,  &ctx->d_results,  &ctx->d_halo,   &ctx->d_counter, &ctx->d_cell_off,
+                      &ctx->d_S,        &ctx->d_code,   &ctx->d_used,     &ctx->d_path_off, &ctx->d_path_j,  &ctx->d_path_q,
+                      &ctx->d_path_s,   &ctx->d_tmp0,   &ctx->d_tmp1,     &ctx->d_tmp2};
+    for (auto b : bufs) b->release();
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *sa_last_error(const sa_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int sa_sync(sa_ctx *ctx) {
+    if (!ctx) return SA_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SA_OK;
+}
+
+int sa_set_maps(sa_ctx *ctx, int side, int32_t n_maps, const int64_t *off, const float *pos, const float *prob) {
+    if (!ctx) return SA_EINVAL;
+    if (side != SA_SIDE_CONTIG && side != SA_SIDE_SEG) return fail(ctx, SA_EINVAL, "bad side");
+    if (n_maps <= 0 || !off || !pos || !prob) return fail(ctx, SA_EINVAL, "empty map set");
+    CU(cudaSetDevice(ctx->device));
+    MapSetHost &S = ctx->sides[side];
+    S.off.assign(off, off + n_maps + 1);
+    S.n_maps = n_maps;
+    S.max_labels = 0;
+    const int64_t n_pos = off[n_maps];
+    const int64_t n_lab = n_pos - n_maps;
+    for (int m = 0; m < n_maps; m++) {
+        if (off[m + 1] - off[m] < 1) return fail(ctx, SA_EINVAL, "map with no entries");
+        S.max_labels = std::max(S.max_labels, S.labels(m));
+    }
+    std::vector<LabelOps> ops((size_t)std::max<int64_t>(n_lab, 1));
+    for (int m = 0; m < n_maps; m++) build_label_ops(pos + off[m], prob + (off[m] - m), S.labels(m), ops.data() + (off[m] - m));
+    CU(S.d_pos.reserve(sizeof(float) * (size_t)n_pos));
+    CU(S.d_prob.reserve(sizeof(float) * (size_t)std::max<int64_t>(n_lab, 1)));
+    CU(S.d_ops.reserve(sizeof(LabelOps) * ops.size()));
+    CU(S.d_off.reserve(sizeof(int64_t) * (size_t)(n_maps + 1)));
+    CU(cudaMemcpyAsync(S.d_pos.p, pos, sizeof(float) * (size_t)n_pos, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_lab > 0) {
+        CU(cudaMemcpyAsync(S.d_prob.p, prob, sizeof(float) * (size_t)n_lab, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(S.d_ops.p, ops.data(), sizeof(LabelOps) * (size_t)n_lab, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(S.d_off.p, off, sizeof(int64_t) * (size_t)(n_maps + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SA_OK;
+}
+
+int sa_score_batch_device(sa_ctx *ctx, const sa_mode *mode, const sa_problem *d_problems, const int32_t *d_order,
+                          int64_t n, sa_result *d_results) {
+    if (!ctx) return SA_EINVAL;
+    if (n <= 0) return SA_OK;
+    CU(cudaSetDevice(ctx->device));
+    FillParams P;
+    int rc = prepare_fill(ctx, P, mode);
+    if (rc) return rc;
+    P.problems = d_problems;
+    P.order = d_order;
+    P.n_problems = n;
+    P.results = d_results;
+    CU(cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    launch_fill(P, false, mode->swap_b_x != 0, n_fill_ctas(ctx), ctx->stream);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->timing.n_launches = 1;
+    ctx->timing.post_ms = 0;
+    ctx->timing.fill_ms = -1.0f;  // resolved lazily by sa_get_timing
+    return SA_OK;
+}
+
+int sa_score_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, sa_result *results) {
+    if (!ctx) return SA_EINVAL;
+    if (n <= 0) return SA_OK;
+    if (!problems || !results) return fail(ctx, SA_EINVAL, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    int rc = check_problems(ctx, problems, n, 0);
+    if (rc) return rc;
+    std::vector<int32_t> order;
+    build_order(ctx, problems, n, order);
+    CU(ctx->d_problems.reserve(sizeof(sa_problem) * (size_t)n));
+    CU(ctx->d_order.reserve(sizeof(int32_t) * (size_t)n));
+    CU(ctx->d_results.reserve(sizeof(sa_result) * (size_t)n));
+    CU(cudaMemcpyAsync(ctx->d_problems.p, problems, sizeof(sa_problem) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_order.p, order.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = sa_score_batch_device(ctx, mode, ctx->d_problems.as<sa_problem>(), ctx->d_order.as<int32_t>(), n,
+                               ctx->d_results.as<sa_result>());
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(results, ctx->d_results.p, sizeof(sa_result) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SA_OK;
+}
+
+int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const uint32_t *used_bits,
+                   int64_t used_words_per_slot, int64_t n_used_slots, const int64_t *path_off, sa_result *results,
+                   int32_t *path_j, int32_t *path_q, float *path_s) {
+    if (!ctx) return SA_EINVAL;
+    if (n <= 0) return SA_OK;
+    if (!problems || !results || !path_off || !path_j || !path_q || !path_s) return fail(ctx, SA_EINVAL, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    int rc = check_problems(ctx, problems, n, used_bits ? n_used_slots : 0);
+    if (rc) return rc;
+    FillParams P;
+    rc = prepare_fill(ctx, P, mode);
+    if (rc) return rc;
+    if (used_bits && n_used_slots > 0) {
+        const size_t bytes = sizeof(uint32_t) * (size_t)(used_words_per_slot * n_used_slots);
+        CU(ctx->d_used.reserve(bytes));
+        CU(cudaMemcpyAsync(ctx->d_used.p, used_bits, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        P.used_bits = ctx->d_used.as<uint32_t>();
+        P.used_words_per_slot = used_words_per_slot;
+    }
+    ctx->timing = {0, 0, 0, 0};
+    // chunk so that the stored matrices fit the budget
+    int64_t k0 = 0;
+    std::vector<int64_t> cell_off;
+    while (k0 < n) {
+        cell_off.clear();
+        int64_t cells = 0, k1 = k0;
+        while (k1 < n) {
+            const int64_t c = (int64_t)ctx->sides[0].labels(problems[k1].contig) * ctx->sides[1].labels(problems[k1].seg);
+            if (k1 > k0 && (size_t)(cells + c) > ctx->store_budget_cells) break;
+            cell_off.push_back(cells);
+            cells += c;
+            k1++;
+        }
+        const int64_t m = k1 - k0;
+        std::vector<int32_t> order;
+        build_order(ctx, problems + k0, m, order);
+        std::vector<int64_t> poff((size_t)m + 1);
+        for (int64_t k = 0; k <= m; k++) poff[(size_t)k] = path_off[k0 + k] - path_off[k0];
+        const int64_t n_path = poff[(size_t)m];
+        CU(ctx->d_problems.reserve(sizeof(sa_problem) * (size_t)m));
+        CU(ctx->d_order.reserve(sizeof(int32_t) * (size_t)m));
+        CU(ctx->d_results.reserve(sizeof(sa_result) * (size_t)m));
+        CU(ctx->d_cell_off.reserve(sizeof(int64_t) * (size_t)m));
+        CU(ctx->d_S.reserve(sizeof(float) * (size_t)cells));
+        CU(ctx->d_code.reserve((size_t)cells));
+        CU(ctx->d_path_off.reserve(sizeof(int64_t) * (size_t)(m + 1)));
+        CU(ctx->d_path_j.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(n_path, 1)));
+        CU(ctx->d_path_q.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(n_path, 1)));
+        CU(ctx->d_path_s.reserve(sizeof(float) * (size_t)std::max<int64_t>(n_path, 1)));
+        CU(cudaMemcpyAsync(ctx->d_problems.p, problems + k0, sizeof(sa_problem) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_order.p, order.data(), sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_cell_off.p, cell_off.data(), sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_path_off.p, poff.data(), sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyHostToDevice, ctx->stream));
+        P.problems = ctx->d_problems.as<sa_problem>();
+        P.order = ctx->d_order.as<int32_t>();
+        P.cell_off = ctx->d_cell_off.as<int64_t>();
+        P.n_problems = m;
+        P.results = ctx->d_results.as<sa_result>();
+        P.S = ctx->d_S.as<float>();
+        P.code = ctx->d_code.as<uint8_t>();
+        CU(cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), ctx->stream));
+        CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+        launch_fill(P, true, mode->swap_b_x != 0, n_fill_ctas(ctx), ctx->stream);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+        TraceParams T;
+        memset(&T, 0, sizeof(T));
+        T.contigs = P.contigs;
+        T.segs = P.segs;
+        T.problems = P.problems;
+        T.cell_off = P.cell_off;
+        T.n_problems = m;
+        T.S = P.S;
+        T.code = P.code;
+        T.path_off = ctx->d_path_off.as<int64_t>();
+        T.results = P.results;
+        T.path_j = ctx->d_path_j.as<int32_t>();
+        T.path_q = ctx->d_path_q.as<int32_t>();
+        T.path_s = ctx->d_path_s.as<float>();
+        launch_traceback(T, ctx->stream);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+        CU(cudaMemcpyAsync(results + k0, ctx->d_results.p, sizeof(sa_result) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (n_path > 0) {
+            CU(cudaMemcpyAsync(path_j + path_off[k0], ctx->d_path_j.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(path_q + path_off[k0], ctx->d_path_q.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(path_s + path_off[k0], ctx->d_path_s.p, sizeof(float) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CU(cudaStreamSynchronize(ctx->stream));
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+        ctx->timing.fill_ms += a;
+        ctx->timing.post_ms += b;
+        ctx->timing.n_launches += 2;
+        k0 = k1;
+    }
+    return SA_OK;
+}
+
+int sa_fill_one(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problem, const uint32_t *used_bits,
+                int64_t used_words, float *S, int32_t *prev, sa_result *result) {
+    if (!ctx) return SA_EINVAL;
+    if (!problem || !result) return fail(ctx, SA_EINVAL, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    sa_problem pr = *problem;
+    int rc = check_problems(ctx, &pr, 1, used_bits ? 1 : 0);
+    if (rc) return rc;
+    const int nb = ctx->sides[0].labels(pr.contig), nx = ctx->sides[1].labels(pr.seg);
+    const int64_t cap = std::min(nb, nx);
+    std::vector<int64_t> poff = {0, cap};
+    std::vector<int32_t> pj((size_t)cap), pq((size_t)cap);
+    std::vector<float> ps((size_t)cap);
+    if (used_bits) pr.used_slot = 0;
+    rc = sa_align_batch(ctx, mode, &pr, 1, used_bits, used_words, used_bits ? 1 : 0, poff.data(), result, pj.data(),
+                        pq.data(), ps.data());
+    if (rc) return rc;
+    const size_t cells = (size_t)nb * nx;
+    if (S) CU(cudaMemcpy(S, ctx->d_S.p, sizeof(float) * cells, cudaMemcpyDeviceToHost));
+    if (prev) {
+        std::vector<uint8_t> code(cells);
+        CU(cudaMemcpy(code.data(), ctx->d_code.p, cells, cudaMemcpyDeviceToHost));
+        for (int j = 0; j < nb; j++)
+            for (int q = 0; q < nx; q++) {
+                const size_t c = (size_t)j * nx + q;
+                if (code[c] == 0) {
+                    prev[2 * c] = -1;
+                    prev[2 * c + 1] = -1;
+                } else {
+                    prev[2 * c] = j - ((code[c] - 1) / LB + 1);
+                    prev[2 * c + 1] = q - ((code[c] - 1) % LB + 1);
+                }
+            }
+    }
+    return SA_OK;
+}
+
+int sa_detect_batch(sa_ctx *ctx, const sa_mode *, const sa_problem *, int64_t, const int32_t *, const int64_t *, float *,
+                    int32_t *) {
+    return fail(ctx, SA_EINVAL, "sa_detect_batch: not implemented yet");
+}
+
+int sa_powf12(sa_ctx *ctx, const float *x, int64_t n, float *out, int use_fast_path) {
+    if (!ctx) return SA_EINVAL;
+    if (n <= 0) return SA_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->d_tmp0.reserve(sizeof(float) * (size_t)n));
+    CU(ctx->d_tmp1.reserve(sizeof(float) * (size_t)n));
+    CU(cudaMemcpyAsync(ctx->d_tmp0.p, x, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    launch_powf12(ctx->d_tmp0.as<float>(), n, ctx->d_tmp1.as<float>(), use_fast_path, ctx->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, ctx->d_tmp1.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SA_OK;
+}
+
+int sa_powf12_range(sa_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, float *out_fast, float *out_generic) {
+    if (!ctx) return SA_EINVAL;
+    if (hi_bits <= lo_bits) return SA_OK;
+    const size_t n = (size_t)hi_bits - lo_bits;
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->d_tmp0.reserve(sizeof(float) * n));
+    CU(ctx->d_tmp1.reserve(sizeof(float) * n));
+    launch_powf12_range(lo_bits, hi_bits, ctx->d_tmp0.as<float>(), ctx->d_tmp1.as<float>(), ctx->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_fast, ctx->d_tmp0.p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_generic, ctx->d_tmp1.p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SA_OK;
+}
+
+int sa_get_timing(sa_ctx *ctx, sa_timing *t) {
+    if (!ctx || !t) return SA_EINVAL;
+    if (ctx->timing.fill_ms < 0) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaEventSynchronize(ctx->ev[1]));
+        float a = 0;
+        CU(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+        ctx->timing.fill_ms = a;
+    }
+    *t = ctx->timing;
+    return SA_OK;
+}
+
+int sa_measure_fp64_peak(sa_ctx *ctx, double *dfma_per_s) {
+    if (!ctx || !dfma_per_s) return SA_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->d_tmp2.reserve(64));
+    const int iters = 4096, ctas = ctx->n_sms * 8;
+    launch_dfma_peak(ctx->d_tmp2.as<double>(), 64, ctas, ctx->stream);  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+        launch_dfma_peak(ctx->d_tmp2.as<double>(), iters, ctas, ctx->stream);
+        CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CU(cudaEventSynchronize(ctx->ev[1]));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        // per thread: iters * 8 unrolled * 8 chains DFMA; thread-level instruction count
+        const double inst = (double)ctas * 256.0 * iters * 64.0;
+        best = std::max(best, inst / (ms * 1e-3));
+    }
+    CU(cudaGetLastError());
+    *dfma_per_s = best;
+    return SA_OK;
+}
+
+}  // extern "C"

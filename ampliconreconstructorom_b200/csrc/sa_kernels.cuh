@@ -1,0 +1,70 @@
+// Device-side data structures shared by the kernels (sa_kernels.cu) and the C-ABI host layer (sa_capi.cu).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "../../include/segaligner_b200.h"
+
+namespace sa {
+
+constexpr int LB = 6;  // banded look-back of the reference (main.cpp:27); the -nl path uses fill_unbanded
+
+// Per-label operand table, built once per map set on the host in exact fp32 with the reference's operation
+// order (build_label_ops in sa_capi.cu):
+//   d[k-1] = pos[l] - pos[l-k]                           interval terms of score_f (SegAligner.cpp:87)
+//   f[k-1] = 5000f * (((0+prob[l-k+1])+...)+prob[l-1])   fp_t of score_f (:86,:90) for a look-back of k
+// Entries whose predecessor l-k does not exist hold 0 (never selected: the predecessor score is -inf).
+struct __align__(16) LabelOps {
+    float d[LB];
+    float f[LB];
+};
+static_assert(sizeof(LabelOps) == 48, "LabelOps must be 48 bytes");
+
+struct MapSetDev {
+    const float *pos;        // concatenated positions, n+1 per map
+    const float *prob;       // concatenated non-collapse probabilities, n per map
+    const LabelOps *ops;     // one per label (concatenated, n per map)
+    const int64_t *pos_off;  // n_maps+1 offsets into pos; labels of map m start at pos_off[m]-m in ops/prob
+    int32_t n_maps;
+    int32_t max_labels;
+};
+
+struct FillParams {
+    MapSetDev contigs, segs;
+    const sa_problem *problems;
+    const int32_t *order;     // processing order (largest first) or nullptr
+    const int64_t *cell_off;  // per problem offset (in cells) into S/code, STORE variants only
+    long long n_problems;
+    const uint32_t *used_bits;
+    long long used_words_per_slot;
+    float *S;       // stored score matrices
+    uint8_t *code;  // stored predecessor codes: 0 = none, else 1 + (dj-1)*6 + (dq-1)
+    sa_result *results;
+    float *halo;    // per-warp scratch: 2 * halo_stride floats each
+    long long halo_stride;
+    unsigned long long *counter;  // work-queue head
+    int init_mode, start_mode, fitting;
+};
+
+struct TraceParams {
+    MapSetDev contigs, segs;
+    const sa_problem *problems;
+    const int64_t *cell_off;
+    long long n_problems;
+    const float *S;
+    const uint8_t *code;
+    const int64_t *path_off;
+    sa_result *results;
+    int32_t *path_j, *path_q;
+    float *path_s;
+};
+
+void launch_fill(const FillParams &p, bool store, bool swap, int n_ctas, cudaStream_t st);
+void launch_traceback(const TraceParams &p, cudaStream_t st);
+void launch_powf12(const float *x, long long n, float *out, int fast, cudaStream_t st);
+void launch_powf12_range(uint32_t lo, uint32_t hi, float *out_fast, float *out_generic, cudaStream_t st);
+void launch_dfma_peak(double *sink, int iters, int n_ctas, cudaStream_t st);
+int fill_ctas_per_sm();
+constexpr int FILL_MINB = 4;   // resident CTAs per SM the fill kernel is compiled for (register budget 128)
+constexpr int FILL_WARPS = 4;  // warps per CTA of the fill kernel (one problem per warp at a time)
+
+}  // namespace sa

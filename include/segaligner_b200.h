@@ -1,0 +1,128 @@
+/* segaligner_b200.h -- C ABI of the B200-native SegAligner DP engine (libsegaligner_b200.so).
+ *
+ * The reference has no in-process FFI for this path: its boundary is the SegAligner executable
+ * (/root/reference/SegAligner/main.cpp:453) that ARAlignDetect.py:283-287, OMPathFinder.py:416-420 and
+ * align_to_candidate_path.py:17-22 exec.  The drop-in is therefore the `SegAligner` executable built from
+ * ampliconreconstructorom_b200/csrc/host/, and THIS header is the thin C layer between that C++ host and the
+ * sm_100a kernels.  Each entry point below names the reference function(s) whose work it replaces, batched
+ * over many independent (contig x segment) problems.  Plain pointers and sizes only; no exceptions cross
+ * the boundary; every function returns 0 on success or a negative SA_E* code (sa_last_error() has text).
+ *
+ * Conventions (identical to the reference): a map with n labels is n+1 floats [pos_0..pos_{n-1}, length]
+ * (SAHelper.cpp:44).  b = contig map = DP rows j; x = segment map = DP columns q.  All scoring arithmetic is
+ * fp32 in the reference's operation order, powf(discrep,1.2f) is reproduced bit-for-bit (fp64 inside).
+ */
+#ifndef SEGALIGNER_B200_H
+#define SEGALIGNER_B200_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SA_OK 0
+#define SA_EINVAL -1  /* bad argument */
+#define SA_ECUDA -2   /* CUDA runtime error (text in sa_last_error) */
+#define SA_ENOMEM -3  /* device or host allocation failed */
+#define SA_ENODEV -4  /* no usable sm_100 device */
+
+/* S-matrix initialisation: init_semiglobal_aln / init_local_aln / init_fitting_aln (SegAligner.cpp:254-287) */
+enum { SA_INIT_SEMIGLOBAL = 0, SA_INIT_LOCAL = 1, SA_INIT_FITTING = 2 };
+/* traceback start: sg_aln_backtrack_start (SegAligner.cpp:172), local_backtrack_start (:142),
+ * fixed (last contig label, last segment label) as run_SA_fitting does (main.cpp:197-199) */
+enum { SA_START_SEMIGLOBAL = 0, SA_START_LOCAL = 1, SA_START_END = 2 };
+enum { SA_SIDE_CONTIG = 0, SA_SIDE_SEG = 1 };
+
+typedef struct sa_ctx sa_ctx; /* one per GPU; not thread-safe: use one host thread per context */
+
+/* Arguments of dp_align (SegAligner.cpp:95-97) that are common to a batch. */
+typedef struct sa_mode {
+    int32_t init_mode;  /* SA_INIT_* */
+    int32_t start_mode; /* SA_START_* */
+    int32_t fitting;    /* dp_align's fitting_aln flag (SegAligner.cpp:111) */
+    int32_t lookback;   /* 6 = banded kernels; anything larger = the -nl path (main.cpp:475-478) */
+    int32_t swap_b_x;   /* dp_align's swap_b_x (SegAligner.cpp:115-121); set by -detection */
+} sa_mode;
+
+/* One DP problem: indices into the uploaded map sets. used_slot selects a used-label bitmap (or -1). */
+typedef struct sa_problem {
+    int32_t contig;
+    int32_t seg;
+    int32_t used_slot;
+    int32_t reserved;
+} sa_problem;
+
+/* Backtrack start and its score (S[j][q]); j = q = -1 when no cell qualifies (as the reference returns). */
+typedef struct sa_result {
+    float score;
+    int32_t j;
+    int32_t q;
+    int32_t path_len; /* filled by sa_align_batch */
+} sa_result;
+
+int sa_device_count(void);
+int sa_ctx_create(int device, sa_ctx **out);
+void sa_ctx_destroy(sa_ctx *ctx);
+const char *sa_last_error(const sa_ctx *ctx);
+
+/* Upload one side's maps.  off[n_maps+1] indexes pos (n_i+1 floats per map); prob holds the non-collapse
+ * probabilities (non_collapse_probs, SegAligner.cpp:40-68), n_i floats per map, concatenated in map order
+ * (map m's probabilities start at off[m]-m).  Host buffers; copied before return. */
+int sa_set_maps(sa_ctx *ctx, int side, int32_t n_maps, const int64_t *off, const float *pos, const float *prob);
+
+/* Phase-1 scoring of a batch: for each problem init S, dp_align, pick the backtrack start, return its score.
+ * Replaces the body of run_SA_score's double loop (main.cpp:124-163, non-detection branch).
+ * Host buffers in, host buffers out; H2D/D2H copies are inside the call. */
+int sa_score_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, sa_result *results);
+
+/* Same work with the problem list and the results resident on the device (device pointers); launches on the
+ * context's stream and does not synchronise.  order (device, may be NULL) is the processing order. */
+int sa_score_batch_device(sa_ctx *ctx, const sa_mode *mode, const sa_problem *d_problems, const int32_t *d_order,
+                          int64_t n, sa_result *d_results);
+int sa_sync(sa_ctx *ctx);
+
+/* Alignment of a batch (one round of run_SA_aln's while loop, main.cpp:268-291, or run_SA_fitting,
+ * main.cpp:190-202): init S, dp_align honouring each problem's used contig labels, backtrack start,
+ * get_aln_list traceback (SAHelper.cpp:83-95).
+ *   used_bits / used_words_per_slot: bitmap pool; problem k with used_slot s>=0 skips contig label j when bit
+ *   j of words [s*used_words_per_slot, (s+1)*used_words_per_slot) is set (dp_align's used_labels set).
+ *   path_off[n+1]: caller-chosen offsets; problem k may write up to path_off[k+1]-path_off[k] entries
+ *   (min(nb,nx) always suffices).  path_j/path_q/path_s receive the traceback end->start, like aln_list. */
+int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n,
+                   const uint32_t *used_bits, int64_t used_words_per_slot, int64_t n_used_slots,
+                   const int64_t *path_off, sa_result *results, int32_t *path_j, int32_t *path_q, float *path_s);
+
+/* Detection-mode scoring (run_SA_score with detection=true, main.cpp:155-159): semiglobal init, dp_align,
+ * then multi_backtrack_scores (SegAligner.cpp:208-233) harvesting n_want[k] path scores per problem in the
+ * reference's order (including its skip of the single best cell).  scores_off[n+1] gives each problem's slot
+ * range in scores_out (capacity >= n_want[k]); n_got[k] receives the number actually produced. */
+int sa_detect_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const int32_t *n_want,
+                    const int64_t *scores_off, float *scores_out, int32_t *n_got);
+
+/* Full stored matrices of ONE problem (testing / debugging aid mirroring dp_align's S and previous outputs):
+ * S is nb*nx floats row-major, prev is 2 ints per cell ({-1,-1} = none). */
+int sa_fill_one(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problem, const uint32_t *used_bits,
+                int64_t used_words, float *S, int32_t *prev, sa_result *result);
+
+/* Bit-exact powf(x, 1.2f) on the device for n host floats (test hook for the score_f delta term). */
+int sa_powf12(sa_ctx *ctx, const float *x, int64_t n, float *out, int use_fast_path);
+/* Exhaustive device check: evaluates both device paths for every float bit pattern in [lo_bits, hi_bits) and
+ * counts results that differ from `expected` (host libm powf supplied by the caller), chunk by chunk. */
+int sa_powf12_range(sa_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, float *out_fast, float *out_generic);
+
+/* Last kernel timings of the most recent batch call on this context, in milliseconds (CUDA events). */
+typedef struct sa_timing {
+    float fill_ms;      /* DP fill kernel(s) */
+    float post_ms;      /* traceback / multi-backtrack kernels */
+    int32_t n_launches; /* kernels launched by the call */
+    int32_t reserved;
+} sa_timing;
+int sa_get_timing(sa_ctx *ctx, sa_timing *t);
+
+/* Microbenchmark: sustained fp64 FMA issue rate (DFMA instructions/s, whole GPU) used as roofline peak. */
+int sa_measure_fp64_peak(sa_ctx *ctx, double *dfma_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,153 @@
+"""GPU parity: the sm_100a kernels (through the C ABI) against the oracle restatement, bit-exact.
+
+Inputs are seeded; sizes are what the oracle finishes in seconds.  Covers the three initialisers, both
+score_f role assignments (swap_b_x), used-label masks, fitting mode, multi-strip contigs (nb > 32) and
+integer-valued maps where exact score ties occur (tie-breaking order of dp_align, SegAligner.cpp:109-127).
+"""
+import numpy as np
+import pytest
+
+import helpers
+from ampliconreconstructorom_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+MODES = [
+    # (init, fitting, swap, start)
+    (capi.SA_INIT_SEMIGLOBAL, 0, 0, capi.SA_START_SEMIGLOBAL),   # standard scoring / alignment
+    (capi.SA_INIT_SEMIGLOBAL, 0, 1, capi.SA_START_LOCAL),        # detection phase 1
+    (capi.SA_INIT_LOCAL, 0, 1, capi.SA_START_LOCAL),             # detection phase 3
+    (capi.SA_INIT_LOCAL, 0, 0, capi.SA_START_LOCAL),             # -local
+    (capi.SA_INIT_FITTING, 1, 0, capi.SA_START_END),             # -fitting
+]
+
+
+def build_sets(rng, oracle, n_pairs, gen, integer_every=3, max_nb=150, max_nx=70):
+    contigs, segs = {}, {}
+    for k in range(n_pairs):
+        nb = int(rng.integers(2, max_nb))
+        nx = int(rng.integers(2, max_nx))
+        b, x = helpers.related_maps(rng, nb, nx, integer=(k % integer_every == 0))
+        contigs[k + 1] = b
+        segs[k + 1] = x
+    cp = oracle.probs(contigs, gen)
+    sp = oracle.probs(segs, gen)
+    return contigs, segs, cp, sp
+
+
+def upload(ctx, maps, probs, side):
+    ids = sorted(maps)
+    off = np.zeros(len(ids) + 1, dtype=np.int64)
+    for k, i in enumerate(ids):
+        off[k + 1] = off[k] + len(maps[i])
+    pos = np.concatenate([maps[i] for i in ids]).astype(np.float32)
+    prob = np.concatenate([probs[i] for i in ids]).astype(np.float32)
+    ctx.set_maps(side, off, pos, prob)
+    return ids
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("gen", [1, 2])
+def test_fill_one_bit_exact(ctx, oracle, gen):
+    rng = np.random.default_rng(100 + gen)
+    contigs, segs, cp, sp = build_sets(rng, oracle, 24, gen)
+    cids = upload(ctx, contigs, cp, capi.SA_SIDE_CONTIG)
+    sids = upload(ctx, segs, sp, capi.SA_SIDE_SEG)
+    for k in range(len(cids)):
+        b, x = contigs[cids[k]], segs[sids[k]]
+        for (init, fit, swap, start) in MODES:
+            used = None
+            if k % 4 == 1 and not fit:
+                used = sorted(set(rng.integers(0, b.size - 1, size=4).tolist()))
+            S, prev, res = ctx.fill_one(ctx.mode(init, start, fit, 6, swap), k, k, used_rows=used)
+            So, prevo = oracle.fill(b, x, cp[cids[k]], sp[sids[k]], init, fit, 6, used, swap)
+            assert np.array_equal(bits(S), bits(So)), f"S differs: pair {k} mode {(init, fit, swap)}"
+            assert np.array_equal(prev, prevo), f"previous differs: pair {k} mode {(init, fit, swap)}"
+            st = oracle.start(So, start)
+            assert (int(res["j"]), int(res["q"])) == st
+            if st[0] >= 0:
+                assert bits(res["score"]) == bits(So[st])
+
+
+def test_score_and_align_batch(ctx, oracle):
+    rng = np.random.default_rng(7)
+    gen = 2
+    contigs, segs, cp, sp = build_sets(rng, oracle, 40, gen, max_nb=300, max_nx=120)
+    cids = upload(ctx, contigs, cp, capi.SA_SIDE_CONTIG)
+    sids = upload(ctx, segs, sp, capi.SA_SIDE_SEG)
+    # all-vs-all problem list
+    cc, ss = np.meshgrid(np.arange(len(cids)), np.arange(len(sids)), indexing="ij")
+    pr = ctx.problems(cc.ravel(), ss.ravel())
+    for (init, fit, swap, start) in MODES[:4]:
+        mode = ctx.mode(init, start, fit, 6, swap)
+        res = ctx.score_batch(mode, pr)
+        # check a seeded subset against the oracle (all of them would take minutes in pure C + Python glue)
+        pick = rng.choice(pr.size, size=120, replace=False)
+        ares, poff, pj, pq, ps = ctx.align_batch(mode, pr[pick])
+        for n, k in enumerate(pick):
+            c, s = int(pr["contig"][k]), int(pr["seg"][k])
+            So, prevo = oracle.fill(contigs[cids[c]], segs[sids[s]], cp[cids[c]], sp[sids[s]], init, fit, 6, None, swap)
+            st = oracle.start(So, start)
+            assert (int(res["j"][k]), int(res["q"][k])) == st
+            assert bits(res["score"][k]) == bits(So[st])
+            oj, oq, os_ = oracle.traceback(So, prevo, *st)
+            L = int(ares["path_len"][n])
+            assert L == oj.size
+            sl = slice(int(poff[n]), int(poff[n]) + L)
+            assert np.array_equal(pj[sl], oj) and np.array_equal(pq[sl], oq)
+            assert np.array_equal(bits(ps[sl]), bits(os_))
+            assert bits(ares["score"][n]) == bits(So[st])
+
+
+def test_used_label_masks_in_batch(ctx, oracle):
+    rng = np.random.default_rng(11)
+    contigs, segs, cp, sp = build_sets(rng, oracle, 12, 1, max_nb=120, max_nx=60)
+    cids = upload(ctx, contigs, cp, capi.SA_SIDE_CONTIG)
+    sids = upload(ctx, segs, sp, capi.SA_SIDE_SEG)
+    n = len(cids)
+    words = (max(len(contigs[c]) - 1 for c in cids) + 31) // 32
+    used_bits = np.zeros((n, words), dtype=np.uint32)
+    used_sets = []
+    for k in range(n):
+        nb = len(contigs[cids[k]]) - 1
+        u = sorted(set(rng.integers(0, nb, size=max(nb // 5, 1)).tolist()))
+        used_sets.append(u)
+        for j in u:
+            used_bits[k, j >> 5] |= np.uint32(1 << (j & 31))
+    pr = ctx.problems(np.arange(n), np.arange(n), used_slot=np.arange(n))
+    mode = ctx.mode(capi.SA_INIT_SEMIGLOBAL, capi.SA_START_SEMIGLOBAL, 0, 6, 0)
+    ares, poff, pj, pq, ps = ctx.align_batch(mode, pr, used_bits.ravel(), words)
+    for k in range(n):
+        So, prevo = oracle.fill(contigs[cids[k]], segs[sids[k]], cp[cids[k]], sp[sids[k]], 0, 0, 6, used_sets[k], 0)
+        st = oracle.start(So, 0)
+        assert (int(ares["j"][k]), int(ares["q"][k])) == st
+        oj, oq, os_ = oracle.traceback(So, prevo, *st)
+        sl = slice(int(poff[k]), int(poff[k]) + int(ares["path_len"][k]))
+        assert np.array_equal(pj[sl], oj) and np.array_equal(pq[sl], oq) and np.array_equal(bits(ps[sl]), bits(os_))
+        assert not set(pj[sl].tolist()) & set(used_sets[k]) or len(oj) == 1
+
+
+def test_powf12_device_matches_host_libm(ctx, oracle):
+    """Both device paths of powf(x,1.2f) against the host libm the reference links, on 2^22 random bit patterns
+    plus every boundary of the fast-path domain and the special values."""
+    rng = np.random.default_rng(5)
+    u = rng.integers(0, 0x7f800000, size=1 << 22, dtype=np.uint32)
+    edge = np.array([0, 1, 0x007fffff, 0x00800000, 0x35330000 - 1, 0x35330000, 0x3f330000, 0x3f800000,
+                     0x4f330000 - 1, 0x4f330000, 0x7f7fffff, 0x7f800000, 0x7fc00000], dtype=np.uint32)
+    x = np.concatenate([u, edge]).view(np.float32)
+    import ctypes as C
+    exp = np.array([oracle.lib.sao_powf12(C.c_float(float(v))) for v in x[-edge.size:]], dtype=np.float32)
+    fast = ctx.powf12(x, fast=True)
+    slow = ctx.powf12(x, fast=False)
+    nanmask = np.isnan(slow)
+    assert np.array_equal(bits(fast)[~nanmask], bits(slow)[~nanmask])
+    assert np.array_equal(np.isnan(fast), nanmask)
+    e_nan = np.isnan(exp)
+    assert np.array_equal(bits(slow[-edge.size:])[~e_nan], bits(exp)[~e_nan])
+    # bulk comparison with numpy's powf (same libm) is not guaranteed bit-equal; use the oracle on a sample
+    samp = rng.choice(u.size, size=20000, replace=False)
+    ref = np.array([oracle.lib.sao_powf12(C.c_float(float(v))) for v in x[samp]], dtype=np.float32)
+    assert np.array_equal(bits(fast[samp]), bits(ref))
