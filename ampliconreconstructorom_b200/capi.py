@@ -35,7 +35,7 @@ class Timing(C.Structure):
 # every symbol include/segaligner_b200.h declares (tests check the library exports exactly these)
 EXPORTS = [
     "sa_device_count", "sa_ctx_create", "sa_ctx_destroy", "sa_last_error", "sa_set_maps", "sa_score_batch",
-    "sa_score_batch_device", "sa_sync", "sa_align_batch", "sa_detect_batch", "sa_fill_one", "sa_powf12",
+    "sa_plan_create", "sa_plan_destroy", "sa_plan_score", "sa_plan_results", "sa_plan_info", "sa_sync", "sa_align_batch", "sa_detect_batch", "sa_fill_one", "sa_powf12",
     "sa_powf12_range", "sa_get_timing", "sa_measure_fp64_peak",
 ]
 
@@ -60,7 +60,12 @@ def load_library() -> C.CDLL:
     lib.sa_last_error.restype = C.c_char_p
     lib.sa_set_maps.argtypes = [vp, C.c_int, i32, vp, vp, vp]
     lib.sa_score_batch.argtypes = [vp, C.POINTER(Mode), vp, i64, vp]
-    lib.sa_score_batch_device.argtypes = [vp, C.POINTER(Mode), vp, vp, i64, vp]
+    lib.sa_plan_create.argtypes = [vp, vp, i64, C.POINTER(vp)]
+    lib.sa_plan_destroy.argtypes = [vp, vp]
+    lib.sa_plan_destroy.restype = None
+    lib.sa_plan_score.argtypes = [vp, vp, C.POINTER(Mode)]
+    lib.sa_plan_results.argtypes = [vp, vp, vp]
+    lib.sa_plan_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_double)]
     lib.sa_sync.argtypes = [vp]
     lib.sa_align_batch.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, i64, i64, vp, vp, vp, vp, vp]
     lib.sa_detect_batch.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, vp, vp, vp]
@@ -79,6 +84,31 @@ def _ptr(a):
 
 class SegAlignerError(RuntimeError):
     pass
+
+
+class Plan:
+    """Device-resident problem list (sa_plan)."""
+
+    def __init__(self, ctx, h, n):
+        self.ctx, self.h, self.n = ctx, h, n
+
+    def score(self, mode: Mode):
+        self.ctx._check(self.ctx.lib.sa_plan_score(self.ctx.h, self.h, C.byref(mode)), "sa_plan_score")
+
+    def results(self) -> np.ndarray:
+        res = np.zeros(self.n, dtype=result_dtype)
+        self.ctx._check(self.ctx.lib.sa_plan_results(self.ctx.h, self.h, _ptr(res)), "sa_plan_results")
+        return res
+
+    def info(self):
+        nb, nl, tc = C.c_int64(), C.c_int64(), C.c_double()
+        self.ctx.lib.sa_plan_info(self.h, C.byref(nb), C.byref(nl), C.byref(tc))
+        return {"n_bulk": nb.value, "n_large": nl.value, "total_cells": tc.value}
+
+    def destroy(self):
+        if self.h:
+            self.ctx.lib.sa_plan_destroy(self.ctx.h, self.h)
+            self.h = None
 
 
 class Context:
@@ -138,10 +168,12 @@ class Context:
                     "sa_score_batch")
         return res
 
-    def score_batch_device(self, mode: Mode, d_problems: int, d_order: int, n: int, d_results: int):
-        self._check(self.lib.sa_score_batch_device(self.h, C.byref(mode), C.c_void_p(d_problems),
-                                                   C.c_void_p(d_order) if d_order else None, n,
-                                                   C.c_void_p(d_results)), "sa_score_batch_device")
+    # staged form of score_batch: problems stay resident in HBM between plan_score calls
+    def plan_create(self, problems: np.ndarray):
+        problems = np.ascontiguousarray(problems, dtype=problem_dtype)
+        h = C.c_void_p()
+        self._check(self.lib.sa_plan_create(self.h, _ptr(problems), problems.size, C.byref(h)), "sa_plan_create")
+        return Plan(self, h, problems.size)
 
     def sync(self):
         self._check(self.lib.sa_sync(self.h), "sa_sync")

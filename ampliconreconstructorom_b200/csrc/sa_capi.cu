@@ -68,14 +68,18 @@ struct sa_ctx {
     int n_sms = 0;
     int ctas_per_sm = 1;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // cooperative (large-problem) launches run beside the bulk kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     MapSetHost sides[2];
     DevBuf d_problems, d_order, d_results, d_halo, d_counter, d_cell_off, d_S, d_code, d_used, d_path_off, d_path_j,
-        d_path_q, d_path_s, d_tmp0, d_tmp1, d_tmp2;
+        d_path_q, d_path_s, d_tmp0, d_tmp1, d_tmp2, d_halo2;
     sa_timing timing = {0, 0, 0, 0};
     size_t store_budget_cells = 0;  // max cells of stored matrices per chunk
 };
+
+struct sa_plan;
 
 namespace {
 
@@ -110,22 +114,63 @@ void build_label_ops(const float *pos, const float *prob, int n, LabelOps *out) 
     }
 }
 
-// Largest-first processing order (LPT): counting sort on a 1/8-octave log2 size class, O(n).
-void build_order(const sa_ctx *c, const sa_problem *pr, int64_t n, std::vector<int32_t> &order) {
-    order.resize((size_t)n);
+// Processing order.  Problems are split into two classes:
+//   large  -> cooperative kernel (one CTA of COOP_WARPS warps per problem), largest first;
+//   bulk   -> one warp per problem, largest first (LPT) via a counting sort on a 1/8-octave size class, O(n).
+// A problem is "large" when one warp would need longer for it than the whole batch needs on the whole GPU
+// (cells_p * n_warp_slots > alpha * total_cells), so that no single problem can become the tail.
+struct Plan {
+    std::vector<int32_t> order;  // bulk problems first, then the large ones
+    int64_t n_bulk = 0, n_large = 0;
+    double total_cells = 0;
+};
+
+void build_plan(const sa_ctx *c, const sa_problem *pr, int64_t n, int n_warp_slots, Plan &plan) {
     const int NB = 8 * 40;
     std::vector<int64_t> cnt(NB + 1, 0);
     std::vector<uint16_t> cls((size_t)n);
+    std::vector<double> cells((size_t)n);
+    double total = 0;
     for (int64_t k = 0; k < n; k++) {
-        const double cells = (double)c->sides[0].labels(pr[k].contig) * (double)c->sides[1].labels(pr[k].seg);
-        int b = cells > 1.0 ? (int)(std::log2(cells) * 8.0) : 0;
+        cells[(size_t)k] = (double)c->sides[0].labels(pr[k].contig) * (double)c->sides[1].labels(pr[k].seg);
+        total += cells[(size_t)k];
+    }
+    double alpha = 0.5;
+    if (const char *e = getenv("SA_COOP_ALPHA")) alpha = atof(e);
+    const double thresh = alpha * total / (double)n_warp_slots;
+    std::vector<std::pair<double, int32_t>> large;
+    for (int64_t k = 0; k < n; k++) {
+        const double cl = cells[(size_t)k];
+        if (alpha > 0 && cl > thresh && cl >= 32.0 * 64.0) {
+            large.emplace_back(-cl, (int32_t)k);
+            cls[(size_t)k] = 0xffff;
+            continue;
+        }
+        int b = cl > 1.0 ? (int)(std::log2(cl) * 8.0) : 0;
         if (b >= NB) b = NB - 1;
-        cls[(size_t)k] = (uint16_t)(NB - 1 - b);  // descending
+        cls[(size_t)k] = (uint16_t)(NB - 1 - b);  // descending size
         cnt[NB - 1 - b + 1]++;
     }
     for (int b = 0; b < NB; b++) cnt[b + 1] += cnt[b];
-    for (int64_t k = 0; k < n; k++) order[(size_t)cnt[cls[(size_t)k]]++] = (int32_t)k;
+    plan.n_large = (int64_t)large.size();
+    plan.n_bulk = n - plan.n_large;
+    plan.total_cells = total;
+    plan.order.resize((size_t)n);
+    for (int64_t k = 0; k < n; k++)
+        if (cls[(size_t)k] != 0xffff) plan.order[(size_t)cnt[cls[(size_t)k]]++] = (int32_t)k;
+    std::sort(large.begin(), large.end());
+    for (size_t k = 0; k < large.size(); k++) plan.order[(size_t)plan.n_bulk + k] = large[k].second;
 }
+
+}  // namespace
+
+struct sa_plan {
+    int64_t n = 0;
+    Plan plan;
+    DevBuf d_problems, d_order, d_results;
+};
+
+namespace {
 
 int check_problems(sa_ctx *ctx, const sa_problem *pr, int64_t n, int64_t n_used_slots) {
     const int nc = ctx->sides[0].n_maps, ns = ctx->sides[1].n_maps;
@@ -153,10 +198,44 @@ int prepare_fill(sa_ctx *ctx, FillParams &P, const sa_mode *mode) {
     P.fitting = mode->fitting;
     const long long n_warps = (long long)n_fill_ctas(ctx) * FILL_WARPS;
     P.halo_stride = (long long)std::max(ctx->sides[1].max_labels, 1) * 8;
-    CU(ctx->d_halo.reserve(sizeof(float) * (size_t)(n_warps * 2 * P.halo_stride)));
-    P.halo = ctx->d_halo.as<float>();
-    CU(ctx->d_counter.reserve(sizeof(unsigned long long)));
-    P.counter = ctx->d_counter.as<unsigned long long>();
+    CU(ctx->d_halo.reserve(sizeof(float) * (size_t)(n_warps * P.halo_stride)));
+    CU(ctx->d_halo2.reserve(sizeof(float) * (size_t)((long long)ctx->n_sms * P.halo_stride)));
+    CU(ctx->d_counter.reserve(2 * sizeof(unsigned long long)));
+    return SA_OK;
+}
+
+// Launch the fill over an uploaded problem list whose device order array holds n_bulk bulk problems followed
+// by n_large large ones.  The two kernels run concurrently (stream / stream2) and join on `stream`.
+int launch_fill_classes(sa_ctx *ctx, FillParams P, const int32_t *d_order, int64_t n_bulk, int64_t n_large,
+                        bool store, bool swap) {
+    unsigned long long *counters = ctx->d_counter.as<unsigned long long>();
+    CU(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    int launches = 0;
+    if (n_large > 0) {
+        CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        FillParams L = P;
+        L.order = d_order + n_bulk;
+        L.n_problems = n_large;
+        L.counter = counters + 1;
+        L.halo = ctx->d_halo2.as<float>();
+        launch_fill(L, store, swap, true, (int)std::min<int64_t>(n_large, ctx->n_sms), ctx->stream2);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
+        launches++;
+    }
+    if (n_bulk > 0) {
+        P.order = d_order;
+        P.n_problems = n_bulk;
+        P.counter = counters;
+        P.halo = ctx->d_halo.as<float>();
+        const int64_t want = (n_bulk + FILL_WARPS - 1) / FILL_WARPS;
+        launch_fill(P, store, swap, false, (int)std::min<int64_t>(want, n_fill_ctas(ctx)), ctx->stream);
+        CU(cudaGetLastError());
+        launches++;
+    }
+    if (n_large > 0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    ctx->timing.n_launches += launches;
     return SA_OK;
 }
 
@@ -190,7 +269,10 @@ int sa_ctx_create(int device, sa_ctx **out) {
         delete ctx;
         return SA_ECUDA;
     }
+    cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     ctx->ctas_per_sm = fill_ctas_per_sm();
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
@@ -213,10 +295,13 @@ void sa_ctx_destroy(sa_ctx *ctx) {
     }
     DevBuf *bufs[] = {&ctx->d_problems, &ctx->d_order,  &ctx->d_results,  &ctx->d_halo,   &ctx->d_counter, &ctx->d_cell_off,
                       &ctx->d_S,        &ctx->d_code,   &ctx->d_used,     &ctx->d_path_off, &ctx->d_path_j,  &ctx->d_path_q,
-                      &ctx->d_path_s,   &ctx->d_tmp0,   &ctx->d_tmp1,     &ctx->d_tmp2};
+                      &ctx->d_path_s,   &ctx->d_tmp0,   &ctx->d_tmp1,     &ctx->d_tmp2,     &ctx->d_halo2};
     for (auto b : bufs) b->release();
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -261,26 +346,77 @@ int sa_set_maps(sa_ctx *ctx, int side, int32_t n_maps, const int64_t *off, const
     return SA_OK;
 }
 
-int sa_score_batch_device(sa_ctx *ctx, const sa_mode *mode, const sa_problem *d_problems, const int32_t *d_order,
-                          int64_t n, sa_result *d_results) {
-    if (!ctx) return SA_EINVAL;
-    if (n <= 0) return SA_OK;
+int sa_plan_create(sa_ctx *ctx, const sa_problem *problems, int64_t n, sa_plan **out) {
+    if (!ctx || !out) return SA_EINVAL;
+    *out = nullptr;
+    if (n <= 0 || !problems) return fail(ctx, SA_EINVAL, "empty problem list");
+    CU(cudaSetDevice(ctx->device));
+    int rc = check_problems(ctx, problems, n, 0);
+    if (rc) return rc;
+    sa_plan *pl = new sa_plan();
+    pl->n = n;
+    build_plan(ctx, problems, n, n_fill_ctas(ctx) * FILL_WARPS, pl->plan);
+    cudaError_t e = pl->d_problems.reserve(sizeof(sa_problem) * (size_t)n);
+    if (e == cudaSuccess) e = pl->d_order.reserve(sizeof(int32_t) * (size_t)n);
+    if (e == cudaSuccess) e = pl->d_results.reserve(sizeof(sa_result) * (size_t)n);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(pl->d_problems.p, problems, sizeof(sa_problem) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(pl->d_order.p, pl->plan.order.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        pl->d_problems.release();
+        pl->d_order.release();
+        pl->d_results.release();
+        delete pl;
+        return fail(ctx, e == cudaErrorMemoryAllocation ? SA_ENOMEM : SA_ECUDA, std::string("sa_plan_create: ") + cudaGetErrorString(e));
+    }
+    *out = pl;
+    return SA_OK;
+}
+
+void sa_plan_destroy(sa_ctx *ctx, sa_plan *pl) {
+    if (!pl) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    pl->d_problems.release();
+    pl->d_order.release();
+    pl->d_results.release();
+    delete pl;
+}
+
+int sa_plan_score(sa_ctx *ctx, sa_plan *pl, const sa_mode *mode) {
+    if (!ctx || !pl) return SA_EINVAL;
     CU(cudaSetDevice(ctx->device));
     FillParams P;
     int rc = prepare_fill(ctx, P, mode);
     if (rc) return rc;
-    P.problems = d_problems;
-    P.order = d_order;
-    P.n_problems = n;
-    P.results = d_results;
-    CU(cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), ctx->stream));
+    P.problems = pl->d_problems.as<sa_problem>();
+    P.results = pl->d_results.as<sa_result>();
+    ctx->timing = {-1.0f, 0, 0, 0};  // fill_ms resolved lazily by sa_get_timing
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    launch_fill(P, false, mode->swap_b_x != 0, n_fill_ctas(ctx), ctx->stream);
-    CU(cudaGetLastError());
+    rc = launch_fill_classes(ctx, P, pl->d_order.as<int32_t>(), pl->plan.n_bulk, pl->plan.n_large, false,
+                             mode->swap_b_x != 0);
+    if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-    ctx->timing.n_launches = 1;
-    ctx->timing.post_ms = 0;
-    ctx->timing.fill_ms = -1.0f;  // resolved lazily by sa_get_timing
+    return SA_OK;
+}
+
+int sa_plan_results(sa_ctx *ctx, sa_plan *pl, sa_result *results) {
+    if (!ctx || !pl || !results) return SA_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(results, pl->d_results.p, sizeof(sa_result) * (size_t)pl->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SA_OK;
+}
+
+int sa_plan_info(const sa_plan *pl, int64_t *n_bulk, int64_t *n_large, double *total_cells) {
+    if (!pl) return SA_EINVAL;
+    if (n_bulk) *n_bulk = pl->plan.n_bulk;
+    if (n_large) *n_large = pl->plan.n_large;
+    if (total_cells) *total_cells = pl->plan.total_cells;
     return SA_OK;
 }
 
@@ -288,22 +424,13 @@ int sa_score_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
     if (!ctx) return SA_EINVAL;
     if (n <= 0) return SA_OK;
     if (!problems || !results) return fail(ctx, SA_EINVAL, "NULL buffer");
-    CU(cudaSetDevice(ctx->device));
-    int rc = check_problems(ctx, problems, n, 0);
+    sa_plan *pl = nullptr;
+    int rc = sa_plan_create(ctx, problems, n, &pl);
     if (rc) return rc;
-    std::vector<int32_t> order;
-    build_order(ctx, problems, n, order);
-    CU(ctx->d_problems.reserve(sizeof(sa_problem) * (size_t)n));
-    CU(ctx->d_order.reserve(sizeof(int32_t) * (size_t)n));
-    CU(ctx->d_results.reserve(sizeof(sa_result) * (size_t)n));
-    CU(cudaMemcpyAsync(ctx->d_problems.p, problems, sizeof(sa_problem) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_order.p, order.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    rc = sa_score_batch_device(ctx, mode, ctx->d_problems.as<sa_problem>(), ctx->d_order.as<int32_t>(), n,
-                               ctx->d_results.as<sa_result>());
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(results, ctx->d_results.p, sizeof(sa_result) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    return SA_OK;
+    rc = sa_plan_score(ctx, pl, mode);
+    if (rc == SA_OK) rc = sa_plan_results(ctx, pl, results);
+    sa_plan_destroy(ctx, pl);
+    return rc;
 }
 
 int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const uint32_t *used_bits,
@@ -340,8 +467,9 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
             k1++;
         }
         const int64_t m = k1 - k0;
-        std::vector<int32_t> order;
-        build_order(ctx, problems + k0, m, order);
+        Plan plan;
+        build_plan(ctx, problems + k0, m, n_fill_ctas(ctx) * FILL_WARPS, plan);
+        const std::vector<int32_t> &order = plan.order;
         std::vector<int64_t> poff((size_t)m + 1);
         for (int64_t k = 0; k <= m; k++) poff[(size_t)k] = path_off[k0 + k] - path_off[k0];
         const int64_t n_path = poff[(size_t)m];
@@ -366,10 +494,9 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
         P.results = ctx->d_results.as<sa_result>();
         P.S = ctx->d_S.as<float>();
         P.code = ctx->d_code.as<uint8_t>();
-        CU(cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), ctx->stream));
         CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-        launch_fill(P, true, mode->swap_b_x != 0, n_fill_ctas(ctx), ctx->stream);
-        CU(cudaGetLastError());
+        rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan.n_bulk, plan.n_large, true, mode->swap_b_x != 0);
+        if (rc) return rc;
         CU(cudaEventRecord(ctx->ev[1], ctx->stream));
         TraceParams T;
         memset(&T, 0, sizeof(T));
@@ -400,7 +527,7 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
         cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
         ctx->timing.fill_ms += a;
         ctx->timing.post_ms += b;
-        ctx->timing.n_launches += 2;
+        ctx->timing.n_launches += 1;
         k0 = k1;
     }
     return SA_OK;

@@ -56,18 +56,55 @@ __device__ __forceinline__ void lds_u32x2(uint32_t addr, uint32_t &lo, uint32_t 
     asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
 }
 
+// Shared-memory layout of the two powf tables, split so that every lookup is bank-conflict free:
+//   invc[16], logc[16]  : 8-byte entries, 128 B each -> entry i owns banks 2i,2i+1 (a half-warp wavefront never
+//                         sees two different addresses in one bank; equal indices broadcast)
+//   exp_lo[32], exp_hi[32]: 4-byte halves of the exp2 table, 128 B each -> entry e owns bank e
+struct __align__(128) PowTabSmem {
+    double invc[16];
+    double logc[16];
+    uint32_t exp_lo[32];
+    uint32_t exp_hi[32];
+};
+static_assert(sizeof(PowTabSmem) == 512, "PowTabSmem layout");
+
+__device__ __forceinline__ void powtab_init(PowTabSmem &t) {
+    if (threadIdx.x < 16) {
+        t.invc[threadIdx.x] = c_logtab[threadIdx.x].invc;
+        t.logc[threadIdx.x] = c_logtab[threadIdx.x].logc;
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 64) {
+        const unsigned long long v = c_exptab[threadIdx.x - 32];
+        t.exp_lo[threadIdx.x - 32] = (uint32_t)v;
+        t.exp_hi[threadIdx.x - 32] = (uint32_t)(v >> 32);
+    }
+}
+
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 // Branch-free replay of powf(ax, 1.2f) for ax inside the fast domain; outside it the result is garbage but the
 // code is still memory-safe (both table indices are masked), so callers evaluate unconditionally and patch the
-// rare out-of-domain lanes afterwards (`bad` tells which).  slog/sexp are 32-bit shared-memory addresses.
-__device__ __forceinline__ float powf12_fast(float ax, uint32_t slog, uint32_t sexp, bool &bad) {
+// rare out-of-domain lanes afterwards (`bad` tells which).  stab = 32-bit shared address of a PowTabSmem
+// (512-byte aligned, so `stab | offset` == `stab + offset`).
+__device__ __forceinline__ float powf12_fast(float ax, uint32_t stab, uint32_t &u_out) {
     const uint32_t ix = __float_as_uint(ax);
     const uint32_t u = ix - IX_LO;
-    bad = u >= IX_RANGE;
+    u_out = u;  // u >= IX_RANGE  <=>  outside the fast domain
     const uint32_t kb = u & 0xff800000u;
     const uint32_t iz = ix - kb + (20u << 23);
     const int k = (int)(u >> 23) - 20;
-    double invc, logc;
-    lds_f64x2(slog + ((u >> 15) & 0xF0u), invc, logc);
+    const uint32_t a_i = stab | ((u >> 16) & 0x78u);  // 8 * ((u >> 19) & 15)
+    const double invc = lds_f64(a_i);
+    const double logc = lds_f64(a_i + 128);
     // log2: 9 fp64 ops, then y*log2(x)
     const double y0 = __dadd_rn(logc, (double)k);
     const double z = (double)__uint_as_float(iz);
@@ -85,9 +122,9 @@ __device__ __forceinline__ float powf12_fast(float ax, uint32_t slog, uint32_t s
     const uint32_t ki = (uint32_t)__double2loint(kd);
     kd = __dadd_rn(kd, c_pk[10]);
     const double rr = __dadd_rn(xd, -kd);
-    uint32_t tlo, thi;
-    lds_u32x2(sexp + ((ki << 3) & 0xF8u), tlo, thi);
-    thi += ki << 15;  // t += ki << 47
+    const uint32_t a_e = stab | (256u + ((ki << 2) & 0x7Cu));
+    const uint32_t tlo = lds_u32(a_e);
+    const uint32_t thi = lds_u32(a_e + 128) + (ki << 15);  // t += ki << 47
     const double sc = __hiloint2double((int)thi, (int)tlo);
     const double zz = __fma_rn(rr, c_pk[6], c_pk[7]);
     const double rr2 = __dmul_rn(rr, rr);
@@ -100,34 +137,50 @@ __device__ __forceinline__ float powf12_fast(float ax, uint32_t slog, uint32_t s
 constexpr int RING_W = 40;  // 6 halo rows + 32 lanes + 2 pad
 #define NEG_INF (-CUDART_INF_F)
 
-// GROUP = number of predecessor candidates evaluated branch-free between two slow-path checks (ILP knob).
-template <bool STORE, bool SWAP, int MINB>
-__global__ void __launch_bounds__(FILL_WARPS * 32, MINB) fill_kernel(const FillParams P) {
-    __shared__ double2 s_log[16];
-    __shared__ unsigned long long s_exp[32];
-    __shared__ float s_ring[FILL_WARPS][LB][RING_W];
+// NW = warps that cooperate on one problem.
+//   NW == 1 : every warp of the CTA pulls its own problem (bulk of the work: thousands of small problems).
+//   NW  > 1 : the whole CTA (NW warps) sweeps ONE large problem as a wavefront: warp w owns row strips
+//             w, w+NW, ... and runs one column behind warp w-1 (strip s at column q needs the bottom rows of
+//             strip s-1 at columns < q).  One __syncthreads per step; bottom rows travel through a
+//             double-buffered shared exchange (warp w-1 -> w) and, for the wrap-around NW-1 -> 0, through the
+//             L2-resident halo scratch.  A round takes R = max(nx, NW) steps so the wrap-around is never early.
+template <bool STORE, bool SWAP, int NW, int MINB>
+__global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_kernel(const FillParams P) {
+    constexpr int WPC = (NW == 1) ? FILL_WARPS : NW;  // warps per CTA
+    __shared__ PowTabSmem s_tab;
+    __shared__ float s_ring[WPC][LB][RING_W];
+    __shared__ float s_xbuf[WPC][2][8];
+    __shared__ unsigned long long s_next;
+    __shared__ float s_red_s[WPC];
+    __shared__ int s_red_j[WPC], s_red_q[WPC];
+    __shared__ long long s_red_o[WPC];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    if (threadIdx.x < 16) s_log[threadIdx.x] = make_double2(c_logtab[threadIdx.x].invc, c_logtab[threadIdx.x].logc);
-    if (threadIdx.x >= 32 && threadIdx.x < 64) s_exp[threadIdx.x - 32] = c_exptab[threadIdx.x - 32];
+    powtab_init(s_tab);
     __syncthreads();
-    const uint32_t a_log = (uint32_t)__cvta_generic_to_shared(s_log);
-    const uint32_t a_exp = (uint32_t)__cvta_generic_to_shared(s_exp);
+    const uint32_t a_tab = (uint32_t)__cvta_generic_to_shared(&s_tab);
     // byte address of this lane's own entry in ring slot 0
     const uint32_t a_my = (uint32_t)__cvta_generic_to_shared(&s_ring[warp][0][6 + lane]);
     const uint32_t a_halo = (uint32_t)__cvta_generic_to_shared(&s_ring[warp][0][lane]);  // lanes 0..5 only
 
-    const long long gwarp = (long long)blockIdx.x * FILL_WARPS + warp;
-    float *halo0 = P.halo + gwarp * 2 * P.halo_stride;
-    float *halo1 = halo0 + P.halo_stride;
+    const long long gunit = (NW == 1) ? ((long long)blockIdx.x * FILL_WARPS + warp) : (long long)blockIdx.x;
+    float *halo = P.halo + gunit * P.halo_stride;
+    const int w = (NW == 1) ? 0 : warp;  // position in the wavefront
 
     for (;;) {
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(P.counter, 1ull);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= (unsigned long long)P.n_problems) break;
-        const long long pidx = P.order ? P.order[t] : (long long)t;
+        unsigned long long t_idx = 0;
+        if (NW == 1) {
+            if (lane == 0) t_idx = atomicAdd(P.counter, 1ull);
+            t_idx = __shfl_sync(0xffffffffu, t_idx, 0);
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) s_next = atomicAdd(P.counter, 1ull);
+            __syncthreads();
+            t_idx = s_next;
+        }
+        if (t_idx >= (unsigned long long)P.n_problems) break;
+        const long long pidx = P.order ? P.order[t_idx] : (long long)t_idx;
         const sa_problem pr = P.problems[pidx];
         const int64_t boff = P.contigs.pos_off[pr.contig];
         const int nb = (int)(P.contigs.pos_off[pr.contig + 1] - boff) - 1;
@@ -150,34 +203,51 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, MINB) fill_kernel(const FillP
         long long st_ord = 0x7fffffffffffffffll;
 
         const int nstrips = (nb + 31) >> 5;
-        for (int strip = 0; strip < nstrips; strip++) {
-            const int j = (strip << 5) + lane;
-            const bool row_ok = j < nb;
-            const int jc = row_ok ? j : nb - 1;
-            float db[LB], fb[LB];
-            {
-                const float4 *src = reinterpret_cast<const float4 *>(bops + jc);
-                const float4 a = __ldg(src), b4 = __ldg(src + 1), c4 = __ldg(src + 2);
-                db[0] = a.x, db[1] = a.y, db[2] = a.z, db[3] = a.w, db[4] = b4.x, db[5] = b4.y;
-                fb[0] = b4.z, fb[1] = b4.w, fb[2] = c4.x, fb[3] = c4.y, fb[4] = c4.z, fb[5] = c4.w;
-            }
-            const bool row_used = used ? ((used[jc >> 5] >> (jc & 31)) & 1u) : false;
-            __syncwarp();
-#pragma unroll
-            for (int s = 0; s < LB; s++) {
-                sts_f32(a_my + s * RING_W * 4, NEG_INF);
-                if (lane < 6) sts_f32(a_halo + s * RING_W * 4, NEG_INF);
-            }
-            __syncwarp();
-            const float *halo_rd = (strip & 1) ? halo0 : halo1;  // written by the previous strip
-            float *halo_wr = (strip & 1) ? halo1 : halo0;
-            // shared addresses of this lane's entry in the ring slots holding columns q-1..q-6 (pc[0] -> q-1)
-            uint32_t pc[LB];
-#pragma unroll
-            for (int d = 0; d < LB; d++) pc[d] = a_my + ((LB - 1 - d) % LB) * RING_W * 4;
-            int slot = 0;
+        const int R = (NW == 1) ? nx : (nx > NW ? nx : NW);  // steps per round
+        const int rounds = (nstrips + NW - 1) / NW;
+        const long long T = (long long)rounds * R + (NW - 1);
 
-            for (int q = 0; q < nx; q++) {
+        // per-warp sweep state
+        int strip = w;
+        int q = 0;  // column within the current round (>= nx: idle tail of a short round)
+        int j = 0, jc = 0;
+        bool row_ok = false, row_used = false;
+        float db[LB], fb[LB];
+        uint32_t pc[LB];
+        int slot = 0;
+#pragma unroll
+        for (int d = 0; d < LB; d++) {
+            db[d] = 0.0f;
+            fb[d] = 0.0f;
+            pc[d] = a_my;
+        }
+
+        for (long long t = 0; t < T; t++) {
+            const bool active = (t >= w) && (strip < nstrips) && (q < nx);
+            float val = 0.0f, rv = 0.0f, hv = NEG_INF;
+            int code = 0;
+            if (active) {
+                if (q == 0) {  // strip set-up: row operands into registers, ring to -inf
+                    j = (strip << 5) + lane;
+                    row_ok = j < nb;
+                    jc = row_ok ? j : nb - 1;
+                    const float4 *src = reinterpret_cast<const float4 *>(bops + jc);
+                    const float4 a = __ldg(src), b4 = __ldg(src + 1), c4 = __ldg(src + 2);
+                    db[0] = a.x, db[1] = a.y, db[2] = a.z, db[3] = a.w, db[4] = b4.x, db[5] = b4.y;
+                    fb[0] = b4.z, fb[1] = b4.w, fb[2] = c4.x, fb[3] = c4.y, fb[4] = c4.z, fb[5] = c4.w;
+                    row_used = used ? ((used[jc >> 5] >> (jc & 31)) & 1u) : false;
+                    __syncwarp();
+#pragma unroll
+                    for (int s = 0; s < LB; s++) {
+                        sts_f32(a_my + s * RING_W * 4, NEG_INF);
+                        if (lane < 6) sts_f32(a_halo + s * RING_W * 4, NEG_INF);
+                    }
+                    __syncwarp();
+                    // shared addresses of this lane's entry in the slots holding columns q-1..q-6 (pc[0] -> q-1)
+#pragma unroll
+                    for (int d = 0; d < LB; d++) pc[d] = a_my + ((LB - 1 - d) % LB) * RING_W * 4;
+                    slot = 0;
+                }
                 float dx[LB], fx[LB];
                 {
                     const float4 *src = reinterpret_cast<const float4 *>(xops + q);
@@ -188,8 +258,11 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, MINB) fill_kernel(const FillP
                         fx[0] = b4.z, fx[1] = b4.w, fx[2] = c4.x, fx[3] = c4.y, fx[4] = c4.z, fx[5] = c4.w;
                     }
                 }
-                float hv = NEG_INF;
-                if (strip > 0 && lane < 6) hv = __ldcg(halo_rd + (long long)q * 8 + lane);
+                // rows above the strip at column q (bottom rows of strip-1)
+                if (strip > 0 && lane < 6) {
+                    if (NW == 1 || w == 0) hv = __ldcg(halo + (long long)q * 8 + lane);
+                    else hv = s_xbuf[w - 1][(t - 1) & 1][lane];
+                }
 
                 float init;
                 if (P.init_mode == SA_INIT_SEMIGLOBAL) init = (j == 0 || q < 2) ? 0.0f : NEG_INF;
@@ -197,20 +270,18 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, MINB) fill_kernel(const FillP
                 else init = (j == 0 || q == 0) ? 0.0f : NEG_INF;
 
                 float best = NEG_INF;
-                int code = 0;
 #pragma unroll
                 for (int dj = 1; dj <= LB; dj++) {
                     float delta[LB], discrep[LB], sc[LB];
-                    bool anybad = false;
+                    uint32_t u[LB];
 #pragma unroll
                     for (int dq = 1; dq <= LB; dq++) {
-                        bool bad;
                         sc[dq - 1] = lds_f32(pc[dq - 1] - dj * 4);
                         discrep[dq - 1] = fabsf(__fsub_rn(db[dj - 1], dx[dq - 1]));
-                        delta[dq - 1] = powf12_fast(discrep[dq - 1], a_log, a_exp, bad);
-                        anybad |= bad;
+                        delta[dq - 1] = powf12_fast(discrep[dq - 1], a_tab, u[dq - 1]);
                     }
-                    if (anybad) {  // rare: discrepancy exactly 0, subnormal-tiny, huge, inf or NaN
+                    const uint32_t umax = __vimax3_u32(__vimax3_u32(u[0], u[1], u[2]), __vimax3_u32(u[3], u[4], u[5]), 0u);
+                    if (umax >= IX_RANGE) {  // rare: discrepancy exactly 0, subnormal-tiny, huge, inf or NaN
 #pragma unroll
                         for (int dq = 1; dq <= LB; dq++)
                             if (__float_as_uint(discrep[dq - 1]) - IX_LO >= IX_RANGE)
@@ -234,19 +305,25 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, MINB) fill_kernel(const FillP
                         }
                     }
                 }
-                float val = init;
+                val = init;
                 if (best > init && !row_used) val = best;
                 else code = 0;
-
-                // publish column q: own row, and the 6 rows above the strip
-                float rv = val;
+                rv = val;
                 if (P.fitting && j == 0 && q > 0) rv = NEG_INF;  // dp_align's `i_ind == 0 && p_ind > 0` break (:111)
-                __syncwarp();
+            }
+            __syncwarp();
+            if (active) {
+                // publish column q: own row, the 6 rows above the strip, and our bottom rows for the strip below
                 sts_f32(a_my + slot * RING_W * 4, rv);
                 if (lane < 6) sts_f32(a_halo + slot * RING_W * 4, hv);
-                if (lane >= 26) __stcg(halo_wr + (long long)q * 8 + (lane - 26), rv);
-                __syncwarp();
-
+                if (lane >= 26) {
+                    if (NW == 1 || w == NW - 1) __stcg(halo + (long long)q * 8 + (lane - 26), rv);
+                    else s_xbuf[w][t & 1][lane - 26] = rv;
+                }
+            }
+            if (NW == 1) __syncwarp();
+            else __syncthreads();
+            if (active) {
                 if (row_ok) {
                     if (STORE) {
                         Sout[(long long)j * nx + q] = val;
@@ -279,9 +356,16 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, MINB) fill_kernel(const FillP
                 pc[0] = a_my + slot * RING_W * 4;
                 slot = (slot == LB - 1) ? 0 : slot + 1;
             }
+            if (t >= w && strip < nstrips) {  // advance within the round (idle steps of a short round included)
+                q++;
+                if (q == R) {
+                    q = 0;
+                    strip += NW;
+                }
+            }
         }
 
-        // reduce the start over lanes: max score, ties -> smallest scan order
+        // reduce the start over lanes (and warps): max score, ties -> smallest scan order
         if (P.start_mode == SA_START_LOCAL) st_ord = (st_j < 0) ? 0x7fffffffffffffffll : (long long)st_j * nx + st_q;
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) {
@@ -297,7 +381,28 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, MINB) fill_kernel(const FillP
                 st_ord = oo;
             }
         }
-        if (lane == 0) {
+        if (NW > 1) {
+            if (lane == 0) {
+                s_red_s[warp] = st_s;
+                s_red_j[warp] = st_j;
+                s_red_q[warp] = st_q;
+                s_red_o[warp] = st_ord;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int k = 1; k < NW; k++) {
+                    const bool take = (s_red_j[k] >= 0) &&
+                                      (st_j < 0 || s_red_s[k] > st_s || (s_red_s[k] == st_s && s_red_o[k] < st_ord));
+                    if (take) {
+                        st_s = s_red_s[k];
+                        st_j = s_red_j[k];
+                        st_q = s_red_q[k];
+                        st_ord = s_red_o[k];
+                    }
+                }
+            }
+        }
+        if ((NW == 1 && lane == 0) || (NW > 1 && threadIdx.x == 0)) {
             sa_result res;
             if (P.start_mode == SA_START_END) {
                 res.j = nb - 1;
@@ -346,33 +451,31 @@ __global__ void trace_kernel(const TraceParams P) {
 }
 
 __global__ void powf12_kernel(const float *x, long long n, float *out, int fast) {
-    __shared__ double2 s_log[16];
-    __shared__ unsigned long long s_exp[32];
-    if (threadIdx.x < 16) s_log[threadIdx.x] = make_double2(c_logtab[threadIdx.x].invc, c_logtab[threadIdx.x].logc);
-    if (threadIdx.x >= 32 && threadIdx.x < 64) s_exp[threadIdx.x - 32] = c_exptab[threadIdx.x - 32];
+    __shared__ PowTabSmem s_tab;
+    powtab_init(s_tab);
     __syncthreads();
+    const uint32_t a_tab = (uint32_t)__cvta_generic_to_shared(&s_tab);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float ax = fabsf(x[i]);
-        bool bad;
-        const float f = powf12_fast(ax, (uint32_t)__cvta_generic_to_shared(s_log), (uint32_t)__cvta_generic_to_shared(s_exp), bad);
-        out[i] = (fast && !bad) ? f : powf12_slow(ax);
+        uint32_t u;
+        const float f = powf12_fast(ax, a_tab, u);
+        out[i] = (fast && u < IX_RANGE) ? f : powf12_slow(ax);
     }
 }
 
 __global__ void powf12_range_kernel(uint32_t lo, uint32_t hi, float *out_fast, float *out_generic) {
-    __shared__ double2 s_log[16];
-    __shared__ unsigned long long s_exp[32];
-    if (threadIdx.x < 16) s_log[threadIdx.x] = make_double2(c_logtab[threadIdx.x].invc, c_logtab[threadIdx.x].logc);
-    if (threadIdx.x >= 32 && threadIdx.x < 64) s_exp[threadIdx.x - 32] = c_exptab[threadIdx.x - 32];
+    __shared__ PowTabSmem s_tab;
+    powtab_init(s_tab);
     __syncthreads();
+    const uint32_t a_tab = (uint32_t)__cvta_generic_to_shared(&s_tab);
     const unsigned long long n = (unsigned long long)hi - lo;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const float ax = __uint_as_float(lo + (uint32_t)i);
-        bool bad;
-        const float f = powf12_fast(ax, (uint32_t)__cvta_generic_to_shared(s_log), (uint32_t)__cvta_generic_to_shared(s_exp), bad);
+        uint32_t u;
+        const float f = powf12_fast(ax, a_tab, u);
         const float g = powf12_slow(ax);
-        out_fast[i] = bad ? g : f;
+        out_fast[i] = (u >= IX_RANGE) ? g : f;
         out_generic[i] = g;
     }
 }
@@ -398,15 +501,20 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *sink, int iters)
     if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
 }
 
-void launch_fill(const FillParams &p, bool store, bool swap, int n_ctas, cudaStream_t st) {
-    dim3 g(n_ctas), b(FILL_WARPS * 32);
+template <int NW, int MINB>
+static void launch_fill_t(const FillParams &p, bool store, bool swap, int n_ctas, cudaStream_t st) {
+    dim3 g(n_ctas), b((NW == 1 ? FILL_WARPS : NW) * 32);
     if (store) {
-        if (swap) fill_kernel<true, true, FILL_MINB><<<g, b, 0, st>>>(p);
-        else fill_kernel<true, false, FILL_MINB><<<g, b, 0, st>>>(p);
+        if (swap) fill_kernel<true, true, NW, MINB><<<g, b, 0, st>>>(p);
+        else fill_kernel<true, false, NW, MINB><<<g, b, 0, st>>>(p);
     } else {
-        if (swap) fill_kernel<false, true, FILL_MINB><<<g, b, 0, st>>>(p);
-        else fill_kernel<false, false, FILL_MINB><<<g, b, 0, st>>>(p);
+        if (swap) fill_kernel<false, true, NW, MINB><<<g, b, 0, st>>>(p);
+        else fill_kernel<false, false, NW, MINB><<<g, b, 0, st>>>(p);
     }
+}
+void launch_fill(const FillParams &p, bool store, bool swap, bool coop, int n_ctas, cudaStream_t st) {
+    if (coop) launch_fill_t<COOP_WARPS, 1>(p, store, swap, n_ctas, st);
+    else launch_fill_t<1, FILL_MINB>(p, store, swap, n_ctas, st);
 }
 
 void launch_traceback(const TraceParams &p, cudaStream_t st) {
@@ -426,7 +534,7 @@ void launch_dfma_peak(double *sink, int iters, int n_ctas, cudaStream_t st) {
 }
 int fill_ctas_per_sm() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<false, false, FILL_MINB>, FILL_WARPS * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<false, false, 1, FILL_MINB>, FILL_WARPS * 32, 0);
     return n > 0 ? n : 1;
 }
 

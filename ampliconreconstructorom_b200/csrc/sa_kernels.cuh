@@ -39,7 +39,7 @@ struct FillParams {
     float *S;       // stored score matrices
     uint8_t *code;  // stored predecessor codes: 0 = none, else 1 + (dj-1)*6 + (dq-1)
     sa_result *results;
-    float *halo;    // per-warp scratch: 2 * halo_stride floats each
+    float *halo;    // per work-unit (warp, or CTA in the cooperative variant) scratch: halo_stride floats each
     long long halo_stride;
     unsigned long long *counter;  // work-queue head
     int init_mode, start_mode, fitting;
@@ -58,13 +58,14 @@ struct TraceParams {
     float *path_s;
 };
 
-void launch_fill(const FillParams &p, bool store, bool swap, int n_ctas, cudaStream_t st);
+void launch_fill(const FillParams &p, bool store, bool swap, bool coop, int n_ctas, cudaStream_t st);
 void launch_traceback(const TraceParams &p, cudaStream_t st);
 void launch_powf12(const float *x, long long n, float *out, int fast, cudaStream_t st);
 void launch_powf12_range(uint32_t lo, uint32_t hi, float *out_fast, float *out_generic, cudaStream_t st);
 void launch_dfma_peak(double *sink, int iters, int n_ctas, cudaStream_t st);
 int fill_ctas_per_sm();
 constexpr int FILL_MINB = 4;   // resident CTAs per SM the fill kernel is compiled for (register budget 128)
+constexpr int COOP_WARPS = 16;  // warps of the cooperative (one problem per CTA) variant used for large problems
 constexpr int FILL_WARPS = 4;  // warps per CTA of the fill kernel (one problem per warp at a time)
 
 }  // namespace sa

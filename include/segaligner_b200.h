@@ -75,10 +75,18 @@ int sa_set_maps(sa_ctx *ctx, int side, int32_t n_maps, const int64_t *off, const
  * Host buffers in, host buffers out; H2D/D2H copies are inside the call. */
 int sa_score_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, sa_result *results);
 
-/* Same work with the problem list and the results resident on the device (device pointers); launches on the
- * context's stream and does not synchronise.  order (device, may be NULL) is the processing order. */
-int sa_score_batch_device(sa_ctx *ctx, const sa_mode *mode, const sa_problem *d_problems, const int32_t *d_order,
-                          int64_t n, sa_result *d_results);
+/* The same work split into its stages, so that a caller (or a benchmark) can keep inputs resident in HBM:
+ *   sa_plan_create   validates + uploads a problem list and its processing order (H2D; synchronises).  Large
+ *                    problems are routed to the cooperative kernel, the rest largest-first to per-warp workers.
+ *   sa_plan_score    launches the scoring kernels on the context's stream; no host<->device traffic; async.
+ *   sa_plan_results  copies the sa_result array back (D2H; synchronises).
+ * sa_score_batch == create + score + results + destroy. */
+typedef struct sa_plan sa_plan;
+int sa_plan_create(sa_ctx *ctx, const sa_problem *problems, int64_t n, sa_plan **out);
+void sa_plan_destroy(sa_ctx *ctx, sa_plan *plan);
+int sa_plan_score(sa_ctx *ctx, sa_plan *plan, const sa_mode *mode);
+int sa_plan_results(sa_ctx *ctx, sa_plan *plan, sa_result *results);
+int sa_plan_info(const sa_plan *plan, int64_t *n_bulk, int64_t *n_large, double *total_cells);
 int sa_sync(sa_ctx *ctx);
 
 /* Alignment of a batch (one round of run_SA_aln's while loop, main.cpp:268-291, or run_SA_fitting,

@@ -46,6 +46,14 @@ def upload(ctx, maps, probs, side):
     return ids
 
 
+@pytest.fixture(params=["bulk", "coop"], autouse=True)
+def kernel_class(request, monkeypatch):
+    """Run every parity case twice: through the one-warp-per-problem kernel and through the cooperative
+    16-warp wavefront kernel (forced by an absurdly low 'large problem' threshold)."""
+    monkeypatch.setenv("SA_COOP_ALPHA", "0" if request.param == "bulk" else "1e-9")
+    return request.param
+
+
 def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
@@ -127,7 +135,8 @@ def test_used_label_masks_in_batch(ctx, oracle):
         oj, oq, os_ = oracle.traceback(So, prevo, *st)
         sl = slice(int(poff[k]), int(poff[k]) + int(ares["path_len"][k]))
         assert np.array_equal(pj[sl], oj) and np.array_equal(pq[sl], oq) and np.array_equal(bits(ps[sl]), bits(os_))
-        assert not set(pj[sl].tolist()) & set(used_sets[k]) or len(oj) == 1
+        # a used row keeps its initial value but may still START a path (dp_align only skips it as a target)
+        assert not set(pj[sl][:-1].tolist()) & set(used_sets[k])
 
 
 def test_powf12_device_matches_host_libm(ctx, oracle):
