@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "lib" / "libsegaligner_b200.so"
+LIB_PATH = Path(os.environ.get("SA_LIB_PATH", PKG_DIR / "lib" / "libsegaligner_b200.so"))  # override: dev experiments only
 BIN_PATH = PKG_DIR / "bin" / "SegAligner"
 
 SA_INIT_SEMIGLOBAL, SA_INIT_LOCAL, SA_INIT_FITTING = 0, 1, 2

@@ -1,0 +1,546 @@
+// SegAligner -- B200-native drop-in for /root/reference/SegAligner (main.cpp:453-656).
+//
+// Same positional arguments, same flags (parse_args, main.cpp:363-435), same output files, same stdout
+// progress lines; the three phase drivers run_SA_score / run_SA_aln / run_SA_fitting (main.cpp:112-358) are
+// re-designed around batched GPU calls through the C ABI of include/segaligner_b200.h:
+//   phase 1  every (segment+-, contig) problem of the run in ONE sa_score_batch / sa_detect_batch per GPU;
+//   phase 3/4 the reference's per-pair `while` loop (main.cpp:268) becomes rounds: round r aligns every pair
+//            that is still live in one sa_align_batch, then the host applies thresholds and filters.
+// -nthreads is accepted; it only fixes the ROW ORDER of *_all_scores.txt (the reference concatenates its
+// per-thread result vectors, main.cpp:547-551), which we reproduce.  Extra flag: -ngpus=N (default: all
+// visible GPUs for big runs, 1 otherwise; unknown flags are ignored by the reference's parser, so callers
+// written for the reference are unaffected).  There is no CPU fallback.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <map>
+#include <set>
+#include <string>
+#include <thread>
+#include <vector>
+#include "cmap.h"
+#include "segaligner_b200.h"
+
+using namespace sah;
+
+namespace {
+
+// ---- globals of the reference (main.cpp:19-37) -------------------------------------------------------------
+struct Options {
+    bool local_aln = false, detection = false, fitting_aln = false, swap_b_x = false;
+    int n_detect_scores = 500, n_threads = 1, min_map_len = 10, lookback = 6, inst_gen = 2;
+    int max_seg_contig_alns = 6;
+    float p_val = 0.0001f, p_val_tip = 0.000001f, p_val_RG = 0.000000001f;
+    std::string sample_prefix = "SA_output", detection_label, contig_list_file;
+    bool limit_lookback = true, do_tip = true;
+    int n_gpus = 0;  // 0 = auto
+};
+
+bool starts_with(const std::string &s, const char *p) { return s.rfind(p, 0) == 0; }
+std::string after_eq(const std::string &s) { return s.substr(s.find('=') + 1); }
+
+int ref_stoi_arg(const std::string &v) {
+    char *e = nullptr;
+    long r = strtol(v.c_str(), &e, 10);
+    if (e == v.c_str()) {
+        fprintf(stderr, "terminate called after throwing an instance of 'std::invalid_argument'\n  what():  stoi\n");
+        abort();
+    }
+    return (int)r;
+}
+
+void parse_args(int argc, char **argv, Options &o) {
+    for (int i = 3; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (a == "-nl") o.limit_lookback = false;
+        else if (a == "-no_tip_aln") o.do_tip = false;
+        else if (a == "-detection") {
+            o.local_aln = o.detection = o.swap_b_x = true;
+            o.do_tip = false;
+            o.detection_label = "_detection";
+            o.p_val = o.p_val_RG;
+            printf("detection mode ON, local ON, swap_b_x ON\n");
+            fflush(stdout);
+        } else if (starts_with(a, "-prefix=")) o.sample_prefix = after_eq(a);
+        else if (starts_with(a, "-contig_list=")) o.contig_list_file = after_eq(a);
+        else if (a == "-local") {
+            o.local_aln = true;
+            printf("Local alignment mode\n");
+            fflush(stdout);
+        } else if (a == "-fitting") {
+            o.fitting_aln = true;
+            printf("Fitting alignment mode. Multithreading will be off.\n\n");
+            fflush(stdout);
+        } else if (starts_with(a, "-nthreads=")) o.n_threads = ref_stoi_arg(after_eq(a));
+        else if (starts_with(a, "-min_labs=")) o.min_map_len = ref_stoi_arg(after_eq(a));
+        else if (starts_with(a, "-n_detect_scores=")) o.n_detect_scores = ref_stoi_arg(after_eq(a));
+        else if (starts_with(a, "-gen=")) {
+            o.inst_gen = ref_stoi_arg(after_eq(a));
+            if (o.inst_gen != 1 && o.inst_gen != 2) {
+                printf("1 or 2 are the only valid arguments for -gen");
+                exit(1);
+            }
+        } else if (starts_with(a, "-ngpus=")) o.n_gpus = ref_stoi_arg(after_eq(a));
+    }
+}
+
+// ---- multi-GPU engine: one context + one host thread per device, problems dealt largest-first ----------------
+struct Engine {
+    std::vector<sa_ctx *> ctx;
+    const MapSet *contigs = nullptr, *segs = nullptr;
+
+    void die(sa_ctx *c, const char *what, int rc) {
+        fprintf(stderr, "SegAligner(b200): %s failed (%d): %s\n", what, rc, c ? sa_last_error(c) : "");
+        exit(2);
+    }
+    void open(int n) {
+        const int avail = sa_device_count();
+        if (avail <= 0) {
+            fprintf(stderr, "SegAligner(b200): no CUDA device visible; this build has no CPU fallback\n");
+            exit(2);
+        }
+        n = std::max(1, std::min(n, avail));
+        ctx.assign((size_t)n, nullptr);
+        std::vector<std::thread> th;
+        std::vector<int> rcs((size_t)n, 0);
+        for (int g = 0; g < n; g++) th.emplace_back([&, g]() { rcs[(size_t)g] = sa_ctx_create(g, &ctx[(size_t)g]); });
+        for (auto &t : th) t.join();
+        for (int g = 0; g < n; g++)
+            if (rcs[(size_t)g]) die(nullptr, "sa_ctx_create (need an sm_100 GPU)", rcs[(size_t)g]);
+    }
+    void close() {
+        for (auto c : ctx) sa_ctx_destroy(c);
+        ctx.clear();
+    }
+    void set_maps(const MapSet &c, const MapSet &s) {
+        contigs = &c;
+        segs = &s;
+        parallel([&](int g) {
+            int rc = sa_set_maps(ctx[(size_t)g], SA_SIDE_CONTIG, c.n_maps(), c.off.data(), c.pos.data(), c.prob.data());
+            if (rc) die(ctx[(size_t)g], "sa_set_maps(contigs)", rc);
+            rc = sa_set_maps(ctx[(size_t)g], SA_SIDE_SEG, s.n_maps(), s.off.data(), s.pos.data(), s.prob.data());
+            if (rc) die(ctx[(size_t)g], "sa_set_maps(segments)", rc);
+        });
+    }
+    template <class F>
+    void parallel(F f) {
+        if (ctx.size() == 1) {
+            f(0);
+            return;
+        }
+        std::vector<std::thread> th;
+        for (int g = 0; g < (int)ctx.size(); g++) th.emplace_back([&, g]() { f(g); });
+        for (auto &t : th) t.join();
+    }
+    // shard[g] = indices of the problems GPU g handles: sorted by cells descending, dealt round-robin
+    std::vector<std::vector<int64_t>> shard(const std::vector<sa_problem> &pr) const {
+        const int G = (int)ctx.size();
+        std::vector<std::vector<int64_t>> sh((size_t)G);
+        if (G == 1) {
+            sh[0].resize(pr.size());
+            for (size_t k = 0; k < pr.size(); k++) sh[0][k] = (int64_t)k;
+            return sh;
+        }
+        std::vector<std::pair<int64_t, int64_t>> key(pr.size());
+        for (size_t k = 0; k < pr.size(); k++)
+            key[k] = {-(int64_t)contigs->labels(pr[k].contig) * segs->labels(pr[k].seg), (int64_t)k};
+        std::sort(key.begin(), key.end());
+        for (size_t r = 0; r < key.size(); r++) sh[r % (size_t)G].push_back(key[r].second);
+        return sh;
+    }
+
+    void score(const sa_mode &mode, const std::vector<sa_problem> &pr, std::vector<sa_result> &res) {
+        res.assign(pr.size(), sa_result{0, -1, -1, 0});
+        if (pr.empty()) return;
+        auto sh = shard(pr);
+        parallel([&](int g) {
+            const auto &idx = sh[(size_t)g];
+            if (idx.empty()) return;
+            std::vector<sa_problem> p(idx.size());
+            std::vector<sa_result> r(idx.size());
+            for (size_t k = 0; k < idx.size(); k++) p[k] = pr[(size_t)idx[k]];
+            int rc = sa_score_batch(ctx[(size_t)g], &mode, p.data(), (int64_t)p.size(), r.data());
+            if (rc) die(ctx[(size_t)g], "sa_score_batch", rc);
+            for (size_t k = 0; k < idx.size(); k++) res[(size_t)idx[k]] = r[k];
+        });
+    }
+
+    // detection scoring: out[k] = the scores multi_backtrack_scores harvests for problem k, in order
+    void detect(const sa_mode &mode, const std::vector<sa_problem> &pr, const std::vector<int32_t> &n_want,
+                std::vector<std::vector<float>> &out) {
+        out.assign(pr.size(), {});
+        if (pr.empty()) return;
+        auto sh = shard(pr);
+        parallel([&](int g) {
+            const auto &idx = sh[(size_t)g];
+            if (idx.empty()) return;
+            const size_t m = idx.size();
+            std::vector<sa_problem> p(m);
+            std::vector<int32_t> want(m), got(m);
+            std::vector<int64_t> off(m + 1, 0);
+            for (size_t k = 0; k < m; k++) {
+                p[k] = pr[(size_t)idx[k]];
+                want[k] = n_want[(size_t)idx[k]];
+                off[k + 1] = off[k] + want[k];
+            }
+            std::vector<float> sc((size_t)std::max<int64_t>(off[m], 1));
+            int rc = sa_detect_batch(ctx[(size_t)g], &mode, p.data(), (int64_t)m, want.data(), off.data(), sc.data(), got.data());
+            if (rc) die(ctx[(size_t)g], "sa_detect_batch", rc);
+            for (size_t k = 0; k < m; k++) out[(size_t)idx[k]].assign(sc.begin() + off[k], sc.begin() + off[k] + got[k]);
+        });
+    }
+
+    // alignment: paths[k] = traceback of problem k, end->start.  used[k] = bitmap of contig labels to skip.
+    void align(const sa_mode &mode, const std::vector<sa_problem> &pr_in, const std::vector<const std::vector<uint32_t> *> &used,
+               std::vector<sa_result> &res, std::vector<std::vector<AlnEntry>> &paths) {
+        res.assign(pr_in.size(), sa_result{0, -1, -1, 0});
+        paths.assign(pr_in.size(), {});
+        if (pr_in.empty()) return;
+        auto sh = shard(pr_in);
+        parallel([&](int g) {
+            const auto &idx = sh[(size_t)g];
+            if (idx.empty()) return;
+            const size_t m = idx.size();
+            std::vector<sa_problem> p(m);
+            int64_t words = 1;
+            for (size_t k = 0; k < m; k++) {
+                p[k] = pr_in[(size_t)idx[k]];
+                words = std::max<int64_t>(words, (contigs->labels(p[k].contig) + 31) / 32);
+            }
+            std::vector<uint32_t> pool;
+            bool any_used = false;
+            for (size_t k = 0; k < m; k++) any_used |= (used[(size_t)idx[k]] != nullptr);
+            if (any_used) pool.assign((size_t)words * m, 0u);
+            std::vector<int64_t> poff(m + 1, 0);
+            for (size_t k = 0; k < m; k++) {
+                p[k].used_slot = -1;
+                if (any_used && used[(size_t)idx[k]]) {
+                    const auto &u = *used[(size_t)idx[k]];
+                    std::copy(u.begin(), u.begin() + (long)std::min<size_t>(u.size(), (size_t)words), pool.begin() + (size_t)words * k);
+                    p[k].used_slot = (int32_t)k;
+                }
+                poff[k + 1] = poff[k] + std::min(contigs->labels(p[k].contig), segs->labels(p[k].seg));
+            }
+            const size_t tot = (size_t)std::max<int64_t>(poff[m], 1);
+            std::vector<int32_t> pj(tot), pq(tot);
+            std::vector<float> ps(tot);
+            std::vector<sa_result> r(m);
+            int rc = sa_align_batch(ctx[(size_t)g], &mode, p.data(), (int64_t)m, any_used ? pool.data() : nullptr, words,
+                                    any_used ? (int64_t)m : 0, poff.data(), r.data(), pj.data(), pq.data(), ps.data());
+            if (rc) die(ctx[(size_t)g], "sa_align_batch", rc);
+            for (size_t k = 0; k < m; k++) {
+                res[(size_t)idx[k]] = r[k];
+                auto &pa = paths[(size_t)idx[k]];
+                pa.resize((size_t)r[k].path_len);
+                for (int t = 0; t < r[k].path_len; t++)
+                    pa[(size_t)t] = AlnEntry{pj[(size_t)poff[k] + t], pq[(size_t)poff[k] + t], ps[(size_t)poff[k] + t]};
+            }
+        });
+    }
+};
+
+using Bitmap = std::vector<uint32_t>;
+inline size_t bm_words(int labels) { return (size_t)std::max((labels + 31) / 32, 1); }
+inline void bm_set(Bitmap &b, int j) { b[(size_t)j >> 5] |= 1u << (j & 31); }
+inline bool bm_any(const Bitmap &b) {
+    for (uint32_t w : b)
+        if (w) return true;
+    return false;
+}
+
+// One pass of run_SA_aln (main.cpp:213-358) over a set of (segment, contig) pairs, as batched rounds.
+// used_seed: per contig the labels already taken (tip phase), else nullptr.  Returns per contig the labels
+// of the alignments that were WRITTEN (discovered_contig_used_labels).
+std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapSet &segs, const MapSet &contigs,
+                                       const std::vector<std::pair<int, int>> &pairs /* (seg idx, contig idx) */,
+                                       const std::vector<std::pair<int, float>> &thresholds /* by seg idx */,
+                                       const std::vector<Bitmap> *used_seed, bool tip_aln) {
+    const int min_aln_labels = 6;
+    const int min_tip_aln_labels = (o.inst_gen == 1) ? 3 : 5;
+    std::vector<Bitmap> discovered((size_t)contigs.n_maps());
+    for (int c = 0; c < contigs.n_maps(); c++) discovered[(size_t)c].assign(bm_words(contigs.labels(c)), 0u);
+    const float med_thresh = tip_aln ? 8750.0f : 8000.0f;
+    const float mean_thresh = tip_aln ? 8750.0f : 7000.0f;
+    int max_alns = o.max_seg_contig_alns;
+    if (tip_aln && o.inst_gen == 2) max_alns = 6;
+
+    struct PairState {
+        int s, c;
+        float thr, curr_best, exp_thresh;
+        int count;
+        Bitmap used;
+        bool live;
+    };
+    std::vector<PairState> st(pairs.size());
+    for (size_t k = 0; k < pairs.size(); k++) {
+        PairState &p = st[k];
+        p.s = pairs[k].first;
+        p.c = pairs[k].second;
+        p.thr = thresholds[(size_t)p.s].second;
+        p.curr_best = p.thr;
+        p.exp_thresh = p.thr;
+        p.count = 0;
+        if (used_seed) p.used = (*used_seed)[(size_t)p.c];
+        else p.used.assign(bm_words(contigs.labels(p.c)), 0u);
+        p.live = true;
+    }
+    sa_mode mode;
+    mode.init_mode = o.local_aln ? SA_INIT_LOCAL : SA_INIT_SEMIGLOBAL;
+    mode.start_mode = o.local_aln ? SA_START_LOCAL : SA_START_SEMIGLOBAL;
+    mode.fitting = 0;
+    mode.lookback = o.lookback;
+    mode.swap_b_x = o.swap_b_x ? 1 : 0;
+
+    for (;;) {
+        std::vector<size_t> live;
+        for (size_t k = 0; k < st.size(); k++) {
+            PairState &p = st[k];
+            if (p.live && p.curr_best >= p.exp_thresh && p.count < max_alns) live.push_back(k);  // main.cpp:268
+            else p.live = false;
+        }
+        if (live.empty()) break;
+        std::vector<sa_problem> pr(live.size());
+        std::vector<const Bitmap *> used(live.size());
+        for (size_t n = 0; n < live.size(); n++) {
+            const PairState &p = st[live[n]];
+            pr[n] = sa_problem{p.c, p.s, -1, 0};
+            used[n] = bm_any(p.used) ? &p.used : nullptr;
+        }
+        std::vector<sa_result> res;
+        std::vector<std::vector<AlnEntry>> paths;
+        eng.align(mode, pr, used, res, paths);
+        for (size_t n = 0; n < live.size(); n++) {
+            PairState &p = st[live[n]];
+            const std::vector<AlnEntry> &aln = paths[n];
+            if (aln.empty()) {  // no backtrack start (cannot happen with >= 1 label each); treat as exhausted
+                p.live = false;
+                continue;
+            }
+            float by_lab, by_len;
+            partial_score_threshold(p.thr, aln, contigs.map(p.c), contigs.size(p.c), by_lab, by_len);
+            p.exp_thresh = fmaxf(by_lab, by_len);  // main.cpp:290
+            p.curr_best = res[n].score;
+            if (!(p.curr_best > p.exp_thresh)) {
+                // equality would spin forever in the reference (same DP, same result); we stop instead
+                if (p.curr_best == p.exp_thresh) p.live = false;
+                continue;
+            }
+            p.count += 1;
+            for (auto &e : aln) bm_set(p.used, e.j);  // main.cpp:298-300
+            if (tip_aln) {                             // must touch a contig end (main.cpp:303-308)
+                const size_t last_lab_gap = (size_t)(contigs.size(p.c) - 2) - (size_t)aln[0].j;
+                if (last_lab_gap > 3 && aln.back().j > 2) continue;
+            }
+            if ((int)aln.size() < min_tip_aln_labels || (!tip_aln && (int)aln.size() < min_aln_labels)) continue;
+            const float mean = aln[0].s / (float)(aln.size() - 1);
+            const float median = aln_median(aln);
+            if (aln.size() < 5) {
+                const float min_score = aln_min(aln);
+                if (mean < 9400 || median < 9400 || min_score < 9200) continue;
+            } else if (mean < mean_thresh || median < med_thresh) {
+                continue;
+            }
+            const int x = segs.ids[(size_t)p.s];
+            const int contig_id = contigs.ids[(size_t)p.c];
+            std::string seg_id = std::to_string(x < 0 ? -x : x);
+            if (x < 0) seg_id += "_r";
+            const std::string outname = o.sample_prefix + "_" + std::to_string(contig_id) + "_" + seg_id + "_" +
+                                        std::to_string(p.count) + (tip_aln ? "_tip" : "") + "_aln.txt";
+            print_alignment(outname, aln, contig_id, x, segs.size(p.s), p.curr_best);
+            for (auto &e : aln) bm_set(discovered[(size_t)p.c], e.j);  // SAHelper.cpp:115
+        }
+    }
+    return discovered;
+}
+
+double wall_now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+int main(int argc, char *argv[]) {
+    if (argc < 3) {  // the reference tests argc < 2 and then dereferences argv[2] regardless (main.cpp:454-468)
+        printf("wrong number of arguments\n");
+        fflush(stdout);
+        exit(1);
+    }
+    const clock_t begin = clock();
+    const double w0 = wall_now();
+    const std::string ref_cmap_file = argv[1];
+    const std::string contig_cmap_file = argv[2];
+    Options o;
+    parse_args(argc, argv, o);
+    if (!o.limit_lookback) {
+        o.lookback = 9999999;
+        printf("Alignment banding OFF. \n");
+    }
+    if (o.inst_gen == 2) o.max_seg_contig_alns *= 2;  // main.cpp:479-481
+
+    MapSet segs_raw, segs, contigs;
+    parse_cmap(ref_cmap_file, segs_raw);
+    if (!o.fitting_aln) segs = make_reverse_cmap(segs_raw, o.min_map_len);
+    else segs = segs_raw;
+    parse_cmap(contig_cmap_file, contigs);
+    non_collapse_probs(segs, o.inst_gen);
+    non_collapse_probs(contigs, o.inst_gen);
+
+    // contig set (get_contig_set, main.cpp:437-447)
+    std::set<int> contig_set;
+    if (!o.contig_list_file.empty()) {
+        for (int id : parse_contig_list(o.contig_list_file)) contig_set.insert(id);
+    } else {
+        for (int id : contigs.ids) contig_set.insert(id);
+    }
+    printf("Running SegAligner on %d segments and %d contigs.\n", segs.n_maps(), contigs.n_maps());
+    fflush(stdout);
+    if (o.lookback != 6) {
+        fprintf(stderr, "SegAligner(b200): -nl (unbanded look-back) is not available in this build yet\n");
+        return 3;
+    }
+    if (segs.n_maps() == 0 || contigs.n_maps() == 0) {
+        // nothing to align; the reference still writes the (empty) score files unless -fitting
+        if (!o.fitting_aln) {
+            write_all_scores({}, o.sample_prefix);
+            write_score_thresholds({}, o.sample_prefix + o.detection_label);
+        }
+        return 0;
+    }
+
+    // GPUs: all visible ones for big runs, one otherwise (context creation costs more than a small run)
+    double total_cells = 0;
+    {
+        double sl = 0, cl = 0;
+        for (int m = 0; m < segs.n_maps(); m++) sl += segs.labels(m);
+        for (int m = 0; m < contigs.n_maps(); m++) cl += contigs.labels(m);
+        total_cells = sl * cl;
+    }
+    int n_gpus = o.n_gpus;
+    if (const char *e = getenv("SA_NGPUS"))
+        if (n_gpus <= 0) n_gpus = atoi(e);
+    if (n_gpus <= 0) n_gpus = total_cells > 2e10 ? sa_device_count() : 1;
+    Engine eng;
+    eng.open(n_gpus);
+    eng.set_maps(contigs, segs);
+
+    // ---------------- fitting mode (main.cpp:512-526, run_SA_fitting :169-208) --------------------------------
+    if (o.fitting_aln) {
+        std::vector<sa_problem> pr;
+        for (int id : contig_set) {
+            const int c = contigs.index_of(id);
+            for (int s = 0; s < segs.n_maps(); s++) {
+                if (c < 0) continue;  // the reference would create an empty map here and crash; skip
+                pr.push_back(sa_problem{c, s, -1, 0});
+            }
+        }
+        sa_mode mode{SA_INIT_FITTING, SA_START_END, 1, o.lookback, o.swap_b_x ? 1 : 0};
+        std::vector<const Bitmap *> used(pr.size(), nullptr);
+        std::vector<sa_result> res;
+        std::vector<std::vector<AlnEntry>> paths;
+        eng.align(mode, pr, used, res, paths);
+        for (size_t k = 0; k < pr.size(); k++) {
+            const int x = segs.ids[(size_t)pr[k].seg];
+            const int contig_id = contigs.ids[(size_t)pr[k].contig];
+            const std::string outname = o.sample_prefix + "_" + std::to_string(contig_id) + "_" +
+                                        std::to_string(x < 0 ? -x : x) + "_fitting_aln.txt";
+            print_alignment(outname, paths[k], contig_id, x, segs.size(pr[k].seg), res[k].score);
+        }
+        printf("elapsed seconds for run %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
+        eng.close();
+        return 0;
+    }
+
+    // ---------------- phase 1: scoring (main.cpp:528-553, run_SA_score :112-167) ------------------------------
+    printf("Computing scoring thresholds.\n");
+    fflush(stdout);
+    const int nt = std::max(o.n_threads, 1);
+    std::vector<std::vector<int>> chunk((size_t)nt);  // contig indices per reference thread, ascending
+    {
+        int count = 0;
+        for (int id : contig_set) {
+            const int c = contigs.index_of(id);
+            if (c >= 0) chunk[(size_t)(count % nt)].push_back(c);
+            count++;
+        }
+    }
+    // problems in the reference's row order: thread, then segment, then contig
+    std::vector<sa_problem> pr;
+    for (int t = 0; t < nt; t++)
+        for (int s = 0; s < segs.n_maps(); s++)
+            for (int c : chunk[(size_t)t]) pr.push_back(sa_problem{c, s, -1, 0});
+    std::vector<ScoreRow> rows;
+    {
+        sa_mode mode;
+        mode.init_mode = SA_INIT_SEMIGLOBAL;  // "handles both cases" (main.cpp:141)
+        mode.start_mode = o.local_aln ? SA_START_LOCAL : SA_START_SEMIGLOBAL;  // tip_aln is false here (:146-152)
+        mode.fitting = 0;
+        mode.lookback = o.lookback;
+        mode.swap_b_x = o.swap_b_x ? 1 : 0;
+        if (o.detection) {
+            int total_labels = 0;
+            for (int c = 0; c < contigs.n_maps(); c++) total_labels += contigs.size(c);  // main.cpp:118-121
+            std::vector<int32_t> want(pr.size());
+            for (size_t k = 0; k < pr.size(); k++)
+                want[k] = int(roundf(o.n_detect_scores * float(contigs.size(pr[k].contig)) / float(total_labels))) + 1;
+            std::vector<std::vector<float>> sc;
+            eng.detect(mode, pr, want, sc);
+            for (size_t k = 0; k < pr.size(); k++)
+                for (float v : sc[k]) rows.push_back(ScoreRow{segs.ids[(size_t)pr[k].seg], contigs.ids[(size_t)pr[k].contig], v});
+        } else {
+            std::vector<sa_result> res;
+            eng.score(mode, pr, res);
+            rows.reserve(pr.size());
+            for (size_t k = 0; k < pr.size(); k++)
+                rows.push_back(ScoreRow{segs.ids[(size_t)pr[k].seg], contigs.ids[(size_t)pr[k].contig], res[k].score});
+        }
+    }
+    write_all_scores(rows, o.sample_prefix);
+
+    // ---------------- phase 2: thresholds (main.cpp:555-557) ---------------------------------------------------
+    auto score_thresholds = compute_score_thresholds(rows, segs, contigs, (double)o.p_val, o.n_detect_scores);
+    auto tip_thresholds = compute_score_thresholds(rows, segs, contigs, (double)o.p_val_tip, o.n_detect_scores);
+    printf("Writing scoring distribution.\n");
+    write_score_thresholds(score_thresholds, o.sample_prefix + o.detection_label);
+    printf("Completed generating scores.\n");
+    printf("elapsed seconds for scoring %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
+    fflush(stdout);
+
+    // ---------------- phase 3: alignment of the pairs that pass (main.cpp:563-604) ----------------------------
+    std::vector<std::pair<int, int>> pairs_list;  // (seg idx, contig idx), in row order, duplicates kept
+    for (auto &r : rows) {
+        const int s = segs.index_of(r.seg);
+        if (r.score >= score_thresholds[(size_t)s].second) pairs_list.emplace_back(s, contigs.index_of(r.contig));
+    }
+    std::vector<std::pair<int, int>> uniq = pairs_list;
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    printf("Performing alignments\n");
+    fflush(stdout);
+    std::vector<Bitmap> contig_used = run_alignment_pass(eng, o, segs, contigs, uniq, score_thresholds, nullptr, false);
+    printf("Finished standard alignment. \n");
+    fflush(stdout);
+
+    // ---------------- phase 4: tip alignment (main.cpp:606-649) ------------------------------------------------
+    if (o.do_tip) {
+        printf("Doing tip alignment.\n");
+        std::set<int> tip_contigs;
+        for (auto &e : pairs_list)
+            if (bm_any(contig_used[(size_t)e.second])) tip_contigs.insert(e.second);
+        std::vector<std::pair<int, int>> tip_pairs;
+        for (int s = 0; s < segs.n_maps(); s++)
+            for (int c : tip_contigs) tip_pairs.emplace_back(s, c);  // every segment (+ and -) x every such contig
+        printf("Performing alignments\n");
+        fflush(stdout);
+        run_alignment_pass(eng, o, segs, contigs, tip_pairs, tip_thresholds, &contig_used, true);
+        printf("Finished tip alignments.\n\n");
+    }
+    printf("elapsed seconds for run %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
+    if (getenv("SA_VERBOSE")) fprintf(stderr, "SegAligner(b200): wall %.3f s on %d GPU(s)\n", wall_now() - w0, (int)eng.ctx.size());
+    fflush(stdout);
+    eng.close();
+    return 0;
+}

@@ -74,7 +74,7 @@ struct sa_ctx {
     std::string err;
     MapSetHost sides[2];
     DevBuf d_problems, d_order, d_results, d_halo, d_counter, d_cell_off, d_S, d_code, d_used, d_path_off, d_path_j,
-        d_path_q, d_path_s, d_tmp0, d_tmp1, d_tmp2, d_halo2;
+        d_path_q, d_path_s, d_tmp0, d_tmp1, d_tmp2, d_halo2, d_row_off, d_rowmax_s, d_rowmax_q;
     sa_timing timing = {0, 0, 0, 0};
     size_t store_budget_cells = 0;  // max cells of stored matrices per chunk
 };
@@ -196,6 +196,7 @@ int prepare_fill(sa_ctx *ctx, FillParams &P, const sa_mode *mode) {
     P.init_mode = mode->init_mode;
     P.start_mode = mode->start_mode;
     P.fitting = mode->fitting;
+    fill_powf_constants(P.pk);
     const long long n_warps = (long long)n_fill_ctas(ctx) * FILL_WARPS;
     P.halo_stride = (long long)std::max(ctx->sides[1].max_labels, 1) * 8;
     CU(ctx->d_halo.reserve(sizeof(float) * (size_t)(n_warps * P.halo_stride)));
@@ -295,7 +296,8 @@ void sa_ctx_destroy(sa_ctx *ctx) {
     }
     DevBuf *bufs[] = {&ctx->d_problems, &ctx->d_order,  &ctx->d_results,  &ctx->d_halo,   &ctx->d_counter, &ctx->d_cell_off,
                       &ctx->d_S,        &ctx->d_code,   &ctx->d_used,     &ctx->d_path_off, &ctx->d_path_j,  &ctx->d_path_q,
-                      &ctx->d_path_s,   &ctx->d_tmp0,   &ctx->d_tmp1,     &ctx->d_tmp2,     &ctx->d_halo2};
+                      &ctx->d_path_s,   &ctx->d_tmp0,   &ctx->d_tmp1,     &ctx->d_tmp2,     &ctx->d_halo2,  &ctx->d_row_off, &ctx->d_rowmax_s,
+                      &ctx->d_rowmax_q};
     for (auto b : bufs) b->release();
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -570,9 +572,106 @@ int sa_fill_one(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problem, con
     return SA_OK;
 }
 
-int sa_detect_batch(sa_ctx *ctx, const sa_mode *, const sa_problem *, int64_t, const int32_t *, const int64_t *, float *,
-                    int32_t *) {
-    return fail(ctx, SA_EINVAL, "sa_detect_batch: not implemented yet");
+int sa_detect_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const int32_t *n_want,
+                    const int64_t *scores_off, float *scores_out, int32_t *n_got) {
+    if (!ctx) return SA_EINVAL;
+    if (n <= 0) return SA_OK;
+    if (!problems || !n_want || !scores_off || !scores_out || !n_got) return fail(ctx, SA_EINVAL, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    int rc = check_problems(ctx, problems, n, 0);
+    if (rc) return rc;
+    for (int64_t k = 0; k < n; k++)
+        if (n_want[k] < 0 || scores_off[k + 1] - scores_off[k] < n_want[k])
+            return fail(ctx, SA_EINVAL, "scores_off leaves less room than n_want");
+    FillParams P;
+    rc = prepare_fill(ctx, P, mode);
+    if (rc) return rc;
+    ctx->timing = {0, 0, 0, 0};
+    int64_t k0 = 0;
+    std::vector<int64_t> cell_off, row_off, soff;
+    while (k0 < n) {
+        cell_off.clear();
+        row_off.clear();
+        int64_t cells = 0, rows = 0, k1 = k0;
+        while (k1 < n) {
+            const int64_t nb = ctx->sides[0].labels(problems[k1].contig);
+            const int64_t c = nb * ctx->sides[1].labels(problems[k1].seg);
+            if (k1 > k0 && (size_t)(cells + c) > ctx->store_budget_cells) break;
+            cell_off.push_back(cells);
+            row_off.push_back(rows);
+            cells += c;
+            rows += nb;
+            k1++;
+        }
+        const int64_t m = k1 - k0;
+        Plan plan;
+        build_plan(ctx, problems + k0, m, n_fill_ctas(ctx) * FILL_WARPS, plan);
+        soff.resize((size_t)m + 1);
+        for (int64_t k = 0; k <= m; k++) soff[(size_t)k] = scores_off[k0 + k] - scores_off[k0];
+        const int64_t n_sc = std::max<int64_t>(soff[(size_t)m], 1);
+        CU(ctx->d_problems.reserve(sizeof(sa_problem) * (size_t)m));
+        CU(ctx->d_order.reserve(sizeof(int32_t) * (size_t)m));
+        CU(ctx->d_results.reserve(sizeof(sa_result) * (size_t)m));
+        CU(ctx->d_cell_off.reserve(sizeof(int64_t) * (size_t)m));
+        CU(ctx->d_row_off.reserve(sizeof(int64_t) * (size_t)m));
+        CU(ctx->d_S.reserve(sizeof(float) * (size_t)cells));
+        CU(ctx->d_code.reserve((size_t)cells));
+        CU(ctx->d_rowmax_s.reserve(sizeof(float) * (size_t)rows));
+        CU(ctx->d_rowmax_q.reserve(sizeof(int32_t) * (size_t)rows));
+        CU(ctx->d_path_off.reserve(sizeof(int64_t) * (size_t)(m + 1)));  // reused: scores_off
+        CU(ctx->d_path_s.reserve(sizeof(float) * (size_t)n_sc));           // reused: scores_out
+        CU(ctx->d_path_j.reserve(sizeof(int32_t) * (size_t)m));            // reused: n_want
+        CU(ctx->d_path_q.reserve(sizeof(int32_t) * (size_t)m));            // reused: n_got
+        CU(cudaMemcpyAsync(ctx->d_problems.p, problems + k0, sizeof(sa_problem) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_order.p, plan.order.data(), sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_cell_off.p, cell_off.data(), sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_row_off.p, row_off.data(), sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_path_off.p, soff.data(), sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_path_j.p, n_want + k0, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        P.problems = ctx->d_problems.as<sa_problem>();
+        P.cell_off = ctx->d_cell_off.as<int64_t>();
+        P.row_off = ctx->d_row_off.as<int64_t>();
+        P.results = ctx->d_results.as<sa_result>();
+        P.S = ctx->d_S.as<float>();
+        P.code = ctx->d_code.as<uint8_t>();
+        P.rowmax_s = ctx->d_rowmax_s.as<float>();
+        P.rowmax_q = ctx->d_rowmax_q.as<int32_t>();
+        CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+        rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan.n_bulk, plan.n_large, true, mode->swap_b_x != 0);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+        DetectParams D;
+        memset(&D, 0, sizeof(D));
+        D.contigs = P.contigs;
+        D.segs = P.segs;
+        D.problems = P.problems;
+        D.cell_off = P.cell_off;
+        D.row_off = P.row_off;
+        D.scores_off = ctx->d_path_off.as<int64_t>();
+        D.n_problems = m;
+        D.S = P.S;
+        D.code = P.code;
+        D.rowmax_s = P.rowmax_s;
+        D.rowmax_q = P.rowmax_q;
+        D.n_want = ctx->d_path_j.as<int32_t>();
+        D.scores_out = ctx->d_path_s.as<float>();
+        D.n_got = ctx->d_path_q.as<int32_t>();
+        launch_detect(D, ctx->stream);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+        if (soff[(size_t)m] > 0)
+            CU(cudaMemcpyAsync(scores_out + scores_off[k0], ctx->d_path_s.p, sizeof(float) * (size_t)soff[(size_t)m], cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(n_got + k0, ctx->d_path_q.p, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+        ctx->timing.fill_ms += a;
+        ctx->timing.post_ms += b;
+        ctx->timing.n_launches += 1;
+        k0 = k1;
+    }
+    return SA_OK;
 }
 
 int sa_powf12(sa_ctx *ctx, const float *x, int64_t n, float *out, int use_fast_path) {

@@ -37,6 +37,7 @@ __constant__ double c_pk[12] = {SA_POWF_A0, SA_POWF_A1, SA_POWF_A2, SA_POWF_A3, 
 constexpr uint32_t IX_LO = SA_POWF_OFF - (20u << 23);
 constexpr uint32_t IX_RANGE = 52u << 23;
 
+#define NEG_INF_F (__int_as_float(0xff800000))
 __device__ __noinline__ float powf12_slow(float ax) {
     return powf12_generic(ax, c_logtab, reinterpret_cast<const uint64_t *>(c_exptab));
 }
@@ -95,7 +96,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 // code is still memory-safe (both table indices are masked), so callers evaluate unconditionally and patch the
 // rare out-of-domain lanes afterwards (`bad` tells which).  stab = 32-bit shared address of a PowTabSmem
 // (512-byte aligned, so `stab | offset` == `stab + offset`).
-__device__ __forceinline__ float powf12_fast(float ax, uint32_t stab, uint32_t &u_out) {
+__device__ __forceinline__ float powf12_fast(float ax, uint32_t stab, const double (&pk)[12], uint32_t &u_out) {
     const uint32_t ix = __float_as_uint(ax);
     const uint32_t u = ix - IX_LO;
     u_out = u;  // u >= IX_RANGE  <=>  outside the fast domain
@@ -109,29 +110,59 @@ __device__ __forceinline__ float powf12_fast(float ax, uint32_t stab, uint32_t &
     const double y0 = __dadd_rn(logc, (double)k);
     const double z = (double)__uint_as_float(iz);
     const double r = __fma_rn(z, invc, -1.0);
-    double y = __fma_rn(r, c_pk[0], c_pk[1]);
-    const double p = __fma_rn(r, c_pk[2], c_pk[3]);
+    double y = __fma_rn(r, pk[0], pk[1]);
+    const double p = __fma_rn(r, pk[2], pk[3]);
     const double r2 = __dmul_rn(r, r);
-    double q = __fma_rn(r, c_pk[4], y0);
+    double q = __fma_rn(r, pk[4], y0);
     const double r4 = __dmul_rn(r2, r2);
     q = __fma_rn(r2, p, q);
     y = __fma_rn(y, r4, q);
-    const double xd = __dmul_rn(c_pk[5], y);
+    const double xd = __dmul_rn(pk[5], y);
     // exp2: 8 fp64 ops
-    double kd = __dadd_rn(xd, c_pk[9]);
+    double kd = __dadd_rn(xd, pk[9]);
     const uint32_t ki = (uint32_t)__double2loint(kd);
-    kd = __dadd_rn(kd, c_pk[10]);
+    kd = __dadd_rn(kd, pk[10]);
     const double rr = __dadd_rn(xd, -kd);
-    const uint32_t a_e = stab | (256u + ((ki << 2) & 0x7Cu));
+    const uint32_t a_e = (stab + 256u) | ((ki << 2) & 0x7Cu);
     const uint32_t tlo = lds_u32(a_e);
     const uint32_t thi = lds_u32(a_e + 128) + (ki << 15);  // t += ki << 47
     const double sc = __hiloint2double((int)thi, (int)tlo);
-    const double zz = __fma_rn(rr, c_pk[6], c_pk[7]);
+    const double zz = __fma_rn(rr, pk[6], pk[7]);
     const double rr2 = __dmul_rn(rr, rr);
-    double yy = __fma_rn(rr, c_pk[8], 1.0);
+    double yy = __fma_rn(rr, pk[8], 1.0);
     yy = __fma_rn(zz, rr2, yy);
     yy = __dmul_rn(yy, sc);
     return __double2float_rn(yy);
+}
+
+// Whole-cell evaluation through the generic powf path, same candidate order and tie rule as the fast path.
+// f[k] = fx[k] (non-swap: fp_t by column look-back) or fb[k] (swap: fp_t by row look-back).
+__device__ __noinline__ float cell_slow(bool swap, float db0, float db1, float db2, float db3, float db4, float db5,
+                                        float dx0, float dx1, float dx2, float dx3, float dx4, float dx5, float f0,
+                                        float f1, float f2, float f3, float f4, float f5, uint32_t pc0, uint32_t pc1,
+                                        uint32_t pc2, uint32_t pc3, uint32_t pc4, uint32_t pc5, int *code_out) {
+    const float db[LB] = {db0, db1, db2, db3, db4, db5};
+    const float dx[LB] = {dx0, dx1, dx2, dx3, dx4, dx5};
+    const float f[LB] = {f0, f1, f2, f3, f4, f5};
+    const uint32_t pc[LB] = {pc0, pc1, pc2, pc3, pc4, pc5};
+    float best = NEG_INF_F;
+    int code = 0;
+    for (int dj = 1; dj <= LB; dj++)
+        for (int dq = 1; dq <= LB; dq++) {
+            const float sc = lds_f32(pc[dq - 1] - dj * 4);
+            const float discrep = fabsf(__fsub_rn(db[dj - 1], dx[dq - 1]));
+            const float delta = powf12_slow(discrep);
+            const float fn = 5000.0f * (float)((swap ? dq : dj) - 1);
+            const float fp = swap ? f[dj - 1] : f[dq - 1];
+            const float r = __fsub_rn(10000.0f, __fadd_rn(__fadd_rn(fn, fp), delta));
+            const float ns = __fadd_rn(sc, r);
+            if (ns >= best) {
+                best = ns;
+                code = 1 + (dj - 1) * LB + (dq - 1);
+            }
+        }
+    *code_out = code;
+    return best;
 }
 
 constexpr int RING_W = 40;  // 6 halo rows + 32 lanes + 2 pad
@@ -215,6 +246,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         float db[LB], fb[LB];
         uint32_t pc[LB];
         int slot = 0;
+        float rm_s = 0.0f;  // detection: best positive score of this lane's row, ties -> larger q
+        int rm_q = -1;
 #pragma unroll
         for (int d = 0; d < LB; d++) {
             db[d] = 0.0f;
@@ -247,6 +280,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
 #pragma unroll
                     for (int d = 0; d < LB; d++) pc[d] = a_my + ((LB - 1 - d) % LB) * RING_W * 4;
                     slot = 0;
+                    rm_s = 0.0f;
+                    rm_q = -1;
                 }
                 float dx[LB], fx[LB];
                 {
@@ -270,23 +305,18 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                 else init = (j == 0 || q == 0) ? 0.0f : NEG_INF;
 
                 float best = NEG_INF;
+                uint32_t umax = 0;
 #pragma unroll
                 for (int dj = 1; dj <= LB; dj++) {
-                    float delta[LB], discrep[LB], sc[LB];
+                    float delta[LB], sc[LB];
                     uint32_t u[LB];
 #pragma unroll
                     for (int dq = 1; dq <= LB; dq++) {
                         sc[dq - 1] = lds_f32(pc[dq - 1] - dj * 4);
-                        discrep[dq - 1] = fabsf(__fsub_rn(db[dj - 1], dx[dq - 1]));
-                        delta[dq - 1] = powf12_fast(discrep[dq - 1], a_tab, u[dq - 1]);
+                        const float discrep = fabsf(__fsub_rn(db[dj - 1], dx[dq - 1]));
+                        delta[dq - 1] = powf12_fast(discrep, a_tab, P.pk, u[dq - 1]);
                     }
-                    const uint32_t umax = __vimax3_u32(__vimax3_u32(u[0], u[1], u[2]), __vimax3_u32(u[3], u[4], u[5]), 0u);
-                    if (umax >= IX_RANGE) {  // rare: discrepancy exactly 0, subnormal-tiny, huge, inf or NaN
-#pragma unroll
-                        for (int dq = 1; dq <= LB; dq++)
-                            if (__float_as_uint(discrep[dq - 1]) - IX_LO >= IX_RANGE)
-                                delta[dq - 1] = powf12_slow(discrep[dq - 1]);
-                    }
+                    umax = __vimax3_u32(umax, __vimax3_u32(u[0], u[1], u[2]), __vimax3_u32(u[3], u[4], u[5]));
 #pragma unroll
                     for (int dq = 1; dq <= LB; dq++) {
                         // fn_t + fp_t (SegAligner.cpp:89-91); with swap_b_x the maps exchange roles (:119)
@@ -304,6 +334,14 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                             best = fmaxf(best, ns);
                         }
                     }
+                }
+                if (umax >= IX_RANGE) {
+                    // rare: some discrepancy of this cell is exactly 0, subnormal-tiny, huge, inf or NaN, where the
+                    // branch-free replay is undefined -> redo the whole cell through the generic powf path
+                    best = cell_slow(SWAP, db[0], db[1], db[2], db[3], db[4], db[5], dx[0], dx[1], dx[2], dx[3], dx[4],
+                                     dx[5], SWAP ? fb[0] : fx[0], SWAP ? fb[1] : fx[1], SWAP ? fb[2] : fx[2],
+                                     SWAP ? fb[3] : fx[3], SWAP ? fb[4] : fx[4], SWAP ? fb[5] : fx[5], pc[0], pc[1],
+                                     pc[2], pc[3], pc[4], pc[5], &code);
                 }
                 val = init;
                 if (best > init && !row_used) val = best;
@@ -328,6 +366,16 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     if (STORE) {
                         Sout[(long long)j * nx + q] = val;
                         Cout[(long long)j * nx + q] = (uint8_t)code;
+                        if (P.rowmax_s) {
+                            if (val > 0.0f && val >= rm_s) {
+                                rm_s = val;
+                                rm_q = q;
+                            }
+                            if (q == nx - 1) {
+                                P.rowmax_s[P.row_off[pidx] + j] = rm_s;
+                                P.rowmax_q[P.row_off[pidx] + j] = rm_q;
+                            }
+                        }
                     }
                     if (P.start_mode == SA_START_LOCAL) {
                         if (val > st_s) {  // per lane (j,q) arrives in increasing row-major order
@@ -450,6 +498,117 @@ __global__ void trace_kernel(const TraceParams P) {
     P.results[k] = res;
 }
 
+// multi_backtrack_scores (SegAligner.cpp:208-233) + zero_out_aln (:198-205) for one problem per CTA.
+// The reference sorts every cell with S > 0 ascending by (score, j, q), walks the list from the top, ALWAYS
+// skips the top entry (:224 decrements before use), and takes an entry when its current S is still > 0, then
+// sets its whole traced path to -inf.  Equivalent formulation used here: kill the top cell, then repeatedly
+// take the largest (score, j, q) among cells that are still > 0 and wipe its path.  Per-row maxima (filled by
+// the sweep) make each selection an O(nb) reduction plus an O(nx) re-scan of the rows the wiped path touched.
+__global__ void __launch_bounds__(256) detect_kernel(const DetectParams P) {
+    const long long k = blockIdx.x;
+    if (k >= P.n_problems) return;
+    const sa_problem pr = P.problems[k];
+    const int64_t boff = P.contigs.pos_off[pr.contig];
+    const int nb = (int)(P.contigs.pos_off[pr.contig + 1] - boff) - 1;
+    const int64_t xoff = P.segs.pos_off[pr.seg];
+    const int nx = (int)(P.segs.pos_off[pr.seg + 1] - xoff) - 1;
+    float *S = P.S + P.cell_off[k];
+    const uint8_t *C = P.code + P.cell_off[k];
+    float *rms = P.rowmax_s + P.row_off[k];
+    int *rmq = P.rowmax_q + P.row_off[k];
+    const int want = P.n_want[k];
+    float *out = P.scores_out + P.scores_off[k];
+    __shared__ float sh_s[256];
+    __shared__ int sh_j[256], sh_q[256];
+    __shared__ int sh_bj, sh_bq;
+    __shared__ float sh_bs;
+    const int tid = threadIdx.x;
+    int got = 0;
+    for (int it = 0; it <= want; it++) {
+        // argmax over rows: score desc, then j desc, then q desc
+        float bs = 0.0f;
+        int bj = -1, bq = -1;
+        for (int r = tid; r < nb; r += 256) {
+            const float s = rms[r];
+            if (s > 0.0f && (s > bs || (s == bs && r > bj))) {
+                bs = s;
+                bj = r;
+                bq = rmq[r];
+            }
+        }
+        sh_s[tid] = bs;
+        sh_j[tid] = bj;
+        sh_q[tid] = bq;
+        __syncthreads();
+        for (int m = 128; m > 0; m >>= 1) {
+            if (tid < m) {
+                const float os = sh_s[tid + m];
+                const int oj = sh_j[tid + m];
+                if (oj >= 0 && (sh_j[tid] < 0 || os > sh_s[tid] || (os == sh_s[tid] && oj > sh_j[tid]))) {
+                    sh_s[tid] = os;
+                    sh_j[tid] = oj;
+                    sh_q[tid] = sh_q[tid + m];
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            sh_bs = sh_s[0];
+            sh_bj = sh_j[0];
+            sh_bq = sh_q[0];
+        }
+        __syncthreads();
+        if (sh_bj < 0) break;  // no positive cell left (the reference would index all_scores[-1] here)
+        if (it > 0) {
+            if (tid == 0) out[got] = sh_bs;
+            got++;
+        }
+        // wipe: the top cell alone on the first pass (it is only skipped, never traced), else the whole path
+        int j = sh_bj, q = sh_bq;
+        __syncthreads();
+        for (;;) {
+            const long long c = (long long)j * nx + q;
+            const int cd = C[c];
+            __syncthreads();
+            if (tid == 0) S[c] = NEG_INF;
+            __syncthreads();
+            // re-scan row j
+            float rs = 0.0f;
+            int rq = -1;
+            for (int x = tid; x < nx; x += 256) {
+                const float s = S[(long long)j * nx + x];
+                if (s > 0.0f && s >= rs) {
+                    rs = s;
+                    rq = x;
+                }
+            }
+            sh_s[tid] = rs;
+            sh_q[tid] = rq;
+            __syncthreads();
+            for (int m = 128; m > 0; m >>= 1) {
+                if (tid < m) {
+                    const float os = sh_s[tid + m];
+                    const int oq = sh_q[tid + m];
+                    if (oq >= 0 && (sh_q[tid] < 0 || os > sh_s[tid] || (os == sh_s[tid] && oq > sh_q[tid]))) {
+                        sh_s[tid] = os;
+                        sh_q[tid] = oq;
+                    }
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                rms[j] = sh_q[0] >= 0 ? sh_s[0] : 0.0f;
+                rmq[j] = sh_q[0];
+            }
+            __syncthreads();
+            if (it == 0 || cd == 0) break;
+            j -= (cd - 1) / LB + 1;
+            q -= (cd - 1) % LB + 1;
+        }
+    }
+    if (tid == 0) P.n_got[k] = got;
+}
+
 __global__ void powf12_kernel(const float *x, long long n, float *out, int fast) {
     __shared__ PowTabSmem s_tab;
     powtab_init(s_tab);
@@ -458,7 +617,7 @@ __global__ void powf12_kernel(const float *x, long long n, float *out, int fast)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float ax = fabsf(x[i]);
         uint32_t u;
-        const float f = powf12_fast(ax, a_tab, u);
+        const float f = powf12_fast(ax, a_tab, c_pk, u);
         out[i] = (fast && u < IX_RANGE) ? f : powf12_slow(ax);
     }
 }
@@ -473,7 +632,7 @@ __global__ void powf12_range_kernel(uint32_t lo, uint32_t hi, float *out_fast, f
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const float ax = __uint_as_float(lo + (uint32_t)i);
         uint32_t u;
-        const float f = powf12_fast(ax, a_tab, u);
+        const float f = powf12_fast(ax, a_tab, c_pk, u);
         const float g = powf12_slow(ax);
         out_fast[i] = (u >= IX_RANGE) ? g : f;
         out_generic[i] = g;
@@ -517,12 +676,21 @@ void launch_fill(const FillParams &p, bool store, bool swap, bool coop, int n_ct
     else launch_fill_t<1, FILL_MINB>(p, store, swap, n_ctas, st);
 }
 
+void fill_powf_constants(double *pk) {
+    const double v[12] = {SA_POWF_A0, SA_POWF_A1, SA_POWF_A2, SA_POWF_A3, SA_POWF_A4, SA_Y12,
+                          SA_EXP2F_C0, SA_EXP2F_C1, SA_EXP2F_C2, SA_EXP2F_SHIFT, -SA_EXP2F_SHIFT, 0.0};
+    for (int i = 0; i < 12; i++) pk[i] = v[i];
+}
+
 void launch_traceback(const TraceParams &p, cudaStream_t st) {
     const int threads = 64;
     const long long blocks = (p.n_problems + threads - 1) / threads;
     if (blocks > 0) trace_kernel<<<(unsigned)blocks, threads, 0, st>>>(p);
 }
 
+void launch_detect(const DetectParams &p, cudaStream_t st) {
+    if (p.n_problems > 0) detect_kernel<<<(unsigned)p.n_problems, 256, 0, st>>>(p);
+}
 void launch_powf12(const float *x, long long n, float *out, int fast, cudaStream_t st) {
     powf12_kernel<<<148 * 8, 256, 0, st>>>(x, n, out, fast);
 }

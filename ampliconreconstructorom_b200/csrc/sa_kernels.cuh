@@ -43,6 +43,10 @@ struct FillParams {
     long long halo_stride;
     unsigned long long *counter;  // work-queue head
     int init_mode, start_mode, fitting;
+    float *rowmax_s;  // detection only: per-row best positive score / its column (ties -> larger q)
+    int32_t *rowmax_q;
+    const int64_t *row_off;  // per problem offset into the rowmax arrays
+    double pk[12];  // fp64 constants of the powf replay (kernel-parameter bank => direct DFMA operands)
 };
 
 struct TraceParams {
@@ -58,13 +62,32 @@ struct TraceParams {
     float *path_s;
 };
 
+struct DetectParams {
+    MapSetDev contigs, segs;
+    const sa_problem *problems;
+    const int64_t *cell_off, *row_off, *scores_off;
+    long long n_problems;
+    float *S;
+    const uint8_t *code;
+    float *rowmax_s;
+    int32_t *rowmax_q;
+    const int32_t *n_want;
+    float *scores_out;
+    int32_t *n_got;
+};
+
+void launch_detect(const DetectParams &p, cudaStream_t st);
 void launch_fill(const FillParams &p, bool store, bool swap, bool coop, int n_ctas, cudaStream_t st);
 void launch_traceback(const TraceParams &p, cudaStream_t st);
 void launch_powf12(const float *x, long long n, float *out, int fast, cudaStream_t st);
 void launch_powf12_range(uint32_t lo, uint32_t hi, float *out_fast, float *out_generic, cudaStream_t st);
 void launch_dfma_peak(double *sink, int iters, int n_ctas, cudaStream_t st);
 int fill_ctas_per_sm();
-constexpr int FILL_MINB = 4;   // resident CTAs per SM the fill kernel is compiled for (register budget 128)
+void fill_powf_constants(double *pk);
+#ifndef SA_FILL_MINB
+#define SA_FILL_MINB 4
+#endif
+constexpr int FILL_MINB = SA_FILL_MINB;   // resident CTAs per SM the fill kernel is compiled for (register budget 128)
 constexpr int COOP_WARPS = 16;  // warps of the cooperative (one problem per CTA) variant used for large problems
 constexpr int FILL_WARPS = 4;  // warps per CTA of the fill kernel (one problem per warp at a time)
 

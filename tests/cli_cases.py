@@ -1,0 +1,89 @@
+"""Shared CLI-level cases: run the reference SegAligner and the B200 SegAligner on the same CMAP files and
+compare every output file byte for byte (used by the gpu-marked tests and by tests/golden/make_golden.py)."""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from ampliconreconstructorom_b200 import synth  # noqa: E402
+
+REF_BIN = ROOT / "oracle" / "_ref" / "SegAligner_ref"
+NEW_BIN = ROOT / "ampliconreconstructorom_b200" / "bin" / "SegAligner"
+
+
+def make_case(seed: int, n_segs=6, n_contigs=60, n_related=14, seg_labels=(12, 70), contig_labels=(40, 260),
+              enzyme="BspQI", integer=False):
+    """Segments tile a region of an in-silico genome; `n_related` contigs are noisy windows over that region
+    (true alignments, some spanning several segments, half reversed); the rest come from elsewhere (null)."""
+    rng = np.random.default_rng(seed)
+    g = synth.genome_positions(rng, 60_000, enzyme)
+    segs, contigs = {}, {}
+    start = 1000
+    cur = start
+    for k in range(n_segs):
+        n = int(rng.integers(*seg_labels))
+        segs[k + 1] = synth.window_map(g, cur, n)
+        cur += n
+    region_end = cur
+    for k in range(n_contigs):
+        n = int(rng.integers(*contig_labels))
+        if k < n_related:
+            s = int(rng.integers(max(start - n // 2, 1), region_end - 5))
+        else:
+            s = int(rng.integers(region_end + 500, g.size - n - 2))
+        contigs[k + 1] = synth.noisy_contig(rng, g, s, n)
+        if integer:
+            contigs[k + 1] = np.round(contigs[k + 1])
+    return segs, contigs
+
+
+def write_case(tmp: Path, segs, contigs):
+    tmp.mkdir(parents=True, exist_ok=True)
+    synth.write_cmap(tmp / "segs.cmap", segs)
+    synth.write_cmap(tmp / "contigs.cmap", contigs)
+    return tmp / "segs.cmap", tmp / "contigs.cmap"
+
+
+def run_bin(binary: Path, workdir: Path, seg_file, contig_file, flags, timeout=1800):
+    workdir.mkdir(parents=True, exist_ok=True)
+    cmd = [str(binary), str(seg_file), str(contig_file), f"-prefix={workdir}/SA"] + list(flags)
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    return p
+
+
+def dir_digest(workdir: Path) -> dict:
+    out = {}
+    for f in sorted(workdir.iterdir()):
+        if f.is_file():
+            out[f.name] = hashlib.sha256(f.read_bytes()).hexdigest()
+    return out
+
+
+def compare_dirs(a: Path, b: Path):
+    da, db = dir_digest(a), dir_digest(b)
+    only_a = sorted(set(da) - set(db))
+    only_b = sorted(set(db) - set(da))
+    diff = sorted(k for k in set(da) & set(db) if da[k] != db[k])
+    return only_a, only_b, diff, len(da)
+
+
+CASES = {
+    # name: (make_case kwargs, flags)
+    "standard_gen2": (dict(seed=1), ["-nthreads=3", "-min_labs=10", "-gen=2"]),
+    "standard_gen1": (dict(seed=2, n_contigs=70), ["-nthreads=2", "-min_labs=10", "-gen=1"]),
+    "local_gen2": (dict(seed=3), ["-nthreads=4", "-min_labs=10", "-gen=2", "-local"]),
+    "no_tip": (dict(seed=4), ["-nthreads=1", "-min_labs=12", "-gen=2", "-no_tip_aln"]),
+    "integer_positions": (dict(seed=5, integer=True), ["-nthreads=2", "-min_labs=10", "-gen=1"]),
+    "few_contigs_nan_thresholds": (dict(seed=6, n_contigs=10, n_related=4), ["-nthreads=2", "-gen=2"]),  # KA-3
+    "detection": (dict(seed=7, n_segs=5, n_contigs=45, n_related=10, contig_labels=(100, 900)),
+                  ["-nthreads=4", "-min_labs=10", "-gen=1", "-detection"]),
+    "detection_small_n": (dict(seed=8, n_segs=4, n_contigs=40, n_related=8, contig_labels=(60, 400)),
+                          ["-nthreads=2", "-min_labs=10", "-gen=2", "-detection", "-n_detect_scores=120"]),
+}

@@ -1,0 +1,69 @@
+"""CLI-level parity on the GPU box: the B200 `SegAligner` executable against the UNMODIFIED reference binary
+(oracle/_ref/SegAligner_ref, built from /root/reference by oracle/Makefile and shipped with the snapshot).
+Every output file must be byte-identical: *_all_scores.txt (same -nthreads => same row order),
+*_score_thresholds.txt and every *_aln.txt, in standard, local, detection, fitting and contig-list runs."""
+import numpy as np
+import pytest
+
+import cli_cases as cc
+from ampliconreconstructorom_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_bins():
+    if not cc.REF_BIN.exists():
+        pytest.skip("oracle/_ref/SegAligner_ref not built")
+    assert cc.NEW_BIN.exists(), "ampliconreconstructorom_b200/bin/SegAligner not built (run __graft_entry__.build())"
+
+
+def _run_both(tmp_path, segs, contigs, flags):
+    seg_f, con_f = cc.write_case(tmp_path / "in", segs, contigs)
+    r = cc.run_bin(cc.REF_BIN, tmp_path / "ref", seg_f, con_f, flags)
+    n = cc.run_bin(cc.NEW_BIN, tmp_path / "new", seg_f, con_f, flags)
+    assert n.returncode == 0, n.stderr[-2000:]
+    assert r.returncode == 0, r.stderr[-2000:]
+    only_ref, only_new, diff, n_files = cc.compare_dirs(tmp_path / "ref", tmp_path / "new")
+    assert not only_ref and not only_new and not diff, (
+        f"files only in reference: {only_ref[:5]}; only in ours: {only_new[:5]}; different: {diff[:5]}")
+    return n_files
+
+
+@pytest.mark.parametrize("name", sorted(cc.CASES))
+def test_cli_matches_reference(tmp_path, name):
+    _need_bins()
+    kwargs, flags = cc.CASES[name]
+    segs, contigs = cc.make_case(**kwargs)
+    n_files = _run_both(tmp_path, segs, contigs, flags)
+    if name.startswith("standard") or name.startswith("detection"):
+        assert n_files > 2, "case produced no alignment files; it does not exercise the alignment phase"
+
+
+def test_cli_contig_list(tmp_path):
+    _need_bins()
+    segs, contigs = cc.make_case(seed=11, n_contigs=80, n_related=16)
+    lst = tmp_path / "list.txt"
+    lst.write_text(" ".join(str(i) for i in range(1, 70)) + "\n")
+    _run_both(tmp_path, segs, contigs, ["-nthreads=3", "-gen=2", f"-contig_list={lst}"])
+
+
+def test_cli_fitting(tmp_path):
+    """OMPathFinder-style call (OMPathFinder.py:407-428): one compound segment map vs one sub-contig map, plus
+    the KA-2 known answer of SURVEY.md section 8(c)."""
+    _need_bins()
+    seg = np.array([0, 5200, 9100, 20500, 31000, 33900, 47000, 47001], dtype=np.float64)
+    contig = np.array([0, 5150, 9300, 15000, 20400, 31200, 34000, 46800, 46801], dtype=np.float64)
+    _run_both(tmp_path / "ka2", {1: seg}, {1: contig}, ["-fitting", "-min_labs=0", "-gen=2"])
+    txt = (tmp_path / "ka2" / "new" / "SA_1_1_fitting_aln.txt").read_text().splitlines()
+    assert txt[1] == "#1+\t51069\tFalse"
+    rows = [l.split("\t") for l in txt[3:]]
+    assert [(r[2], r[3], r[7]) for r in rows] == [("1", "1", "0"), ("2", "2", "9890.66"), ("3", "3", "19136.4"),
+                                                   ("5", "4", "23197.7"), ("6", "5", "32258.9"),
+                                                   ("7", "6", "42007.7"), ("8", "7", "51069")]
+    rng = np.random.default_rng(3)
+    for t in range(3):
+        g = synth.genome_positions(rng, 500)
+        s = synth.window_map(g, 10, int(rng.integers(5, 40)))
+        c = synth.noisy_contig(rng, g, 8, int(rng.integers(10, 60)))
+        _run_both(tmp_path / f"f{t}", {1: s, 2: synth.window_map(g, 100, 12)}, {1: c, 3: synth.noisy_contig(rng, g, 90, 30)},
+                  ["-fitting", "-min_labs=0", "-gen=1"])
