@@ -36,7 +36,9 @@ class Timing(C.Structure):
 EXPORTS = [
     "sa_device_count", "sa_ctx_create", "sa_ctx_destroy", "sa_last_error", "sa_set_maps", "sa_score_batch",
     "sa_plan_create", "sa_plan_destroy", "sa_plan_score", "sa_plan_results", "sa_plan_info", "sa_sync", "sa_align_batch", "sa_detect_batch", "sa_fill_one", "sa_powf12",
-    "sa_powf12_range", "sa_get_timing", "sa_measure_fp64_peak",
+    "sa_powf12_range", "sa_get_timing", "sa_measure_fp64_peak", "sa_event_record", "sa_event_elapsed_ms",
+    "sa_host_non_collapse_probs", "sa_host_make_reverse", "sa_host_parse_cmap", "sa_host_score_thresholds",
+    "sa_host_format_float",
 ]
 
 _lib = None
@@ -74,8 +76,99 @@ def load_library() -> C.CDLL:
     lib.sa_powf12_range.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp]
     lib.sa_get_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.sa_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.sa_event_record.argtypes = [vp, i32]
+    lib.sa_event_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.sa_host_non_collapse_probs.argtypes = [i32, vp, vp, i32, vp]
+    lib.sa_host_make_reverse.argtypes = [i32, vp, vp, vp, i32, i32, i64, vp, vp, vp, C.POINTER(i32), C.POINTER(i64)]
+    lib.sa_host_parse_cmap.argtypes = [C.c_char_p, i32, i64, vp, vp, vp, C.POINTER(i32), C.POINTER(i64)]
+    lib.sa_host_score_thresholds.argtypes = [i64, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, C.c_double, i32, vp]
+    lib.sa_host_format_float.argtypes = [C.c_float, C.c_char_p, i32]
     _lib = lib
     return lib
+
+
+# ---- host-side (CPU) preparation helpers: the executable's own C++ behind the C ABI -------------------------------
+
+def flatten_maps(maps: dict):
+    """{id: positions incl. length} -> (ids int32, off int64, pos float32) in ascending-id order."""
+    ids = np.array(sorted(maps), dtype=np.int32)
+    off = np.zeros(ids.size + 1, dtype=np.int64)
+    for k, i in enumerate(ids):
+        off[k + 1] = off[k] + len(maps[int(i)])
+    pos = (np.concatenate([np.asarray(maps[int(i)], dtype=np.float32) for i in ids])
+           if ids.size else np.zeros(0, dtype=np.float32))
+    return ids, off, pos
+
+
+def unflatten_maps(ids, off, pos) -> dict:
+    return {int(ids[k]): pos[off[k]:off[k + 1]].copy() for k in range(len(ids))}
+
+
+def host_non_collapse_probs(off, pos, gen: int) -> np.ndarray:
+    lib = load_library()
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    pos = np.ascontiguousarray(pos, dtype=np.float32)
+    n = off.size - 1
+    out = np.zeros(max(int(off[-1]) - n, 1), dtype=np.float32)
+    rc = lib.sa_host_non_collapse_probs(n, _ptr(off), _ptr(pos), gen, _ptr(out))
+    if rc:
+        raise SegAlignerError(f"sa_host_non_collapse_probs failed ({rc})")
+    return out[:int(off[-1]) - n]
+
+
+def host_make_reverse(ids, off, pos, min_map_len: int):
+    lib = load_library()
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    pos = np.ascontiguousarray(pos, dtype=np.float32)
+    n_out, n_pos = C.c_int32(), C.c_int64()
+    lib.sa_host_make_reverse(ids.size, _ptr(ids), _ptr(off), _ptr(pos), min_map_len, 0, 0, None, None, None,
+                             C.byref(n_out), C.byref(n_pos))
+    oi = np.zeros(max(n_out.value, 1), dtype=np.int32)
+    oo = np.zeros(n_out.value + 1, dtype=np.int64)
+    op = np.zeros(max(n_pos.value, 1), dtype=np.float32)
+    rc = lib.sa_host_make_reverse(ids.size, _ptr(ids), _ptr(off), _ptr(pos), min_map_len, n_out.value, n_pos.value,
+                                  _ptr(oi), _ptr(oo), _ptr(op), C.byref(n_out), C.byref(n_pos))
+    if rc:
+        raise SegAlignerError(f"sa_host_make_reverse failed ({rc})")
+    return oi[:n_out.value], oo, op[:n_pos.value]
+
+
+def host_parse_cmap(path):
+    lib = load_library()
+    n_out, n_pos = C.c_int32(), C.c_int64()
+    rc = lib.sa_host_parse_cmap(str(path).encode(), 0, 0, None, None, None, C.byref(n_out), C.byref(n_pos))
+    if rc:
+        raise SegAlignerError(f"sa_host_parse_cmap({path}) failed ({rc})")
+    oi = np.zeros(max(n_out.value, 1), dtype=np.int32)
+    oo = np.zeros(n_out.value + 1, dtype=np.int64)
+    op = np.zeros(max(n_pos.value, 1), dtype=np.float32)
+    lib.sa_host_parse_cmap(str(path).encode(), n_out.value, n_pos.value, _ptr(oi), _ptr(oo), _ptr(op),
+                           C.byref(n_out), C.byref(n_pos))
+    return oi[:n_out.value], oo, op[:n_pos.value]
+
+
+def host_score_thresholds(row_seg, row_contig, row_score, segs: dict, contigs: dict, pvalue: float, n_detect=500):
+    lib = load_library()
+    si, so, sp = flatten_maps(segs)
+    ci, co, cp = flatten_maps(contigs)
+    row_seg = np.ascontiguousarray(row_seg, dtype=np.int32)
+    row_contig = np.ascontiguousarray(row_contig, dtype=np.int32)
+    row_score = np.ascontiguousarray(row_score, dtype=np.float32)
+    out = np.zeros(max(si.size, 1), dtype=np.float32)
+    rc = lib.sa_host_score_thresholds(row_score.size, _ptr(row_seg), _ptr(row_contig), _ptr(row_score), si.size,
+                                      _ptr(si), _ptr(so), _ptr(sp), ci.size, _ptr(ci), _ptr(co), _ptr(cp),
+                                      C.c_double(pvalue), n_detect, _ptr(out))
+    if rc:
+        raise SegAlignerError(f"sa_host_score_thresholds failed ({rc})")
+    return {int(si[k]): out[k] for k in range(si.size)}
+
+
+def host_format_float(v: float) -> str:
+    lib = load_library()
+    buf = C.create_string_buffer(64)
+    lib.sa_host_format_float(C.c_float(v), buf, 64)
+    return buf.value.decode()
 
 
 def _ptr(a):
@@ -247,6 +340,14 @@ class Context:
         t = Timing()
         self._check(self.lib.sa_get_timing(self.h, C.byref(t)), "sa_get_timing")
         return t
+
+    def event_record(self, slot: int):
+        self._check(self.lib.sa_event_record(self.h, slot), "sa_event_record")
+
+    def event_elapsed_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self.lib.sa_event_elapsed_ms(self.h, C.byref(ms)), "sa_event_elapsed_ms")
+        return ms.value
 
     def fp64_peak(self) -> float:
         v = C.c_double()

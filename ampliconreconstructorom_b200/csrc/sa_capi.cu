@@ -71,6 +71,7 @@ struct sa_ctx {
     cudaStream_t stream2 = nullptr;  // cooperative (large-problem) launches run beside the bulk kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_user[2] = {nullptr, nullptr};
     std::string err;
     MapSetHost sides[2];
     DevBuf d_problems, d_order, d_results, d_halo, d_counter, d_cell_off, d_S, d_code, d_used, d_path_off, d_path_j,
@@ -272,6 +273,7 @@ int sa_ctx_create(int device, sa_ctx **out) {
     }
     cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    for (auto &e : ctx->ev_user) cudaEventCreate(&e);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     ctx->ctas_per_sm = fill_ctas_per_sm();
@@ -300,6 +302,8 @@ void sa_ctx_destroy(sa_ctx *ctx) {
                       &ctx->d_rowmax_q};
     for (auto b : bufs) b->release();
     for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_user)
         if (e) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -713,6 +717,21 @@ int sa_get_timing(sa_ctx *ctx, sa_timing *t) {
         ctx->timing.fill_ms = a;
     }
     *t = ctx->timing;
+    return SA_OK;
+}
+
+int sa_event_record(sa_ctx *ctx, int32_t slot) {
+    if (!ctx || slot < 0 || slot > 1) return SA_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev_user[slot], ctx->stream));
+    return SA_OK;
+}
+
+int sa_event_elapsed_ms(sa_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return SA_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->ev_user[1]));
+    CU(cudaEventElapsedTime(ms, ctx->ev_user[0], ctx->ev_user[1]));
     return SA_OK;
 }
 

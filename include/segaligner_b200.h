@@ -130,6 +130,29 @@ int sa_get_timing(sa_ctx *ctx, sa_timing *t);
 /* Microbenchmark: sustained fp64 FMA issue rate (DFMA instructions/s, whole GPU) used as roofline peak. */
 int sa_measure_fp64_peak(sa_ctx *ctx, double *dfma_per_s);
 
+/* ---- host-side (CPU) preparation helpers: the executable's own code behind extern "C" -------------------------
+ * None of these is on the DP hot path; they exist so that every caller prepares inputs identically.
+ *   sa_host_non_collapse_probs  non_collapse_probs (SegAligner.cpp:40-68) over a map set in id order
+ *   sa_host_make_reverse        make_reverse_cmap (SAHelper.cpp:61-81); two-call sizing: pass caps of 0 first
+ *   sa_host_parse_cmap          parse_cmap (SAHelper.cpp:17-48); two-call sizing
+ *   sa_host_score_thresholds    compute_score_thresholds (main.cpp:43-105), one float per segment (id order)
+ *   sa_host_format_float        what `ostream << float` prints (the number format of every output file) */
+int sa_host_non_collapse_probs(int32_t n_maps, const int64_t *off, const float *pos, int32_t inst_gen, float *prob_out);
+int sa_host_make_reverse(int32_t n_maps, const int32_t *ids, const int64_t *off, const float *pos, int32_t min_map_len,
+                         int32_t cap_maps, int64_t cap_pos, int32_t *out_ids, int64_t *out_off, float *out_pos,
+                         int32_t *n_out, int64_t *n_pos_out);
+int sa_host_parse_cmap(const char *path, int32_t cap_maps, int64_t cap_pos, int32_t *out_ids, int64_t *out_off,
+                       float *out_pos, int32_t *n_out, int64_t *n_pos_out);
+int sa_host_score_thresholds(int64_t n_rows, const int32_t *row_seg, const int32_t *row_contig, const float *row_score,
+                             int32_t n_segs, const int32_t *seg_ids, const int64_t *seg_off, const float *seg_pos,
+                             int32_t n_contigs, const int32_t *contig_ids, const int64_t *contig_off,
+                             const float *contig_pos, double pvalue, int32_t n_detect_scores, float *thr_out);
+int sa_host_format_float(float v, char *buf, int32_t cap);
+
+/* Device-time bracket on the context's stream (CUDA events): record slot 0 / 1, then read the elapsed ms. */
+int sa_event_record(sa_ctx *ctx, int32_t slot);
+int sa_event_elapsed_ms(sa_ctx *ctx, float *ms);
+
 #ifdef __cplusplus
 }
 #endif
