@@ -398,10 +398,6 @@ int main(int argc, char *argv[]) {
     }
     printf("Running SegAligner on %d segments and %d contigs.\n", segs.n_maps(), contigs.n_maps());
     fflush(stdout);
-    if (o.lookback != 6) {
-        fprintf(stderr, "SegAligner(b200): -nl (unbanded look-back) is not available in this build yet\n");
-        return 3;
-    }
     if (segs.n_maps() == 0 || contigs.n_maps() == 0) {
         // nothing to align; the reference still writes the (empty) score files unless -fitting
         if (!o.fitting_aln) {

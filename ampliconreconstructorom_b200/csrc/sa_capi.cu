@@ -75,7 +75,7 @@ struct sa_ctx {
     std::string err;
     MapSetHost sides[2];
     DevBuf d_problems, d_order, d_results, d_halo, d_counter, d_cell_off, d_S, d_code, d_used, d_path_off, d_path_j,
-        d_path_q, d_path_s, d_tmp0, d_tmp1, d_tmp2, d_halo2, d_row_off, d_rowmax_s, d_rowmax_q;
+        d_path_q, d_path_s, d_tmp0, d_tmp1, d_tmp2, d_halo2, d_row_off, d_rowmax_s, d_rowmax_q, d_prev32;
     sa_timing timing = {0, 0, 0, 0};
     size_t store_budget_cells = 0;  // max cells of stored matrices per chunk
 };
@@ -185,12 +185,20 @@ int check_problems(sa_ctx *ctx, const sa_problem *pr, int64_t n, int64_t n_used_
     return SA_OK;
 }
 
+int check_unbanded_sizes(sa_ctx *ctx, const sa_mode *mode, const sa_problem *pr, int64_t n) {
+    if (!mode || mode->lookback == LB) return SA_OK;
+    for (int64_t k = 0; k < n; k++)  // packed predecessor i<<16|p of the -nl kernel
+        if (ctx->sides[0].labels(pr[k].contig) > 32767 || ctx->sides[1].labels(pr[k].seg) > 65535)
+            return fail(ctx, SA_EINVAL, "-nl (unbanded) supports contigs up to 32767 and segments up to 65535 labels");
+    return SA_OK;
+}
+
 int n_fill_ctas(const sa_ctx *ctx) { return ctx->n_sms * ctx->ctas_per_sm; }
 
 int prepare_fill(sa_ctx *ctx, FillParams &P, const sa_mode *mode) {
     if (!mode) return fail(ctx, SA_EINVAL, "mode is NULL");
     if (ctx->sides[0].n_maps == 0 || ctx->sides[1].n_maps == 0) return fail(ctx, SA_EINVAL, "maps not uploaded");
-    if (mode->lookback != LB) return fail(ctx, SA_EINVAL, "banded kernels need lookback == 6");
+    if (mode->lookback < LB) return fail(ctx, SA_EINVAL, "lookback must be 6 (banded kernels) or larger (-nl, unbanded)");
     memset(&P, 0, sizeof(P));
     P.contigs = ctx->sides[0].dev();
     P.segs = ctx->sides[1].dev();
@@ -299,7 +307,7 @@ void sa_ctx_destroy(sa_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->d_problems, &ctx->d_order,  &ctx->d_results,  &ctx->d_halo,   &ctx->d_counter, &ctx->d_cell_off,
                       &ctx->d_S,        &ctx->d_code,   &ctx->d_used,     &ctx->d_path_off, &ctx->d_path_j,  &ctx->d_path_q,
                       &ctx->d_path_s,   &ctx->d_tmp0,   &ctx->d_tmp1,     &ctx->d_tmp2,     &ctx->d_halo2,  &ctx->d_row_off, &ctx->d_rowmax_s,
-                      &ctx->d_rowmax_q};
+                      &ctx->d_rowmax_q, &ctx->d_prev32};
     for (auto b : bufs) b->release();
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -396,6 +404,7 @@ void sa_plan_destroy(sa_ctx *ctx, sa_plan *pl) {
 int sa_plan_score(sa_ctx *ctx, sa_plan *pl, const sa_mode *mode) {
     if (!ctx || !pl) return SA_EINVAL;
     CU(cudaSetDevice(ctx->device));
+    if (mode && mode->lookback != LB) return fail(ctx, SA_EINVAL, "sa_plan_score is banded-only; use sa_score_batch for -nl");
     FillParams P;
     int rc = prepare_fill(ctx, P, mode);
     if (rc) return rc;
@@ -430,6 +439,12 @@ int sa_score_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
     if (!ctx) return SA_EINVAL;
     if (n <= 0) return SA_OK;
     if (!problems || !results) return fail(ctx, SA_EINVAL, "NULL buffer");
+    if (mode && mode->lookback != LB) {  // -nl: the unbanded kernel always stores its matrices; reuse the alignment path
+        std::vector<int64_t> poff((size_t)n + 1, 0);
+        int32_t dj = 0, dq = 0;
+        float ds = 0;
+        return sa_align_batch(ctx, mode, problems, n, nullptr, 0, 0, poff.data(), results, &dj, &dq, &ds);
+    }
     sa_plan *pl = nullptr;
     int rc = sa_plan_create(ctx, problems, n, &pl);
     if (rc) return rc;
@@ -447,6 +462,8 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
     if (!problems || !results || !path_off || !path_j || !path_q || !path_s) return fail(ctx, SA_EINVAL, "NULL buffer");
     CU(cudaSetDevice(ctx->device));
     int rc = check_problems(ctx, problems, n, used_bits ? n_used_slots : 0);
+    if (rc) return rc;
+    rc = check_unbanded_sizes(ctx, mode, problems, n);
     if (rc) return rc;
     FillParams P;
     rc = prepare_fill(ctx, P, mode);
@@ -483,8 +500,10 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
         CU(ctx->d_order.reserve(sizeof(int32_t) * (size_t)m));
         CU(ctx->d_results.reserve(sizeof(sa_result) * (size_t)m));
         CU(ctx->d_cell_off.reserve(sizeof(int64_t) * (size_t)m));
+        const bool unbanded = mode->lookback != LB;
         CU(ctx->d_S.reserve(sizeof(float) * (size_t)cells));
-        CU(ctx->d_code.reserve((size_t)cells));
+        if (unbanded) CU(ctx->d_prev32.reserve(sizeof(int32_t) * (size_t)cells));
+        else CU(ctx->d_code.reserve((size_t)cells));
         CU(ctx->d_path_off.reserve(sizeof(int64_t) * (size_t)(m + 1)));
         CU(ctx->d_path_j.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(n_path, 1)));
         CU(ctx->d_path_q.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(n_path, 1)));
@@ -501,18 +520,28 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
         P.S = ctx->d_S.as<float>();
         P.code = ctx->d_code.as<uint8_t>();
         CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-        rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan.n_bulk, plan.n_large, true, mode->swap_b_x != 0);
-        if (rc) return rc;
+        if (unbanded) {
+            P.order = nullptr;
+            P.n_problems = m;
+            launch_fill_unbanded(P, ctx->d_prev32.as<int32_t>(), mode->swap_b_x != 0,
+                                 (int)std::min<int64_t>(m, (int64_t)ctx->n_sms * 8), ctx->stream);
+            CU(cudaGetLastError());
+            ctx->timing.n_launches += 1;
+        } else {
+            rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan.n_bulk, plan.n_large, true, mode->swap_b_x != 0);
+            if (rc) return rc;
+        }
         CU(cudaEventRecord(ctx->ev[1], ctx->stream));
         TraceParams T;
         memset(&T, 0, sizeof(T));
+        T.prev32 = unbanded ? ctx->d_prev32.as<int32_t>() : nullptr;
         T.contigs = P.contigs;
         T.segs = P.segs;
         T.problems = P.problems;
         T.cell_off = P.cell_off;
         T.n_problems = m;
         T.S = P.S;
-        T.code = P.code;
+        T.code = unbanded ? nullptr : P.code;
         T.path_off = ctx->d_path_off.as<int64_t>();
         T.results = P.results;
         T.path_j = ctx->d_path_j.as<int32_t>();
@@ -558,7 +587,14 @@ int sa_fill_one(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problem, con
     if (rc) return rc;
     const size_t cells = (size_t)nb * nx;
     if (S) CU(cudaMemcpy(S, ctx->d_S.p, sizeof(float) * cells, cudaMemcpyDeviceToHost));
-    if (prev) {
+    if (prev && mode->lookback != LB) {
+        std::vector<int32_t> pv(cells);
+        CU(cudaMemcpy(pv.data(), ctx->d_prev32.p, sizeof(int32_t) * cells, cudaMemcpyDeviceToHost));
+        for (size_t c = 0; c < cells; c++) {
+            prev[2 * c] = pv[c] < 0 ? -1 : (pv[c] >> 16);
+            prev[2 * c + 1] = pv[c] < 0 ? -1 : (pv[c] & 0xffff);
+        }
+    } else if (prev) {
         std::vector<uint8_t> code(cells);
         CU(cudaMemcpy(code.data(), ctx->d_code.p, cells, cudaMemcpyDeviceToHost));
         for (int j = 0; j < nb; j++)
@@ -587,6 +623,8 @@ int sa_detect_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
     for (int64_t k = 0; k < n; k++)
         if (n_want[k] < 0 || scores_off[k + 1] - scores_off[k] < n_want[k])
             return fail(ctx, SA_EINVAL, "scores_off leaves less room than n_want");
+    rc = check_unbanded_sizes(ctx, mode, problems, n);
+    if (rc) return rc;
     FillParams P;
     rc = prepare_fill(ctx, P, mode);
     if (rc) return rc;
@@ -618,8 +656,10 @@ int sa_detect_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
         CU(ctx->d_results.reserve(sizeof(sa_result) * (size_t)m));
         CU(ctx->d_cell_off.reserve(sizeof(int64_t) * (size_t)m));
         CU(ctx->d_row_off.reserve(sizeof(int64_t) * (size_t)m));
+        const bool unbanded = mode->lookback != LB;
         CU(ctx->d_S.reserve(sizeof(float) * (size_t)cells));
-        CU(ctx->d_code.reserve((size_t)cells));
+        if (unbanded) CU(ctx->d_prev32.reserve(sizeof(int32_t) * (size_t)cells));
+        else CU(ctx->d_code.reserve((size_t)cells));
         CU(ctx->d_rowmax_s.reserve(sizeof(float) * (size_t)rows));
         CU(ctx->d_rowmax_q.reserve(sizeof(int32_t) * (size_t)rows));
         CU(ctx->d_path_off.reserve(sizeof(int64_t) * (size_t)(m + 1)));  // reused: scores_off
@@ -641,11 +681,21 @@ int sa_detect_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
         P.rowmax_s = ctx->d_rowmax_s.as<float>();
         P.rowmax_q = ctx->d_rowmax_q.as<int32_t>();
         CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-        rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan.n_bulk, plan.n_large, true, mode->swap_b_x != 0);
-        if (rc) return rc;
+        if (unbanded) {
+            P.order = nullptr;
+            P.n_problems = m;
+            launch_fill_unbanded(P, ctx->d_prev32.as<int32_t>(), mode->swap_b_x != 0,
+                                 (int)std::min<int64_t>(m, (int64_t)ctx->n_sms * 8), ctx->stream);
+            CU(cudaGetLastError());
+            ctx->timing.n_launches += 1;
+        } else {
+            rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan.n_bulk, plan.n_large, true, mode->swap_b_x != 0);
+            if (rc) return rc;
+        }
         CU(cudaEventRecord(ctx->ev[1], ctx->stream));
         DetectParams D;
         memset(&D, 0, sizeof(D));
+        D.prev32 = unbanded ? ctx->d_prev32.as<int32_t>() : nullptr;
         D.contigs = P.contigs;
         D.segs = P.segs;
         D.problems = P.problems;
@@ -654,7 +704,7 @@ int sa_detect_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
         D.scores_off = ctx->d_path_off.as<int64_t>();
         D.n_problems = m;
         D.S = P.S;
-        D.code = P.code;
+        D.code = unbanded ? nullptr : P.code;
         D.rowmax_s = P.rowmax_s;
         D.rowmax_q = P.rowmax_q;
         D.n_want = ctx->d_path_j.as<int32_t>();

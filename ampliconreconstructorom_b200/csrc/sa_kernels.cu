@@ -467,6 +467,153 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
     }
 }
 
+// -nl: dp_align with lookback = 9999999 (main.cpp:475-478): every i < j and p < q is a predecessor, O(nb^2 nx^2)
+// ("not recommended for large datasets", README.md:222).  Straight restatement, one CTA per problem: rows are
+// sequential, threads take the columns of a row; each thread scans its predecessors in the reference's order
+// (i ascending, p ascending, strict '>') with the generic powf path and the sequential fp32 accumulate of score_f.
+// S and the (i,p) predecessor (packed i<<16|p, -1 = none) are always stored; the start scan runs afterwards.
+__global__ void __launch_bounds__(128) fill_unbanded_kernel(const FillParams P, int32_t *prev32, int swap) {
+    __shared__ float sh_s[128];
+    __shared__ int sh_j[128], sh_q[128];
+    __shared__ long long sh_o[128];
+    for (long long t = blockIdx.x; t < P.n_problems; t += gridDim.x) {
+        const long long pidx = P.order ? P.order[t] : t;
+        const sa_problem pr = P.problems[pidx];
+        const int64_t boff = P.contigs.pos_off[pr.contig];
+        const int nb = (int)(P.contigs.pos_off[pr.contig + 1] - boff) - 1;
+        const float *b = P.contigs.pos + boff;
+        const float *bprob = P.contigs.prob + (boff - pr.contig);
+        const int64_t xoff = P.segs.pos_off[pr.seg];
+        const int nx = (int)(P.segs.pos_off[pr.seg + 1] - xoff) - 1;
+        const float *x = P.segs.pos + xoff;
+        const float *xprob = P.segs.prob + (xoff - pr.seg);
+        const uint32_t *used =
+            (P.used_bits && pr.used_slot >= 0) ? P.used_bits + (long long)pr.used_slot * P.used_words_per_slot : nullptr;
+        float *S = P.S + P.cell_off[pidx];
+        int32_t *PV = prev32 + P.cell_off[pidx];
+        for (int j = 0; j < nb; j++) {
+            const bool row_used = used ? ((used[j >> 5] >> (j & 31)) & 1u) : false;
+            float rm_s = 0.0f;
+            int rm_q = -1;
+            for (int q = threadIdx.x; q < nx; q += blockDim.x) {
+                float cur;
+                if (P.init_mode == SA_INIT_SEMIGLOBAL) cur = (j == 0 || q < 2) ? 0.0f : NEG_INF;
+                else if (P.init_mode == SA_INIT_LOCAL) cur = 0.0f;
+                else cur = (j == 0 || q == 0) ? 0.0f : NEG_INF;
+                int pv = -1;
+                if (!row_used) {
+                    for (int i = 0; i < j; i++) {
+                        for (int p = 0; p < q; p++) {
+                            if (P.fitting && i == 0 && p > 0) break;
+                            float acc = 0.0f, fn;
+                            if (!swap) {
+                                for (int k = p + 1; k < q; k++) acc = __fadd_rn(acc, xprob[k]);
+                                fn = 5000.0f * (float)(j - (i + 1));
+                            } else {
+                                for (int k = i + 1; k < j; k++) acc = __fadd_rn(acc, bprob[k]);
+                                fn = 5000.0f * (float)(q - (p + 1));
+                            }
+                            const float discrep = fabsf(__fsub_rn(__fsub_rn(b[j], b[i]), __fsub_rn(x[q], x[p])));
+                            const float delta = powf12_slow(discrep);
+                            const float fp = __fmul_rn(5000.0f, acc);
+                            const float sc = __fsub_rn(10000.0f, __fadd_rn(__fadd_rn(fn, fp), delta));
+                            const float ns = __fadd_rn(S[(long long)i * nx + p], sc);
+                            if (ns > cur) {
+                                cur = ns;
+                                pv = (i << 16) | p;
+                            }
+                        }
+                    }
+                }
+                S[(long long)j * nx + q] = cur;
+                PV[(long long)j * nx + q] = pv;
+                if (cur > 0.0f && cur >= rm_s) {
+                    rm_s = cur;
+                    rm_q = q;
+                }
+            }
+            if (P.rowmax_s) {  // per-row maximum for the detection harvest (ties -> larger q)
+                sh_s[threadIdx.x] = rm_s;
+                sh_q[threadIdx.x] = rm_q;
+                __syncthreads();
+                for (int m = 64; m > 0; m >>= 1) {
+                    if ((int)threadIdx.x < m) {
+                        const float os = sh_s[threadIdx.x + m];
+                        const int oq = sh_q[threadIdx.x + m];
+                        if (oq >= 0 && (sh_q[threadIdx.x] < 0 || os > sh_s[threadIdx.x] ||
+                                        (os == sh_s[threadIdx.x] && oq > sh_q[threadIdx.x]))) {
+                            sh_s[threadIdx.x] = os;
+                            sh_q[threadIdx.x] = oq;
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (threadIdx.x == 0) {
+                    P.rowmax_s[P.row_off[pidx] + j] = sh_q[0] >= 0 ? sh_s[0] : 0.0f;
+                    P.rowmax_q[P.row_off[pidx] + j] = sh_q[0];
+                }
+            }
+            __syncthreads();  // row j complete (global writes visible to the CTA) before row j+1 reads it
+        }
+        // backtrack start: scan in the reference's order (see fill_kernel), parallel max with order keys
+        float st_s = NEG_INF;
+        int st_j = -1, st_q = -1;
+        long long st_ord = 0x7fffffffffffffffll;
+        if (P.start_mode != SA_START_END) {
+            for (long long c = threadIdx.x; c < (long long)nb * nx; c += blockDim.x) {
+                const int j = (int)(c / nx), q = (int)(c % nx);
+                long long ord;
+                if (P.start_mode == SA_START_LOCAL) ord = c;
+                else {
+                    const bool last_row = (j == nb - 1), last_cols = (q >= nx - 2);
+                    if (!last_row && !last_cols) continue;
+                    ord = last_row ? (long long)q : (long long)nx + 2ll * j + (q - (nx - 2));
+                }
+                const float v = S[c];
+                if (v > st_s || (v == st_s && ord < st_ord && v > NEG_INF)) {
+                    st_s = v;
+                    st_j = j;
+                    st_q = q;
+                    st_ord = ord;
+                }
+            }
+            sh_s[threadIdx.x] = st_s;
+            sh_j[threadIdx.x] = st_j;
+            sh_q[threadIdx.x] = st_q;
+            sh_o[threadIdx.x] = st_ord;
+            __syncthreads();
+            for (int m = 64; m > 0; m >>= 1) {
+                if ((int)threadIdx.x < m) {
+                    const int o = threadIdx.x + m;
+                    if (sh_j[o] >= 0 && (sh_j[threadIdx.x] < 0 || sh_s[o] > sh_s[threadIdx.x] ||
+                                         (sh_s[o] == sh_s[threadIdx.x] && sh_o[o] < sh_o[threadIdx.x]))) {
+                        sh_s[threadIdx.x] = sh_s[o];
+                        sh_j[threadIdx.x] = sh_j[o];
+                        sh_q[threadIdx.x] = sh_q[o];
+                        sh_o[threadIdx.x] = sh_o[o];
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (threadIdx.x == 0) {
+            sa_result res;
+            if (P.start_mode == SA_START_END) {
+                res.j = nb - 1;
+                res.q = nx - 1;
+                res.score = S[(long long)(nb - 1) * nx + (nx - 1)];
+            } else {
+                res.j = sh_j[0];
+                res.q = sh_q[0];
+                res.score = sh_s[0];
+            }
+            res.path_len = 0;
+            P.results[pidx] = res;
+        }
+        __syncthreads();
+    }
+}
+
 // get_aln_list (SAHelper.cpp:83-95): follow the stored predecessor codes from the start cell.
 __global__ void trace_kernel(const TraceParams P) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -475,7 +622,7 @@ __global__ void trace_kernel(const TraceParams P) {
     const int64_t xoff = P.segs.pos_off[pr.seg];
     const int nx = (int)(P.segs.pos_off[pr.seg + 1] - xoff) - 1;
     const float *S = P.S + P.cell_off[k];
-    const uint8_t *C = P.code + P.cell_off[k];
+    const uint8_t *C = P.code ? P.code + P.cell_off[k] : nullptr;
     sa_result res = P.results[k];
     int j = res.j, q = res.q;
     const long long base = P.path_off[k];
@@ -488,11 +635,18 @@ __global__ void trace_kernel(const TraceParams P) {
         P.path_q[base + n] = q;
         P.path_s[base + n] = S[c];
         n++;
-        const int cd = C[c];
-        if (cd == 0) break;
-        const int dj = (cd - 1) / LB + 1, dq = (cd - 1) % LB + 1;
-        j -= dj;
-        q -= dq;
+        if (P.prev32) {
+            const int pv = P.prev32[P.cell_off[k] + c];
+            if (pv < 0) break;
+            j = pv >> 16;
+            q = pv & 0xffff;
+        } else {
+            const int cd = C[c];
+            if (cd == 0) break;
+            const int dj = (cd - 1) / LB + 1, dq = (cd - 1) % LB + 1;
+            j -= dj;
+            q -= dq;
+        }
     }
     res.path_len = n;
     P.results[k] = res;
@@ -513,7 +667,8 @@ __global__ void __launch_bounds__(256) detect_kernel(const DetectParams P) {
     const int64_t xoff = P.segs.pos_off[pr.seg];
     const int nx = (int)(P.segs.pos_off[pr.seg + 1] - xoff) - 1;
     float *S = P.S + P.cell_off[k];
-    const uint8_t *C = P.code + P.cell_off[k];
+    const uint8_t *C = P.code ? P.code + P.cell_off[k] : nullptr;
+    const int32_t *PV = P.prev32 ? P.prev32 + P.cell_off[k] : nullptr;
     float *rms = P.rowmax_s + P.row_off[k];
     int *rmq = P.rowmax_q + P.row_off[k];
     const int want = P.n_want[k];
@@ -568,7 +723,20 @@ __global__ void __launch_bounds__(256) detect_kernel(const DetectParams P) {
         __syncthreads();
         for (;;) {
             const long long c = (long long)j * nx + q;
-            const int cd = C[c];
+            int nj = -1, nq = -1;  // predecessor on the traced path
+            if (PV) {
+                const int pv = PV[c];
+                if (pv >= 0) {
+                    nj = pv >> 16;
+                    nq = pv & 0xffff;
+                }
+            } else {
+                const int cd = C[c];
+                if (cd != 0) {
+                    nj = j - ((cd - 1) / LB + 1);
+                    nq = q - ((cd - 1) % LB + 1);
+                }
+            }
             __syncthreads();
             if (tid == 0) S[c] = NEG_INF;
             __syncthreads();
@@ -601,9 +769,9 @@ __global__ void __launch_bounds__(256) detect_kernel(const DetectParams P) {
                 rmq[j] = sh_q[0];
             }
             __syncthreads();
-            if (it == 0 || cd == 0) break;
-            j -= (cd - 1) / LB + 1;
-            q -= (cd - 1) % LB + 1;
+            if (it == 0 || nj < 0) break;
+            j = nj;
+            q = nq;
         }
     }
     if (tid == 0) P.n_got[k] = got;
@@ -680,6 +848,10 @@ void fill_powf_constants(double *pk) {
     const double v[12] = {SA_POWF_A0, SA_POWF_A1, SA_POWF_A2, SA_POWF_A3, SA_POWF_A4, SA_Y12,
                           SA_EXP2F_C0, SA_EXP2F_C1, SA_EXP2F_C2, SA_EXP2F_SHIFT, -SA_EXP2F_SHIFT, 0.0};
     for (int i = 0; i < 12; i++) pk[i] = v[i];
+}
+
+void launch_fill_unbanded(const FillParams &p, int32_t *prev32, bool swap, int n_ctas, cudaStream_t st) {
+    fill_unbanded_kernel<<<n_ctas, 128, 0, st>>>(p, prev32, swap ? 1 : 0);
 }
 
 void launch_traceback(const TraceParams &p, cudaStream_t st) {

@@ -55,7 +55,8 @@ struct TraceParams {
     const int64_t *cell_off;
     long long n_problems;
     const float *S;
-    const uint8_t *code;
+    const uint8_t *code;     // banded: predecessor codes
+    const int32_t *prev32;   // unbanded (-nl): packed predecessors i<<16|p, -1 = none
     const int64_t *path_off;
     sa_result *results;
     int32_t *path_j, *path_q;
@@ -69,6 +70,7 @@ struct DetectParams {
     long long n_problems;
     float *S;
     const uint8_t *code;
+    const int32_t *prev32;
     float *rowmax_s;
     int32_t *rowmax_q;
     const int32_t *n_want;
@@ -78,6 +80,7 @@ struct DetectParams {
 
 void launch_detect(const DetectParams &p, cudaStream_t st);
 void launch_fill(const FillParams &p, bool store, bool swap, bool coop, int n_ctas, cudaStream_t st);
+void launch_fill_unbanded(const FillParams &p, int32_t *prev32, bool swap, int n_ctas, cudaStream_t st);
 void launch_traceback(const TraceParams &p, cudaStream_t st);
 void launch_powf12(const float *x, long long n, float *out, int fast, cudaStream_t st);
 void launch_powf12_range(uint32_t lo, uint32_t hi, float *out_fast, float *out_generic, cudaStream_t st);

@@ -84,6 +84,8 @@ CASES = {
     "few_contigs_nan_thresholds": (dict(seed=6, n_contigs=10, n_related=4), ["-nthreads=2", "-gen=2"]),  # KA-3
     "detection": (dict(seed=7, n_segs=5, n_contigs=45, n_related=10, contig_labels=(100, 900)),
                   ["-nthreads=4", "-min_labs=10", "-gen=1", "-detection"]),
+    "unbanded_nl": (dict(seed=9, n_segs=3, n_contigs=36, n_related=6, seg_labels=(12, 26), contig_labels=(30, 70)),
+                    ["-nthreads=2", "-min_labs=10", "-gen=2", "-nl"]),
     "detection_small_n": (dict(seed=8, n_segs=4, n_contigs=40, n_related=8, contig_labels=(60, 400)),
                           ["-nthreads=2", "-min_labs=10", "-gen=2", "-detection", "-n_detect_scores=120"]),
 }

@@ -160,3 +160,29 @@ def test_powf12_device_matches_host_libm(ctx, oracle):
     samp = rng.choice(u.size, size=20000, replace=False)
     ref = np.array([oracle.lib.sao_powf12(C.c_float(float(v))) for v in x[samp]], dtype=np.float32)
     assert np.array_equal(bits(fast[samp]), bits(ref))
+
+
+def test_unbanded_lookback_nl(ctx, oracle):
+    """-nl: lookback = 9999999 (main.cpp:475-478) through the generic kernel, all modes."""
+    rng = np.random.default_rng(31)
+    contigs, segs, cp, sp = build_sets(rng, oracle, 6, 2, max_nb=45, max_nx=28)
+    cids = upload(ctx, contigs, cp, capi.SA_SIDE_CONTIG)
+    sids = upload(ctx, segs, sp, capi.SA_SIDE_SEG)
+    for k in range(len(cids)):
+        for (init, fit, swap, start) in MODES:
+            used = [1, 4] if (k == 2 and not fit and len(contigs[cids[k]]) > 6) else None
+            S, prev, res = ctx.fill_one(ctx.mode(init, start, fit, 9999999, swap), k, k, used_rows=used)
+            So, prevo = oracle.fill(contigs[cids[k]], segs[sids[k]], cp[cids[k]], sp[sids[k]], init, fit, 9999999, used, swap)
+            assert np.array_equal(bits(S), bits(So)) and np.array_equal(prev, prevo)
+            assert (int(res["j"]), int(res["q"])) == oracle.start(So, start)
+    pr = ctx.problems(np.arange(len(cids)), np.arange(len(cids)))
+    mode = ctx.mode(0, 0, 0, 9999999, 0)
+    res = ctx.score_batch(mode, pr)
+    ares, poff, pj, pq, ps = ctx.align_batch(mode, pr)
+    for k in range(pr.size):
+        So, prevo = oracle.fill(contigs[cids[k]], segs[sids[k]], cp[cids[k]], sp[sids[k]], 0, 0, 9999999, None, 0)
+        st = oracle.start(So, 0)
+        assert (int(res["j"][k]), int(res["q"][k])) == st and bits(res["score"][k]) == bits(So[st])
+        oj, oq, os_ = oracle.traceback(So, prevo, *st)
+        sl = slice(int(poff[k]), int(poff[k]) + int(ares["path_len"][k]))
+        assert np.array_equal(pj[sl], oj) and np.array_equal(pq[sl], oq) and np.array_equal(bits(ps[sl]), bits(os_))
