@@ -22,6 +22,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <unistd.h>
 #include "cmap.h"
 #include "segaligner_b200.h"
 
@@ -110,6 +111,19 @@ struct Engine {
         for (int g = 0; g < n; g++) th.emplace_back([&, g]() { rcs[(size_t)g] = sa_ctx_create(g, &ctx[(size_t)g]); });
         for (auto &t : th) t.join();
         for (int g = 0; g < n; g++)
+            if (rcs[(size_t)g]) die(nullptr, "sa_ctx_create (need an sm_100 GPU)", rcs[(size_t)g]);
+    }
+    void open_more(int n) {  // device 0 is already open; add devices 1..n-1
+        const int avail = sa_device_count();
+        n = std::max(1, std::min(n, avail));
+        const int have = (int)ctx.size();
+        if (n <= have) return;
+        ctx.resize((size_t)n, nullptr);
+        std::vector<std::thread> th;
+        std::vector<int> rcs((size_t)n, 0);
+        for (int g = have; g < n; g++) th.emplace_back([&, g]() { rcs[(size_t)g] = sa_ctx_create(g, &ctx[(size_t)g]); });
+        for (auto &t : th) t.join();
+        for (int g = have; g < n; g++)
             if (rcs[(size_t)g]) die(nullptr, "sa_ctx_create (need an sm_100 GPU)", rcs[(size_t)g]);
     }
     void close() {
@@ -360,6 +374,16 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
 double wall_now() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+struct PhaseTimer {  // SA_VERBOSE=1: per-phase wall times on stderr
+    bool on = getenv("SA_VERBOSE") != nullptr;
+    double t = wall_now();
+    void lap(const char *what) {
+        if (!on) return;
+        const double n = wall_now();
+        fprintf(stderr, "SegAligner(b200): %-28s %8.3f s\n", what, n - t);
+        t = n;
+    }
+};
 
 }  // namespace
 
@@ -381,6 +405,10 @@ int main(int argc, char *argv[]) {
     }
     if (o.inst_gen == 2) o.max_seg_contig_alns *= 2;  // main.cpp:479-481
 
+    PhaseTimer pt;
+    // CUDA start-up (driver init + context, ~0.3 s) overlaps with CMAP parsing: open device 0 right away
+    Engine eng;
+    std::thread gpu_open([&eng]() { eng.open(1); });
     MapSet segs_raw, segs, contigs;
     parse_cmap(ref_cmap_file, segs_raw);
     if (!o.fitting_aln) segs = make_reverse_cmap(segs_raw, o.min_map_len);
@@ -388,6 +416,7 @@ int main(int argc, char *argv[]) {
     parse_cmap(contig_cmap_file, contigs);
     non_collapse_probs(segs, o.inst_gen);
     non_collapse_probs(contigs, o.inst_gen);
+    pt.lap("parse + prepare maps");
 
     // contig set (get_contig_set, main.cpp:437-447)
     std::set<int> contig_set;
@@ -404,6 +433,8 @@ int main(int argc, char *argv[]) {
             write_all_scores({}, o.sample_prefix);
             write_score_thresholds({}, o.sample_prefix + o.detection_label);
         }
+        gpu_open.join();
+        eng.close();
         return 0;
     }
 
@@ -419,9 +450,11 @@ int main(int argc, char *argv[]) {
     if (const char *e = getenv("SA_NGPUS"))
         if (n_gpus <= 0) n_gpus = atoi(e);
     if (n_gpus <= 0) n_gpus = total_cells > 2e10 ? sa_device_count() : 1;
-    Engine eng;
-    eng.open(n_gpus);
+    gpu_open.join();
+    if (n_gpus > 1) eng.open_more(n_gpus);
+    pt.lap("open GPU context(s)");
     eng.set_maps(contigs, segs);
+    pt.lap("upload maps");
 
     // ---------------- fitting mode (main.cpp:512-526, run_SA_fitting :169-208) --------------------------------
     if (o.fitting_aln) {
@@ -446,6 +479,7 @@ int main(int argc, char *argv[]) {
             print_alignment(outname, paths[k], contig_id, x, segs.size(pr[k].seg), res[k].score);
         }
         printf("elapsed seconds for run %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
+        fflush(stdout);
         eng.close();
         return 0;
     }
@@ -494,7 +528,9 @@ int main(int argc, char *argv[]) {
                 rows.push_back(ScoreRow{segs.ids[(size_t)pr[k].seg], contigs.ids[(size_t)pr[k].contig], res[k].score});
         }
     }
+    pt.lap("phase 1 scoring (GPU)");
     write_all_scores(rows, o.sample_prefix);
+    pt.lap("write all_scores");
 
     // ---------------- phase 2: thresholds (main.cpp:555-557) ---------------------------------------------------
     auto score_thresholds = compute_score_thresholds(rows, segs, contigs, (double)o.p_val, o.n_detect_scores);
@@ -505,6 +541,7 @@ int main(int argc, char *argv[]) {
     printf("elapsed seconds for scoring %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
     fflush(stdout);
 
+    pt.lap("thresholds");
     // ---------------- phase 3: alignment of the pairs that pass (main.cpp:563-604) ----------------------------
     std::vector<std::pair<int, int>> pairs_list;  // (seg idx, contig idx), in row order, duplicates kept
     for (auto &r : rows) {
@@ -519,6 +556,7 @@ int main(int argc, char *argv[]) {
     std::vector<Bitmap> contig_used = run_alignment_pass(eng, o, segs, contigs, uniq, score_thresholds, nullptr, false);
     printf("Finished standard alignment. \n");
     fflush(stdout);
+    pt.lap("phase 3 alignment");
 
     // ---------------- phase 4: tip alignment (main.cpp:606-649) ------------------------------------------------
     if (o.do_tip) {
@@ -533,10 +571,13 @@ int main(int argc, char *argv[]) {
         fflush(stdout);
         run_alignment_pass(eng, o, segs, contigs, tip_pairs, tip_thresholds, &contig_used, true);
         printf("Finished tip alignments.\n\n");
+        pt.lap("phase 4 tip alignment");
     }
     printf("elapsed seconds for run %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
     if (getenv("SA_VERBOSE")) fprintf(stderr, "SegAligner(b200): wall %.3f s on %d GPU(s)\n", wall_now() - w0, (int)eng.ctx.size());
     fflush(stdout);
-    eng.close();
+    fflush(stderr);
+    eng.close();  // orderly teardown: abandoning the context (_exit) only moves the cost into the next process start
+    pt.lap("close");
     return 0;
 }

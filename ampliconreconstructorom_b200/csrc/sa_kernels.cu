@@ -57,27 +57,69 @@ __device__ __forceinline__ void lds_u32x2(uint32_t addr, uint32_t &lo, uint32_t 
     asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
 }
 
-// Shared-memory layout of the two powf tables, split so that every lookup is bank-conflict free:
-//   invc[16], logc[16]  : 8-byte entries, 128 B each -> entry i owns banks 2i,2i+1 (a half-warp wavefront never
-//                         sees two different addresses in one bank; equal indices broadcast)
-//   exp_lo[32], exp_hi[32]: 4-byte halves of the exp2 table, 128 B each -> entry e owns bank e
-struct __align__(128) PowTabSmem {
-    double invc[16];
-    double logc[16];
+// ---- shared-memory tables of the powf replay -----------------------------------------------------------------
+// Variant knobs (compile time, measured on B200 -- see DESIGN.md 4.1):
+//   SA_TAB2D   1: one LDS.128 fetches {invc_i, logc_i + (double)k} from a 52x16-entry table indexed by the top
+//                 bits of (ix - IX_LO); removes LEA.HI + I2F.F64 + DADD per evaluation (y0 is the same IEEE sum,
+//                 computed once per table entry).  0: 16-entry invc/logc tables (conflict free) + I2F + DADD.
+//   SA_EXP64   1: exp2 table as 32 x u64, one LDS.64 (entries e, e+16 share banks).  0: split hi/lo, 2 LDS.32.
+#ifndef SA_TAB2D
+#define SA_TAB2D 1
+#endif
+#ifndef SA_EXP64
+#define SA_EXP64 1
+#endif
+
+#if SA_TAB2D
+constexpr int TAB2D_N = 52 * 16;  // (k + 20) * 16 + i
+struct __align__(16) PowTabSmem {  // placed at a 16 KB-aligned SHARED address by the kernels (tab_place)
+    double2 t2d[TAB2D_N];           // {invc, y0}; byte offset = ((u >> 15) & 0x3FF0) stays inside this struct
+    unsigned long long exp64[32];   // at byte 13312
     uint32_t exp_lo[32];
     uint32_t exp_hi[32];
+    unsigned char pad[16384 - TAB2D_N * 16 - 256 - 256];
 };
-static_assert(sizeof(PowTabSmem) == 512, "PowTabSmem layout");
+static_assert(sizeof(PowTabSmem) == 16384, "PowTabSmem layout");
+constexpr uint32_t TAB_EXP_OFF = TAB2D_N * 16;
+#else
+struct __align__(1024) PowTabSmem {
+    double invc[16];
+    double logc[16];
+    unsigned long long exp64[32];  // at byte 256
+    uint32_t exp_lo[32];
+    uint32_t exp_hi[32];
+    unsigned char pad[256];
+};
+static_assert(sizeof(PowTabSmem) == 1024, "PowTabSmem layout");
+constexpr uint32_t TAB_EXP_OFF = 256;
+#endif
+
+// The `stab | offset` addressing needs the table at a shared-window address aligned to its size; static shared
+// variables start at a toolchain-chosen offset, so kernels over-allocate dynamic shared memory and align here.
+constexpr uint32_t TAB_ALIGN = sizeof(PowTabSmem);
+constexpr uint32_t TAB_SMEM_BYTES = 2 * TAB_ALIGN;  // what a kernel must reserve in front of its own buffers
+__device__ __forceinline__ PowTabSmem *tab_place(unsigned char *dyn) {
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(dyn);
+    return reinterpret_cast<PowTabSmem *>(dyn + ((TAB_ALIGN - (base & (TAB_ALIGN - 1))) & (TAB_ALIGN - 1)));
+}
 
 __device__ __forceinline__ void powtab_init(PowTabSmem &t) {
+#if SA_TAB2D
+    for (int e = threadIdx.x; e < TAB2D_N; e += blockDim.x) {
+        const int k = (e >> 4) - 20, i = e & 15;
+        t.t2d[e] = make_double2(c_logtab[i].invc, __dadd_rn(c_logtab[i].logc, (double)k));
+    }
+#else
     if (threadIdx.x < 16) {
         t.invc[threadIdx.x] = c_logtab[threadIdx.x].invc;
         t.logc[threadIdx.x] = c_logtab[threadIdx.x].logc;
     }
+#endif
     if (threadIdx.x >= 32 && threadIdx.x < 64) {
         const unsigned long long v = c_exptab[threadIdx.x - 32];
         t.exp_lo[threadIdx.x - 32] = (uint32_t)v;
         t.exp_hi[threadIdx.x - 32] = (uint32_t)(v >> 32);
+        t.exp64[threadIdx.x - 32] = v;
     }
 }
 
@@ -93,21 +135,25 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 }
 
 // Branch-free replay of powf(ax, 1.2f) for ax inside the fast domain; outside it the result is garbage but the
-// code is still memory-safe (both table indices are masked), so callers evaluate unconditionally and patch the
-// rare out-of-domain lanes afterwards (`bad` tells which).  stab = 32-bit shared address of a PowTabSmem
-// (512-byte aligned, so `stab | offset` == `stab + offset`).
+// code is still memory-safe (every table index is masked), so callers evaluate unconditionally and patch the
+// rare out-of-domain lanes afterwards (u_out >= IX_RANGE tells which).  stab = 32-bit shared address of a
+// PowTabSmem (aligned to its size, so `stab | offset` == `stab + offset`).
 __device__ __forceinline__ float powf12_fast(float ax, uint32_t stab, const double (&pk)[12], uint32_t &u_out) {
     const uint32_t ix = __float_as_uint(ax);
     const uint32_t u = ix - IX_LO;
-    u_out = u;  // u >= IX_RANGE  <=>  outside the fast domain
+    u_out = u;
     const uint32_t kb = u & 0xff800000u;
     const uint32_t iz = ix - kb + (20u << 23);
+    double invc, y0;
+#if SA_TAB2D
+    lds_f64x2(stab | ((u >> 15) & 0x3FF0u), invc, y0);
+#else
     const int k = (int)(u >> 23) - 20;
     const uint32_t a_i = stab | ((u >> 16) & 0x78u);  // 8 * ((u >> 19) & 15)
-    const double invc = lds_f64(a_i);
-    const double logc = lds_f64(a_i + 128);
-    // log2: 9 fp64 ops, then y*log2(x)
-    const double y0 = __dadd_rn(logc, (double)k);
+    invc = lds_f64(a_i);
+    y0 = __dadd_rn(lds_f64(a_i + 128), (double)k);
+#endif
+    // log2: 8 fp64 ops (+ the logc + k sum, folded into the table when SA_TAB2D), then y*log2(x)
     const double z = (double)__uint_as_float(iz);
     const double r = __fma_rn(z, invc, -1.0);
     double y = __fma_rn(r, pk[0], pk[1]);
@@ -123,9 +169,15 @@ __device__ __forceinline__ float powf12_fast(float ax, uint32_t stab, const doub
     const uint32_t ki = (uint32_t)__double2loint(kd);
     kd = __dadd_rn(kd, pk[10]);
     const double rr = __dadd_rn(xd, -kd);
-    const uint32_t a_e = (stab + 256u) | ((ki << 2) & 0x7Cu);
-    const uint32_t tlo = lds_u32(a_e);
-    const uint32_t thi = lds_u32(a_e + 128) + (ki << 15);  // t += ki << 47
+    uint32_t tlo, thi;
+#if SA_EXP64
+    lds_u32x2((stab + TAB_EXP_OFF) | ((ki << 3) & 0xF8u), tlo, thi);
+#else
+    const uint32_t a_e = (stab + TAB_EXP_OFF + 256u) | ((ki << 2) & 0x7Cu);
+    tlo = lds_u32(a_e);
+    thi = lds_u32(a_e + 128);
+#endif
+    thi += ki << 15;  // t += ki << 47
     const double sc = __hiloint2double((int)thi, (int)tlo);
     const double zz = __fma_rn(rr, pk[6], pk[7]);
     const double rr2 = __dmul_rn(rr, rr);
@@ -178,7 +230,8 @@ constexpr int RING_W = 40;  // 6 halo rows + 32 lanes + 2 pad
 template <bool STORE, bool SWAP, int NW, int MINB>
 __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_kernel(const FillParams P) {
     constexpr int WPC = (NW == 1) ? FILL_WARPS : NW;  // warps per CTA
-    __shared__ PowTabSmem s_tab;
+    extern __shared__ unsigned char s_dyn[];
+    PowTabSmem &s_tab = *tab_place(s_dyn);
     __shared__ float s_ring[WPC][LB][RING_W];
     __shared__ float s_xbuf[WPC][2][8];
     __shared__ unsigned long long s_next;
@@ -778,7 +831,8 @@ __global__ void __launch_bounds__(256) detect_kernel(const DetectParams P) {
 }
 
 __global__ void powf12_kernel(const float *x, long long n, float *out, int fast) {
-    __shared__ PowTabSmem s_tab;
+    extern __shared__ unsigned char s_dyn[];
+    PowTabSmem &s_tab = *tab_place(s_dyn);
     powtab_init(s_tab);
     __syncthreads();
     const uint32_t a_tab = (uint32_t)__cvta_generic_to_shared(&s_tab);
@@ -791,7 +845,8 @@ __global__ void powf12_kernel(const float *x, long long n, float *out, int fast)
 }
 
 __global__ void powf12_range_kernel(uint32_t lo, uint32_t hi, float *out_fast, float *out_generic) {
-    __shared__ PowTabSmem s_tab;
+    extern __shared__ unsigned char s_dyn[];
+    PowTabSmem &s_tab = *tab_place(s_dyn);
     powtab_init(s_tab);
     __syncthreads();
     const uint32_t a_tab = (uint32_t)__cvta_generic_to_shared(&s_tab);
@@ -831,13 +886,20 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *sink, int iters)
 template <int NW, int MINB>
 static void launch_fill_t(const FillParams &p, bool store, bool swap, int n_ctas, cudaStream_t st) {
     dim3 g(n_ctas), b((NW == 1 ? FILL_WARPS : NW) * 32);
+    const size_t sm = TAB_SMEM_BYTES;
+#define SA_LAUNCH_FILL(S_, W_)                                                                                   \
+    do {                                                                                                         \
+        cudaFuncSetAttribute(fill_kernel<S_, W_, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        fill_kernel<S_, W_, NW, MINB><<<g, b, sm, st>>>(p);                                                      \
+    } while (0)
     if (store) {
-        if (swap) fill_kernel<true, true, NW, MINB><<<g, b, 0, st>>>(p);
-        else fill_kernel<true, false, NW, MINB><<<g, b, 0, st>>>(p);
+        if (swap) SA_LAUNCH_FILL(true, true);
+        else SA_LAUNCH_FILL(true, false);
     } else {
-        if (swap) fill_kernel<false, true, NW, MINB><<<g, b, 0, st>>>(p);
-        else fill_kernel<false, false, NW, MINB><<<g, b, 0, st>>>(p);
+        if (swap) SA_LAUNCH_FILL(false, true);
+        else SA_LAUNCH_FILL(false, false);
     }
+#undef SA_LAUNCH_FILL
 }
 void launch_fill(const FillParams &p, bool store, bool swap, bool coop, int n_ctas, cudaStream_t st) {
     if (coop) launch_fill_t<COOP_WARPS, 1>(p, store, swap, n_ctas, st);
@@ -864,17 +926,17 @@ void launch_detect(const DetectParams &p, cudaStream_t st) {
     if (p.n_problems > 0) detect_kernel<<<(unsigned)p.n_problems, 256, 0, st>>>(p);
 }
 void launch_powf12(const float *x, long long n, float *out, int fast, cudaStream_t st) {
-    powf12_kernel<<<148 * 8, 256, 0, st>>>(x, n, out, fast);
+    powf12_kernel<<<148 * 4, 256, TAB_SMEM_BYTES, st>>>(x, n, out, fast);
 }
 void launch_powf12_range(uint32_t lo, uint32_t hi, float *out_fast, float *out_generic, cudaStream_t st) {
-    powf12_range_kernel<<<148 * 8, 256, 0, st>>>(lo, hi, out_fast, out_generic);
+    powf12_range_kernel<<<148 * 4, 256, TAB_SMEM_BYTES, st>>>(lo, hi, out_fast, out_generic);
 }
 void launch_dfma_peak(double *sink, int iters, int n_ctas, cudaStream_t st) {
     dfma_peak_kernel<<<n_ctas, 256, 0, st>>>(sink, iters);
 }
 int fill_ctas_per_sm() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<false, false, 1, FILL_MINB>, FILL_WARPS * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<false, false, 1, FILL_MINB>, FILL_WARPS * 32, TAB_SMEM_BYTES);
     return n > 0 ? n : 1;
 }
 

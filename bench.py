@@ -331,7 +331,8 @@ def main():
                                              f"-nthreads={n_threads}"}
         elif world == 1:
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
-                                   "sample": "oracle/_ref/SegAligner_ref not present"}
+                                   "sample": "skipped (--no-cpu-baseline)" if args.no_cpu_baseline
+                                   else "oracle/_ref/SegAligner_ref not present"}
         print(json.dumps(out))
     plan.destroy()
     ctx.close()
