@@ -69,13 +69,15 @@ struct sa_ctx {
     int ctas_per_sm = 1;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // cooperative (large-problem) launches run beside the bulk kernel
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream3 = nullptr;  // cluster-cooperative (huge-problem) launches
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
+    int n_clusters = 0;              // co-resident clusters of the cluster variant (0 = unavailable)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_user[2] = {nullptr, nullptr};
     std::string err;
     MapSetHost sides[2];
     DevBuf d_problems, d_order, d_results, d_halo, d_counter, d_cell_off, d_S, d_code, d_used, d_path_off, d_path_j,
-        d_path_q, d_path_s, d_tmp0, d_tmp1, d_tmp2, d_halo2, d_row_off, d_rowmax_s, d_rowmax_q, d_prev32;
+        d_path_q, d_path_s, d_tmp0, d_tmp1, d_tmp2, d_halo2, d_row_off, d_rowmax_s, d_rowmax_q, d_prev32, d_halo3, d_mail;
     sa_timing timing = {0, 0, 0, 0};
     size_t store_budget_cells = 0;  // max cells of stored matrices per chunk
 };
@@ -120,9 +122,11 @@ void build_label_ops(const float *pos, const float *prob, int n, LabelOps *out) 
 //   bulk   -> one warp per problem, largest first (LPT) via a counting sort on a 1/8-octave size class, O(n).
 // A problem is "large" when one warp would need longer for it than the whole batch needs on the whole GPU
 // (cells_p * n_warp_slots > alpha * total_cells), so that no single problem can become the tail.
+//   huge   -> cluster-cooperative kernel (CLUSTER_CTAS SMs per problem) when even ONE SM would need longer for
+//             the problem than the whole batch needs on the whole GPU (cells_p * n_sms > alpha * total_cells).
 struct Plan {
-    std::vector<int32_t> order;  // bulk problems first, then the large ones
-    int64_t n_bulk = 0, n_large = 0;
+    std::vector<int32_t> order;  // bulk problems first, then the large ones, then the huge ones
+    int64_t n_bulk = 0, n_large = 0, n_huge = 0;
     double total_cells = 0;
 };
 
@@ -139,9 +143,24 @@ void build_plan(const sa_ctx *c, const sa_problem *pr, int64_t n, int n_warp_slo
     double alpha = 0.5;
     if (const char *e = getenv("SA_COOP_ALPHA")) alpha = atof(e);
     const double thresh = alpha * total / (double)n_warp_slots;
-    std::vector<std::pair<double, int32_t>> large;
+    bool no_cluster = false;
+    if (const char *e = getenv("SA_NO_CLUSTER")) no_cluster = atoi(e) != 0;
+    double huge_min_cells = 4096.0 * 64.0;
+    if (const char *e = getenv("SA_HUGE_MIN_CELLS")) huge_min_cells = atof(e);
+    // the cluster wavefront pays a cluster barrier per step and idles when nx < its 128 warps, so it is reserved for
+    // problems that would otherwise be the tail: single-SM time > alpha_huge x the batch's ideal makespan
+    double alpha_huge = 2.0;
+    if (const char *e = getenv("SA_HUGE_ALPHA")) alpha_huge = atof(e);
+    const double thresh_huge =
+        (c->n_clusters > 0 && alpha > 0 && !no_cluster) ? std::min(alpha, alpha_huge) * 0 + (alpha < 1e-6 ? alpha : alpha_huge) * total / (double)c->n_sms : 1e300;
+    std::vector<std::pair<double, int32_t>> large, huge;
     for (int64_t k = 0; k < n; k++) {
         const double cl = cells[(size_t)k];
+        if (cl > thresh_huge && cl >= huge_min_cells) {
+            huge.emplace_back(-cl, (int32_t)k);
+            cls[(size_t)k] = 0xffff;
+            continue;
+        }
         if (alpha > 0 && cl > thresh && cl >= 32.0 * 64.0) {
             large.emplace_back(-cl, (int32_t)k);
             cls[(size_t)k] = 0xffff;
@@ -154,13 +173,16 @@ void build_plan(const sa_ctx *c, const sa_problem *pr, int64_t n, int n_warp_slo
     }
     for (int b = 0; b < NB; b++) cnt[b + 1] += cnt[b];
     plan.n_large = (int64_t)large.size();
-    plan.n_bulk = n - plan.n_large;
+    plan.n_huge = (int64_t)huge.size();
+    plan.n_bulk = n - plan.n_large - plan.n_huge;
     plan.total_cells = total;
     plan.order.resize((size_t)n);
     for (int64_t k = 0; k < n; k++)
         if (cls[(size_t)k] != 0xffff) plan.order[(size_t)cnt[cls[(size_t)k]]++] = (int32_t)k;
     std::sort(large.begin(), large.end());
+    std::sort(huge.begin(), huge.end());
     for (size_t k = 0; k < large.size(); k++) plan.order[(size_t)plan.n_bulk + k] = large[k].second;
+    for (size_t k = 0; k < huge.size(); k++) plan.order[(size_t)(plan.n_bulk + plan.n_large) + k] = huge[k].second;
 }
 
 }  // namespace
@@ -210,26 +232,44 @@ int prepare_fill(sa_ctx *ctx, FillParams &P, const sa_mode *mode) {
     P.halo_stride = (long long)std::max(ctx->sides[1].max_labels, 1) * 8;
     CU(ctx->d_halo.reserve(sizeof(float) * (size_t)(n_warps * P.halo_stride)));
     CU(ctx->d_halo2.reserve(sizeof(float) * (size_t)((long long)ctx->n_sms * P.halo_stride)));
-    CU(ctx->d_counter.reserve(2 * sizeof(unsigned long long)));
+    CU(ctx->d_counter.reserve(4 * sizeof(unsigned long long)));
+    if (ctx->n_clusters > 0) {
+        CU(ctx->d_halo3.reserve(sizeof(float) * (size_t)((long long)ctx->n_clusters * P.halo_stride)));
+        CU(ctx->d_mail.reserve(sizeof(float) * (size_t)ctx->n_clusters * CLUSTER_MAIL_FLOATS));
+    }
     return SA_OK;
 }
 
 // Launch the fill over an uploaded problem list whose device order array holds n_bulk bulk problems followed
 // by n_large large ones.  The two kernels run concurrently (stream / stream2) and join on `stream`.
-int launch_fill_classes(sa_ctx *ctx, FillParams P, const int32_t *d_order, int64_t n_bulk, int64_t n_large,
-                        bool store, bool swap) {
+int launch_fill_classes(sa_ctx *ctx, FillParams P, const int32_t *d_order, const Plan &plan, bool store, bool swap) {
+    const int64_t n_bulk = plan.n_bulk, n_large = plan.n_large, n_huge = plan.n_huge;
     unsigned long long *counters = ctx->d_counter.as<unsigned long long>();
-    CU(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     int launches = 0;
+    if (n_large > 0 || n_huge > 0) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    if (n_huge > 0) {  // longest first: clusters of CLUSTER_CTAS SMs
+        CU(cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork, 0));
+        FillParams H = P;
+        H.order = d_order + n_bulk + n_large;
+        H.n_problems = n_huge;
+        H.counter = counters + 2;
+        H.halo = ctx->d_halo3.as<float>();
+        H.cluster_mail = ctx->d_mail.as<float>();
+        const int ncl = (int)std::min<int64_t>(n_huge, ctx->n_clusters);
+        launch_fill(H, store, swap, 2, ncl * CLUSTER_CTAS, ctx->stream3);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev_join3, ctx->stream3));
+        launches++;
+    }
     if (n_large > 0) {
-        CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
         CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
         FillParams L = P;
         L.order = d_order + n_bulk;
         L.n_problems = n_large;
         L.counter = counters + 1;
         L.halo = ctx->d_halo2.as<float>();
-        launch_fill(L, store, swap, true, (int)std::min<int64_t>(n_large, ctx->n_sms), ctx->stream2);
+        launch_fill(L, store, swap, 1, (int)std::min<int64_t>(n_large, ctx->n_sms), ctx->stream2);
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
         launches++;
@@ -240,11 +280,12 @@ int launch_fill_classes(sa_ctx *ctx, FillParams P, const int32_t *d_order, int64
         P.counter = counters;
         P.halo = ctx->d_halo.as<float>();
         const int64_t want = (n_bulk + FILL_WARPS - 1) / FILL_WARPS;
-        launch_fill(P, store, swap, false, (int)std::min<int64_t>(want, n_fill_ctas(ctx)), ctx->stream);
+        launch_fill(P, store, swap, 0, (int)std::min<int64_t>(want, n_fill_ctas(ctx)), ctx->stream);
         CU(cudaGetLastError());
         launches++;
     }
     if (n_large > 0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    if (n_huge > 0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join3, 0));
     ctx->timing.n_launches += launches;
     return SA_OK;
 }
@@ -280,6 +321,9 @@ int sa_ctx_create(int device, sa_ctx **out) {
         return SA_ECUDA;
     }
     cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_join3, cudaEventDisableTiming);
+    ctx->n_clusters = max_clusters();
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     for (auto &e : ctx->ev_user) cudaEventCreate(&e);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
@@ -287,8 +331,8 @@ int sa_ctx_create(int device, sa_ctx **out) {
     ctx->ctas_per_sm = fill_ctas_per_sm();
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    // stored matrices cost 5 bytes per cell; keep a chunk below a quarter of free memory and below 2^31 cells
-    ctx->store_budget_cells = std::min<size_t>(free_b / 4 / 5, (size_t)1 << 31);
+    // stored matrices cost 5 bytes per cell; keep a chunk below a third of free memory
+    ctx->store_budget_cells = free_b / 3 / 5;
     if (const char *e = getenv("SA_STORE_BUDGET_CELLS")) ctx->store_budget_cells = (size_t)atoll(e);
     *out = ctx;
     return SA_OK;
@@ -307,7 +351,7 @@ void sa_ctx_destroy(sa_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->d_problems, &ctx->d_order,  &ctx->d_results,  &ctx->d_halo,   &ctx->d_counter, &ctx->d_cell_off,
                       &ctx->d_S,        &ctx->d_code,   &ctx->d_used,     &ctx->d_path_off, &ctx->d_path_j,  &ctx->d_path_q,
                       &ctx->d_path_s,   &ctx->d_tmp0,   &ctx->d_tmp1,     &ctx->d_tmp2,     &ctx->d_halo2,  &ctx->d_row_off, &ctx->d_rowmax_s,
-                      &ctx->d_rowmax_q, &ctx->d_prev32};
+                      &ctx->d_rowmax_q, &ctx->d_prev32, &ctx->d_halo3, &ctx->d_mail};
     for (auto b : bufs) b->release();
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -315,7 +359,9 @@ void sa_ctx_destroy(sa_ctx *ctx) {
         if (e) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_join3) cudaEventDestroy(ctx->ev_join3);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -412,8 +458,7 @@ int sa_plan_score(sa_ctx *ctx, sa_plan *pl, const sa_mode *mode) {
     P.results = pl->d_results.as<sa_result>();
     ctx->timing = {-1.0f, 0, 0, 0};  // fill_ms resolved lazily by sa_get_timing
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    rc = launch_fill_classes(ctx, P, pl->d_order.as<int32_t>(), pl->plan.n_bulk, pl->plan.n_large, false,
-                             mode->swap_b_x != 0);
+    rc = launch_fill_classes(ctx, P, pl->d_order.as<int32_t>(), pl->plan, false, mode->swap_b_x != 0);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     return SA_OK;
@@ -430,7 +475,7 @@ int sa_plan_results(sa_ctx *ctx, sa_plan *pl, sa_result *results) {
 int sa_plan_info(const sa_plan *pl, int64_t *n_bulk, int64_t *n_large, double *total_cells) {
     if (!pl) return SA_EINVAL;
     if (n_bulk) *n_bulk = pl->plan.n_bulk;
-    if (n_large) *n_large = pl->plan.n_large;
+    if (n_large) *n_large = pl->plan.n_large + pl->plan.n_huge;
     if (total_cells) *total_cells = pl->plan.total_cells;
     return SA_OK;
 }
@@ -528,7 +573,7 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
             CU(cudaGetLastError());
             ctx->timing.n_launches += 1;
         } else {
-            rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan.n_bulk, plan.n_large, true, mode->swap_b_x != 0);
+            rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan, true, mode->swap_b_x != 0);
             if (rc) return rc;
         }
         CU(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -563,6 +608,9 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
         ctx->timing.fill_ms += a;
         ctx->timing.post_ms += b;
         ctx->timing.n_launches += 1;
+        if (getenv("SA_VERBOSE"))
+            fprintf(stderr, "  sa_align_batch chunk: %lld problems, %.3e cells, fill %.2f ms (large %lld), traceback %.2f ms\n",
+                    (long long)m, (double)cells, a, (long long)(plan.n_large * 1000 + plan.n_huge), b);
         k0 = k1;
     }
     return SA_OK;
@@ -689,7 +737,7 @@ int sa_detect_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
             CU(cudaGetLastError());
             ctx->timing.n_launches += 1;
         } else {
-            rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan.n_bulk, plan.n_large, true, mode->swap_b_x != 0);
+            rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan, true, mode->swap_b_x != 0);
             if (rc) return rc;
         }
         CU(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -723,6 +771,9 @@ int sa_detect_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
         ctx->timing.fill_ms += a;
         ctx->timing.post_ms += b;
         ctx->timing.n_launches += 1;
+        if (getenv("SA_VERBOSE"))
+            fprintf(stderr, "  sa_detect_batch chunk: %lld problems, %.3e cells, fill %.2f ms (large %lld), harvest %.2f ms\n",
+                    (long long)m, (double)cells, a, (long long)(plan.n_large * 1000 + plan.n_huge), b);
         k0 = k1;
     }
     return SA_OK;

@@ -22,6 +22,8 @@
 // (dj = j-i ascending, dq = q-p ascending) and replace on '>=', which selects the same predecessor.
 #include <cstdio>
 #include <math_constants.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 #include "sa_kernels.cuh"
 #include "powf12.cuh"
 
@@ -69,8 +71,11 @@ __device__ __forceinline__ void lds_u32x2(uint32_t addr, uint32_t &lo, uint32_t 
 #ifndef SA_EXP64
 #define SA_EXP64 1
 #endif
+#ifndef SA_BREADTH
+#define SA_BREADTH 1  // breadth-first scheduling of the 6 powf chains of a look-back row
+#endif
 
-#if SA_TAB2D
+#if SA_TAB2D == 1
 constexpr int TAB2D_N = 52 * 16;  // (k + 20) * 16 + i
 struct __align__(16) PowTabSmem {  // placed at a 16 KB-aligned SHARED address by the kernels (tab_place)
     double2 t2d[TAB2D_N];           // {invc, y0}; byte offset = ((u >> 15) & 0x3FF0) stays inside this struct
@@ -81,6 +86,22 @@ struct __align__(16) PowTabSmem {  // placed at a 16 KB-aligned SHARED address b
 };
 static_assert(sizeof(PowTabSmem) == 16384, "PowTabSmem layout");
 constexpr uint32_t TAB_EXP_OFF = TAB2D_N * 16;
+#elif SA_TAB2D == 2
+// y0 = logc_i + k from an 8-byte 2-D table (byte offset (u >> 16) & 0x1FF8), invc from the conflict-free 16-entry
+// table: two LDS.64 instead of one LDS.128 -- fewer shared-memory wavefronts (the 16-byte 2-D entries conflict
+// 2-3 ways per quarter-warp), one more instruction.
+constexpr int TAB2D_N = 52 * 16;
+struct __align__(16) PowTabSmem {
+    double y0[1024];                // 8 KB (832 used)
+    double invc[16];                // at 8192
+    unsigned char pad0[128];
+    unsigned long long exp64[32];   // at 8448
+    uint32_t exp_lo[32];
+    uint32_t exp_hi[32];
+    unsigned char pad[16384 - 8192 - 256 - 256 - 256];
+};
+static_assert(sizeof(PowTabSmem) == 16384, "PowTabSmem layout");
+constexpr uint32_t TAB_EXP_OFF = 8448;
 #else
 struct __align__(1024) PowTabSmem {
     double invc[16];
@@ -104,11 +125,17 @@ __device__ __forceinline__ PowTabSmem *tab_place(unsigned char *dyn) {
 }
 
 __device__ __forceinline__ void powtab_init(PowTabSmem &t) {
-#if SA_TAB2D
+#if SA_TAB2D == 1
     for (int e = threadIdx.x; e < TAB2D_N; e += blockDim.x) {
         const int k = (e >> 4) - 20, i = e & 15;
         t.t2d[e] = make_double2(c_logtab[i].invc, __dadd_rn(c_logtab[i].logc, (double)k));
     }
+#elif SA_TAB2D == 2
+    for (int e = threadIdx.x; e < 1024; e += blockDim.x) {
+        const int k = (e >> 4) - 20, i = e & 15;
+        t.y0[e] = e < TAB2D_N ? __dadd_rn(c_logtab[i].logc, (double)k) : 0.0;
+    }
+    if (threadIdx.x < 16) t.invc[threadIdx.x] = c_logtab[threadIdx.x].invc;
 #else
     if (threadIdx.x < 16) {
         t.invc[threadIdx.x] = c_logtab[threadIdx.x].invc;
@@ -145,8 +172,12 @@ __device__ __forceinline__ float powf12_fast(float ax, uint32_t stab, const doub
     const uint32_t kb = u & 0xff800000u;
     const uint32_t iz = ix - kb + (20u << 23);
     double invc, y0;
-#if SA_TAB2D
+#if SA_TAB2D == 1
     lds_f64x2(stab | ((u >> 15) & 0x3FF0u), invc, y0);
+#elif SA_TAB2D == 2
+    const uint32_t t16 = u >> 16;
+    y0 = lds_f64(stab | (t16 & 0x1FF8u));
+    invc = lds_f64((stab + 8192u) | (t16 & 0x78u));
 #else
     const int k = (int)(u >> 23) - 20;
     const uint32_t a_i = stab | ((u >> 16) & 0x78u);  // 8 * ((u >> 19) & 15)
@@ -185,6 +216,83 @@ __device__ __forceinline__ float powf12_fast(float ax, uint32_t stab, const doub
     yy = __fma_rn(zz, rr2, yy);
     yy = __dmul_rn(yy, sc);
     return __double2float_rn(yy);
+}
+
+// Breadth-first replay of NC independent powf(ax,1.2f) chains: every stage is applied to all chains before the
+// next one, so that dependent fp64 instructions of one chain are NC issue slots apart (DFMA latency ~10 cycles,
+// one fp64 warp-instruction per 2 cycles per SM sub-partition).  Same arithmetic as powf12_fast.
+template <int NC>
+__device__ __forceinline__ void powf12_fastN(const float (&ax)[NC], uint32_t stab, const double (&pk)[12],
+                                             float (&out)[NC], uint32_t (&uo)[NC]) {
+    uint32_t iz[NC], ki[NC], tlo[NC], thi[NC];
+    double invc[NC], y0[NC], r[NC], y[NC], p[NC], r2[NC], q[NC], xd[NC], kd[NC], rr[NC], zz[NC], yy[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const uint32_t ix = __float_as_uint(ax[c]);
+        const uint32_t u = ix - IX_LO;
+        uo[c] = u;
+        iz[c] = ix - (u & 0xff800000u) + (20u << 23);
+#if SA_TAB2D == 1
+        lds_f64x2(stab | ((u >> 15) & 0x3FF0u), invc[c], y0[c]);
+#elif SA_TAB2D == 2
+        const uint32_t t16 = u >> 16;
+        y0[c] = lds_f64(stab | (t16 & 0x1FF8u));
+        invc[c] = lds_f64((stab + 8192u) | (t16 & 0x78u));
+#else
+        const int k = (int)(u >> 23) - 20;
+        const uint32_t a_i = stab | ((u >> 16) & 0x78u);
+        invc[c] = lds_f64(a_i);
+        y0[c] = __dadd_rn(lds_f64(a_i + 128), (double)k);
+#endif
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) r[c] = __fma_rn((double)__uint_as_float(iz[c]), invc[c], -1.0);
+#pragma unroll
+    for (int c = 0; c < NC; c++) y[c] = __fma_rn(r[c], pk[0], pk[1]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) p[c] = __fma_rn(r[c], pk[2], pk[3]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) r2[c] = __dmul_rn(r[c], r[c]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) q[c] = __fma_rn(r[c], pk[4], y0[c]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) q[c] = __fma_rn(r2[c], p[c], q[c]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) r2[c] = __dmul_rn(r2[c], r2[c]);  // r4
+#pragma unroll
+    for (int c = 0; c < NC; c++) y[c] = __fma_rn(y[c], r2[c], q[c]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) xd[c] = __dmul_rn(pk[5], y[c]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) kd[c] = __dadd_rn(xd[c], pk[9]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        ki[c] = (uint32_t)__double2loint(kd[c]);
+#if SA_EXP64
+        lds_u32x2((stab + TAB_EXP_OFF) | ((ki[c] << 3) & 0xF8u), tlo[c], thi[c]);
+#else
+        const uint32_t a_e = (stab + TAB_EXP_OFF + 256u) | ((ki[c] << 2) & 0x7Cu);
+        tlo[c] = lds_u32(a_e);
+        thi[c] = lds_u32(a_e + 128);
+#endif
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) kd[c] = __dadd_rn(kd[c], pk[10]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) rr[c] = __dadd_rn(xd[c], -kd[c]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) zz[c] = __fma_rn(rr[c], pk[6], pk[7]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) yy[c] = __fma_rn(rr[c], pk[8], 1.0);
+#pragma unroll
+    for (int c = 0; c < NC; c++) rr[c] = __dmul_rn(rr[c], rr[c]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) yy[c] = __fma_rn(zz[c], rr[c], yy[c]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const double sc = __hiloint2double((int)(thi[c] + (ki[c] << 15)), (int)tlo[c]);
+        out[c] = __double2float_rn(__dmul_rn(yy[c], sc));
+    }
 }
 
 // Whole-cell evaluation through the generic powf path, same candidate order and tie rule as the fast path.
@@ -227,9 +335,15 @@ constexpr int RING_W = 40;  // 6 halo rows + 32 lanes + 2 pad
 //             strip s-1 at columns < q).  One __syncthreads per step; bottom rows travel through a
 //             double-buffered shared exchange (warp w-1 -> w) and, for the wrap-around NW-1 -> 0, through the
 //             L2-resident halo scratch.  A round takes R = max(nx, NW) steps so the wrap-around is never early.
-template <bool STORE, bool SWAP, int NW, int MINB>
+//   CS  > 1 : a thread-block CLUSTER of CS such CTAs (CS*NW warps on CS SMs) sweeps one huge problem: same wavefront,
+//             the step barrier becomes a cluster barrier, bottom rows cross CTA boundaries through a small
+//             L2-resident mailbox.  Used for chromosome-sized problems whose single-SM time would be the tail.
+template <bool STORE, bool SWAP, int NW, int MINB, int CS>
 __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_kernel(const FillParams P) {
     constexpr int WPC = (NW == 1) ? FILL_WARPS : NW;  // warps per CTA
+    constexpr int NWT = NW * CS;                        // warps in the wavefront
+    static_assert(CS == 1 || NW > 1, "clusters only for the cooperative shape");
+    const int crank = (CS > 1) ? (int)cg::this_cluster().block_rank() : 0;
     extern __shared__ unsigned char s_dyn[];
     PowTabSmem &s_tab = *tab_place(s_dyn);
     __shared__ float s_ring[WPC][LB][RING_W];
@@ -248,20 +362,31 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
     const uint32_t a_my = (uint32_t)__cvta_generic_to_shared(&s_ring[warp][0][6 + lane]);
     const uint32_t a_halo = (uint32_t)__cvta_generic_to_shared(&s_ring[warp][0][lane]);  // lanes 0..5 only
 
-    const long long gunit = (NW == 1) ? ((long long)blockIdx.x * FILL_WARPS + warp) : (long long)blockIdx.x;
+    const long long gunit = (NW == 1) ? ((long long)blockIdx.x * FILL_WARPS + warp) : (long long)(blockIdx.x / CS);
     float *halo = P.halo + gunit * P.halo_stride;
-    const int w = (NW == 1) ? 0 : warp;  // position in the wavefront
+    const int w = (NW == 1) ? 0 : crank * NW + warp;  // position in the wavefront
+    // cluster mailbox (CS > 1): [0..CS) next-problem broadcast slot 0, then per-CTA exchange [CS][2][8] floats,
+    // then per-CTA start candidates
+    float *cmail = (CS > 1) ? P.cluster_mail + gunit * CLUSTER_MAIL_FLOATS : nullptr;
 
     for (;;) {
         unsigned long long t_idx = 0;
         if (NW == 1) {
             if (lane == 0) t_idx = atomicAdd(P.counter, 1ull);
             t_idx = __shfl_sync(0xffffffffu, t_idx, 0);
-        } else {
+        } else if (CS == 1) {
             __syncthreads();
             if (threadIdx.x == 0) s_next = atomicAdd(P.counter, 1ull);
             __syncthreads();
             t_idx = s_next;
+        } else {
+            cg::this_cluster().sync();
+            if (crank == 0 && threadIdx.x == 0) {
+                const unsigned long long v = atomicAdd(P.counter, 1ull);
+                __stcg(reinterpret_cast<unsigned long long *>(cmail), v);
+            }
+            cg::this_cluster().sync();
+            t_idx = __ldcg(reinterpret_cast<const unsigned long long *>(cmail));
         }
         if (t_idx >= (unsigned long long)P.n_problems) break;
         const long long pidx = P.order ? P.order[t_idx] : (long long)t_idx;
@@ -287,9 +412,9 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         long long st_ord = 0x7fffffffffffffffll;
 
         const int nstrips = (nb + 31) >> 5;
-        const int R = (NW == 1) ? nx : (nx > NW ? nx : NW);  // steps per round
-        const int rounds = (nstrips + NW - 1) / NW;
-        const long long T = (long long)rounds * R + (NW - 1);
+        const int R = (NW == 1) ? nx : (nx > NWT ? nx : NWT);  // steps per round
+        const int rounds = (nstrips + NWT - 1) / NWT;
+        const long long T = (long long)rounds * R + (NWT - 1);
 
         // per-warp sweep state
         int strip = w;
@@ -349,7 +474,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                 // rows above the strip at column q (bottom rows of strip-1)
                 if (strip > 0 && lane < 6) {
                     if (NW == 1 || w == 0) hv = __ldcg(halo + (long long)q * 8 + lane);
-                    else hv = s_xbuf[w - 1][(t - 1) & 1][lane];
+                    else if (CS > 1 && warp == 0) hv = __ldcg(cmail + 16 + ((crank - 1) * 2 + ((t - 1) & 1)) * 8 + lane);
+                    else hv = s_xbuf[warp - 1][(t - 1) & 1][lane];
                 }
 
                 float init;
@@ -361,14 +487,19 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                 uint32_t umax = 0;
 #pragma unroll
                 for (int dj = 1; dj <= LB; dj++) {
-                    float delta[LB], sc[LB];
+                    float delta[LB], sc[LB], discrep[LB];
                     uint32_t u[LB];
 #pragma unroll
                     for (int dq = 1; dq <= LB; dq++) {
                         sc[dq - 1] = lds_f32(pc[dq - 1] - dj * 4);
-                        const float discrep = fabsf(__fsub_rn(db[dj - 1], dx[dq - 1]));
-                        delta[dq - 1] = powf12_fast(discrep, a_tab, P.pk, u[dq - 1]);
+                        discrep[dq - 1] = fabsf(__fsub_rn(db[dj - 1], dx[dq - 1]));
                     }
+#if SA_BREADTH
+                    powf12_fastN<LB>(discrep, a_tab, P.pk, delta, u);
+#else
+#pragma unroll
+                    for (int dq = 1; dq <= LB; dq++) delta[dq - 1] = powf12_fast(discrep[dq - 1], a_tab, P.pk, u[dq - 1]);
+#endif
                     umax = __vimax3_u32(umax, __vimax3_u32(u[0], u[1], u[2]), __vimax3_u32(u[3], u[4], u[5]));
 #pragma unroll
                     for (int dq = 1; dq <= LB; dq++) {
@@ -408,12 +539,14 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                 sts_f32(a_my + slot * RING_W * 4, rv);
                 if (lane < 6) sts_f32(a_halo + slot * RING_W * 4, hv);
                 if (lane >= 26) {
-                    if (NW == 1 || w == NW - 1) __stcg(halo + (long long)q * 8 + (lane - 26), rv);
-                    else s_xbuf[w][t & 1][lane - 26] = rv;
+                    if (NW == 1 || w == NWT - 1) __stcg(halo + (long long)q * 8 + (lane - 26), rv);
+                    else if (CS > 1 && warp == NW - 1) __stcg(cmail + 16 + (crank * 2 + (t & 1)) * 8 + (lane - 26), rv);
+                    else s_xbuf[warp][t & 1][lane - 26] = rv;
                 }
             }
             if (NW == 1) __syncwarp();
-            else __syncthreads();
+            else if (CS == 1) __syncthreads();
+            else cg::this_cluster().sync();
             if (active) {
                 if (row_ok) {
                     if (STORE) {
@@ -461,7 +594,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                 q++;
                 if (q == R) {
                     q = 0;
-                    strip += NW;
+                    strip += NWT;
                 }
             }
         }
@@ -502,8 +635,33 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     }
                 }
             }
+            if (CS > 1) {  // per-CTA candidates through the mailbox, CTA 0 picks the winner
+                float *slot = cmail + 16 + CS * 16 + crank * 8;
+                if (threadIdx.x == 0) {
+                    __stcg(slot + 0, st_s);
+                    __stcg(reinterpret_cast<int *>(slot) + 1, st_j);
+                    __stcg(reinterpret_cast<int *>(slot) + 2, st_q);
+                    __stcg(reinterpret_cast<long long *>(slot) + 2, st_ord);
+                }
+                cg::this_cluster().sync();
+                if (crank == 0 && threadIdx.x == 0) {
+                    for (int k = 1; k < CS; k++) {
+                        const float *o = cmail + 16 + CS * 16 + k * 8;
+                        const float os = __ldcg(o);
+                        const int oj = __ldcg(reinterpret_cast<const int *>(o) + 1);
+                        const int oq = __ldcg(reinterpret_cast<const int *>(o) + 2);
+                        const long long oo = __ldcg(reinterpret_cast<const long long *>(o) + 2);
+                        if (oj >= 0 && (st_j < 0 || os > st_s || (os == st_s && oo < st_ord))) {
+                            st_s = os;
+                            st_j = oj;
+                            st_q = oq;
+                            st_ord = oo;
+                        }
+                    }
+                }
+            }
         }
-        if ((NW == 1 && lane == 0) || (NW > 1 && threadIdx.x == 0)) {
+        if ((NW == 1 && lane == 0) || (NW > 1 && threadIdx.x == 0 && crank == 0)) {
             sa_result res;
             if (P.start_mode == SA_START_END) {
                 res.j = nb - 1;
@@ -883,14 +1041,25 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *sink, int iters)
     if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
 }
 
-template <int NW, int MINB>
+template <int NW, int MINB, int CS>
 static void launch_fill_t(const FillParams &p, bool store, bool swap, int n_ctas, cudaStream_t st) {
-    dim3 g(n_ctas), b((NW == 1 ? FILL_WARPS : NW) * 32);
     const size_t sm = TAB_SMEM_BYTES;
-#define SA_LAUNCH_FILL(S_, W_)                                                                                   \
-    do {                                                                                                         \
-        cudaFuncSetAttribute(fill_kernel<S_, W_, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-        fill_kernel<S_, W_, NW, MINB><<<g, b, sm, st>>>(p);                                                      \
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_ctas);
+    cfg.blockDim = dim3((NW == 1 ? FILL_WARPS : NW) * 32);
+    cfg.dynamicSmemBytes = sm;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (CS > 1) ? 1 : 0;
+#define SA_LAUNCH_FILL(S_, W_)                                                                                         \
+    do {                                                                                                               \
+        cudaFuncSetAttribute(fill_kernel<S_, W_, NW, MINB, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        cudaLaunchKernelEx(&cfg, fill_kernel<S_, W_, NW, MINB, CS>, p);                                                \
     } while (0)
     if (store) {
         if (swap) SA_LAUNCH_FILL(true, true);
@@ -901,19 +1070,21 @@ static void launch_fill_t(const FillParams &p, bool store, bool swap, int n_ctas
     }
 #undef SA_LAUNCH_FILL
 }
-void launch_fill(const FillParams &p, bool store, bool swap, bool coop, int n_ctas, cudaStream_t st) {
-    if (coop) launch_fill_t<COOP_WARPS, 1>(p, store, swap, n_ctas, st);
-    else launch_fill_t<1, FILL_MINB>(p, store, swap, n_ctas, st);
+// shape: 0 = bulk (one warp per problem), 1 = cooperative CTA, 2 = cooperative cluster of CLUSTER_CTAS CTAs
+void launch_fill(const FillParams &p, bool store, bool swap, int shape, int n_ctas, cudaStream_t st) {
+    if (shape == 2) launch_fill_t<COOP_WARPS, 1, CLUSTER_CTAS>(p, store, swap, n_ctas, st);
+    else if (shape == 1) launch_fill_t<COOP_WARPS, 1, 1>(p, store, swap, n_ctas, st);
+    else launch_fill_t<1, FILL_MINB, 1>(p, store, swap, n_ctas, st);
+}
+
+void launch_fill_unbanded(const FillParams &p, int32_t *prev32, bool swap, int n_ctas, cudaStream_t st) {
+    fill_unbanded_kernel<<<n_ctas, 128, 0, st>>>(p, prev32, swap ? 1 : 0);
 }
 
 void fill_powf_constants(double *pk) {
     const double v[12] = {SA_POWF_A0, SA_POWF_A1, SA_POWF_A2, SA_POWF_A3, SA_POWF_A4, SA_Y12,
                           SA_EXP2F_C0, SA_EXP2F_C1, SA_EXP2F_C2, SA_EXP2F_SHIFT, -SA_EXP2F_SHIFT, 0.0};
     for (int i = 0; i < 12; i++) pk[i] = v[i];
-}
-
-void launch_fill_unbanded(const FillParams &p, int32_t *prev32, bool swap, int n_ctas, cudaStream_t st) {
-    fill_unbanded_kernel<<<n_ctas, 128, 0, st>>>(p, prev32, swap ? 1 : 0);
 }
 
 void launch_traceback(const TraceParams &p, cudaStream_t st) {
@@ -934,9 +1105,30 @@ void launch_powf12_range(uint32_t lo, uint32_t hi, float *out_fast, float *out_g
 void launch_dfma_peak(double *sink, int iters, int n_ctas, cudaStream_t st) {
     dfma_peak_kernel<<<n_ctas, 256, 0, st>>>(sink, iters);
 }
+int max_clusters() {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CLUSTER_CTAS * 64);
+    cfg.blockDim = dim3(COOP_WARPS * 32);
+    cfg.dynamicSmemBytes = TAB_SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER_CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaFuncSetAttribute(fill_kernel<false, false, COOP_WARPS, 1, CLUSTER_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)TAB_SMEM_BYTES);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, fill_kernel<false, false, COOP_WARPS, 1, CLUSTER_CTAS>, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
 int fill_ctas_per_sm() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<false, false, 1, FILL_MINB>, FILL_WARPS * 32, TAB_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<false, false, 1, FILL_MINB, 1>, FILL_WARPS * 32, TAB_SMEM_BYTES);
     return n > 0 ? n : 1;
 }
 

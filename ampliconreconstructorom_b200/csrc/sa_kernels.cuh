@@ -42,6 +42,7 @@ struct FillParams {
     float *halo;    // per work-unit (warp, or CTA in the cooperative variant) scratch: halo_stride floats each
     long long halo_stride;
     unsigned long long *counter;  // work-queue head
+    float *cluster_mail;          // cluster variant: CLUSTER_MAIL_FLOATS floats per cluster
     int init_mode, start_mode, fitting;
     float *rowmax_s;  // detection only: per-row best positive score / its column (ties -> larger q)
     int32_t *rowmax_q;
@@ -79,7 +80,8 @@ struct DetectParams {
 };
 
 void launch_detect(const DetectParams &p, cudaStream_t st);
-void launch_fill(const FillParams &p, bool store, bool swap, bool coop, int n_ctas, cudaStream_t st);
+void launch_fill(const FillParams &p, bool store, bool swap, int shape, int n_ctas, cudaStream_t st);
+int max_clusters();
 void launch_fill_unbanded(const FillParams &p, int32_t *prev32, bool swap, int n_ctas, cudaStream_t st);
 void launch_traceback(const TraceParams &p, cudaStream_t st);
 void launch_powf12(const float *x, long long n, float *out, int fast, cudaStream_t st);
@@ -88,9 +90,11 @@ void launch_dfma_peak(double *sink, int iters, int n_ctas, cudaStream_t st);
 int fill_ctas_per_sm();
 void fill_powf_constants(double *pk);
 #ifndef SA_FILL_MINB
-#define SA_FILL_MINB 4
+#define SA_FILL_MINB 3  // 168 registers: lets ptxas interleave the 6 powf chains (measured best on B200)
 #endif
 constexpr int FILL_MINB = SA_FILL_MINB;   // resident CTAs per SM the fill kernel is compiled for (register budget 128)
+constexpr int CLUSTER_CTAS = 8;   // CTAs (SMs) per cluster of the cluster-cooperative variant used for huge problems
+constexpr int CLUSTER_MAIL_FLOATS = 16 + CLUSTER_CTAS * 16 + CLUSTER_CTAS * 8;  // per-cluster L2 mailbox
 constexpr int COOP_WARPS = 16;  // warps of the cooperative (one problem per CTA) variant used for large problems
 constexpr int FILL_WARPS = 4;  // warps per CTA of the fill kernel (one problem per warp at a time)
 

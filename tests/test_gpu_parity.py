@@ -46,11 +46,13 @@ def upload(ctx, maps, probs, side):
     return ids
 
 
-@pytest.fixture(params=["bulk", "coop"], autouse=True)
+@pytest.fixture(params=["bulk", "coop", "cluster"], autouse=True)
 def kernel_class(request, monkeypatch):
-    """Run every parity case twice: through the one-warp-per-problem kernel and through the cooperative
-    16-warp wavefront kernel (forced by an absurdly low 'large problem' threshold)."""
+    """Run every parity case three times: through the one-warp-per-problem kernel, the cooperative 16-warp CTA
+    wavefront and the 8-CTA thread-block-cluster wavefront (forced by absurdly low size-class thresholds)."""
     monkeypatch.setenv("SA_COOP_ALPHA", "0" if request.param == "bulk" else "1e-9")
+    monkeypatch.setenv("SA_NO_CLUSTER", "0" if request.param == "cluster" else "1")
+    monkeypatch.setenv("SA_HUGE_MIN_CELLS", "0")
     return request.param
 
 
