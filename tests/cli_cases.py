@@ -89,3 +89,23 @@ CASES = {
     "detection_small_n": (dict(seed=8, n_segs=4, n_contigs=40, n_related=8, contig_labels=(60, 400)),
                           ["-nthreads=2", "-min_labs=10", "-gen=2", "-detection", "-n_detect_scores=120"]),
 }
+
+
+def make_edge_case(seed: int):
+    """Degenerate shapes next to normal ones: contigs with 1-3 labels, segments with 1-3 labels (kept because
+    -min_labs=1), a segment that repeats a contig exactly (zero discrepancies -> the generic powf path)."""
+    rng = np.random.default_rng(seed)
+    # >= 170 contigs: with fewer, the reference dies with std::length_error for segments of < 12 labels (main.cpp:77-84)
+    segs, contigs = make_case(seed, n_segs=3, n_contigs=176, n_related=8, seg_labels=(12, 30), contig_labels=(20, 60))
+    g = synth.genome_positions(rng, 4000)
+    segs[4] = synth.window_map(g, 100, 2)
+    segs[5] = synth.window_map(g, 300, 3)
+    segs[6] = synth.window_map(g, 500, 4)
+    contigs[177] = synth.noisy_contig(rng, g, 700, 2)
+    contigs[178] = synth.noisy_contig(rng, g, 900, 3)
+    contigs[179] = np.array(segs[1], dtype=np.float64)  # identical to segment 1: discrepancies of exactly 0
+    contigs[180] = synth.window_map(g, 100, 40)          # exact in-silico window containing segs[4]
+    return segs, contigs
+
+
+EDGE_FLAGS = ["-nthreads=2", "-min_labs=2", "-gen=2"]

@@ -67,3 +67,11 @@ def test_cli_fitting(tmp_path):
         c = synth.noisy_contig(rng, g, 8, int(rng.integers(10, 60)))
         _run_both(tmp_path / f"f{t}", {1: s, 2: synth.window_map(g, 100, 12)}, {1: c, 3: synth.noisy_contig(rng, g, 90, 30)},
                   ["-fitting", "-min_labs=0", "-gen=1"])
+
+
+def test_cli_degenerate_shapes(tmp_path):
+    """1-3 label contigs, 2-4 label segments (-min_labs=2), exact copies (zero discrepancies)."""
+    _need_bins()
+    segs, contigs = cc.make_edge_case(21)
+    _run_both(tmp_path, segs, contigs, cc.EDGE_FLAGS)
+    _run_both(tmp_path / "loc", segs, contigs, cc.EDGE_FLAGS + ["-local", "-no_tip_aln"])
