@@ -30,6 +30,13 @@ using namespace sah;
 
 namespace {
 
+// Leaving a job early: the stand-alone process turns this into exit(code); the resident server replies with the
+// code and keeps running (unless fatal: a CUDA failure leaves the context unusable).
+struct JobExit {
+    int code;
+    bool fatal;
+};
+
 // ---- globals of the reference (main.cpp:19-37) -------------------------------------------------------------
 struct Options {
     bool local_aln = false, detection = false, fitting_aln = false, swap_b_x = false;
@@ -83,7 +90,7 @@ void parse_args(int argc, char **argv, Options &o) {
             o.inst_gen = ref_stoi_arg(after_eq(a));
             if (o.inst_gen != 1 && o.inst_gen != 2) {
                 printf("1 or 2 are the only valid arguments for -gen");
-                exit(1);
+                throw JobExit{1, false};
             }
         } else if (starts_with(a, "-ngpus=")) o.n_gpus = ref_stoi_arg(after_eq(a));
     }
@@ -96,13 +103,14 @@ struct Engine {
 
     void die(sa_ctx *c, const char *what, int rc) {
         fprintf(stderr, "SegAligner(b200): %s failed (%d): %s\n", what, rc, c ? sa_last_error(c) : "");
-        exit(2);
+        throw JobExit{2, true};
     }
     void open(int n) {
+        if (!ctx.empty()) return;  // resident server: contexts stay open between jobs
         const int avail = sa_device_count();
         if (avail <= 0) {
             fprintf(stderr, "SegAligner(b200): no CUDA device visible; this build has no CPU fallback\n");
-            exit(2);
+            throw JobExit{2, true};
         }
         n = std::max(1, std::min(n, avail));
         ctx.assign((size_t)n, nullptr);
@@ -387,11 +395,13 @@ struct PhaseTimer {  // SA_VERBOSE=1: per-phase wall times on stderr
 
 }  // namespace
 
-int main(int argc, char *argv[]) {
+// One SegAligner run (the body of the reference's main, main.cpp:453-656).  `eng` may already hold open contexts
+// (resident server); `keep_open` leaves them open on return.
+static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
     if (argc < 3) {  // the reference tests argc < 2 and then dereferences argv[2] regardless (main.cpp:454-468)
         printf("wrong number of arguments\n");
         fflush(stdout);
-        exit(1);
+        throw JobExit{1, false};
     }
     const clock_t begin = clock();
     const double w0 = wall_now();
@@ -407,8 +417,20 @@ int main(int argc, char *argv[]) {
 
     PhaseTimer pt;
     // CUDA start-up (driver init + context, ~0.3 s) overlaps with CMAP parsing: open device 0 right away
-    Engine eng;
-    std::thread gpu_open([&eng]() { eng.open(1); });
+    JobExit open_err{0, false};
+    std::thread gpu_open([&eng, &open_err]() {
+        try {
+            eng.open(1);
+        } catch (const JobExit &e) {
+            open_err = e;
+        }
+    });
+    struct Joiner {  // the opener thread must be joined on every exit path (exceptions included)
+        std::thread &t;
+        ~Joiner() {
+            if (t.joinable()) t.join();
+        }
+    } joiner{gpu_open};
     MapSet segs_raw, segs, contigs;
     parse_cmap(ref_cmap_file, segs_raw);
     if (!o.fitting_aln) segs = make_reverse_cmap(segs_raw, o.min_map_len);
@@ -434,7 +456,8 @@ int main(int argc, char *argv[]) {
             write_score_thresholds({}, o.sample_prefix + o.detection_label);
         }
         gpu_open.join();
-        eng.close();
+        if (open_err.code) throw open_err;
+        if (!keep_open) eng.close();
         return 0;
     }
 
@@ -451,6 +474,7 @@ int main(int argc, char *argv[]) {
         if (n_gpus <= 0) n_gpus = atoi(e);
     if (n_gpus <= 0) n_gpus = total_cells > 2e10 ? sa_device_count() : 1;
     gpu_open.join();
+    if (open_err.code) throw open_err;
     if (n_gpus > 1) eng.open_more(n_gpus);
     pt.lap("open GPU context(s)");
     eng.set_maps(contigs, segs);
@@ -480,7 +504,7 @@ int main(int argc, char *argv[]) {
         }
         printf("elapsed seconds for run %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
         fflush(stdout);
-        eng.close();
+        if (!keep_open) eng.close();
         return 0;
     }
 
@@ -577,7 +601,215 @@ int main(int argc, char *argv[]) {
     if (getenv("SA_VERBOSE")) fprintf(stderr, "SegAligner(b200): wall %.3f s on %d GPU(s)\n", wall_now() - w0, (int)eng.ctx.size());
     fflush(stdout);
     fflush(stderr);
-    eng.close();  // orderly teardown: abandoning the context (_exit) only moves the cost into the next process start
+    if (!keep_open) eng.close();  // orderly teardown: abandoning the context only moves the cost to the next start
     pt.lap("close");
     return 0;
+}
+
+// ---- resident server (opt-in, SA_SERVER=1) ----------------------------------------------------------------------
+// OMPathFinder.py:407-428 execs one `SegAligner -fitting` process per candidate path (a 50-cell problem, 0.2 ms in
+// the reference); creating a CUDA context costs 0.3-1.7 s per process.  With SA_SERVER=1 the first invocation leaves
+// a background server holding the GPU context on a Unix socket; later invocations forward argv + cwd to it and
+// print the stdout it returns.  Same executable, same files, same exit codes; no CPU fallback anywhere.
+#include <fcntl.h>
+#include <poll.h>
+#include <signal.h>
+#include <sys/socket.h>
+#include <sys/stat.h>
+#include <sys/un.h>
+#include <sys/wait.h>
+
+namespace {
+
+std::string server_socket_path() {
+    if (const char *e = getenv("SA_SERVER_SOCKET")) return e;
+    return "/tmp/segaligner_b200_" + std::to_string((long)getuid()) + ".sock";
+}
+
+bool write_all(int fd, const void *buf, size_t n) {
+    const char *p = (const char *)buf;
+    while (n) {
+        const ssize_t w = write(fd, p, n);
+        if (w <= 0) return false;
+        p += w;
+        n -= (size_t)w;
+    }
+    return true;
+}
+bool read_all(int fd, void *buf, size_t n) {
+    char *p = (char *)buf;
+    while (n) {
+        const ssize_t r = read(fd, p, n);
+        if (r <= 0) return false;
+        p += r;
+        n -= (size_t)r;
+    }
+    return true;
+}
+bool send_str(int fd, const std::string &s) {
+    const uint32_t n = (uint32_t)s.size();
+    return write_all(fd, &n, 4) && write_all(fd, s.data(), n);
+}
+bool recv_str(int fd, std::string &s) {
+    uint32_t n = 0;
+    if (!read_all(fd, &n, 4) || n > (64u << 20)) return false;
+    s.resize(n);
+    return n == 0 || read_all(fd, &s[0], n);
+}
+
+int connect_server(const std::string &path) {
+    const int fd = socket(AF_UNIX, SOCK_STREAM, 0);
+    if (fd < 0) return -1;
+    sockaddr_un a{};
+    a.sun_family = AF_UNIX;
+    snprintf(a.sun_path, sizeof a.sun_path, "%s", path.c_str());
+    if (connect(fd, (sockaddr *)&a, sizeof a) != 0) {
+        close(fd);
+        return -1;
+    }
+    return fd;
+}
+
+[[noreturn]] void serve(const std::string &path) {
+    const int ls = socket(AF_UNIX, SOCK_STREAM, 0);
+    sockaddr_un a{};
+    a.sun_family = AF_UNIX;
+    snprintf(a.sun_path, sizeof a.sun_path, "%s", path.c_str());
+    if (ls < 0 || bind(ls, (sockaddr *)&a, sizeof a) != 0 || listen(ls, 64) != 0) _exit(0);  // somebody else serves
+    chmod(path.c_str(), 0600);
+    int idle_s = 300;
+    if (const char *e = getenv("SA_SERVER_IDLE")) idle_s = std::max(1, atoi(e));
+    Engine eng;
+    bool fatal = false;
+    while (!fatal) {
+        pollfd pf{ls, POLLIN, 0};
+        if (poll(&pf, 1, idle_s * 1000) <= 0) break;  // idle: give the GPU back
+        const int c = accept(ls, nullptr, nullptr);
+        if (c < 0) continue;
+        uint32_t n_args = 0;
+        std::vector<std::string> args;
+        std::string cwd;
+        bool ok = read_all(c, &n_args, 4) && n_args < 4096;
+        for (uint32_t k = 0; ok && k < n_args; k++) {
+            std::string s;
+            ok = recv_str(c, s);
+            args.push_back(s);
+        }
+        ok = ok && recv_str(c, cwd);
+        if (!ok) {
+            close(c);
+            continue;
+        }
+        if (args.size() == 2 && args[1] == "--server-stop") {
+            const uint32_t code = 0;
+            const uint64_t zero = 0;
+            write_all(c, &code, 4);
+            write_all(c, &zero, 8);
+            close(c);
+            break;
+        }
+        // run the job with stdout captured into an unlinked temp file
+        char tmpl[] = "/tmp/sa_b200_out_XXXXXX";
+        const int tf = mkstemp(tmpl);
+        unlink(tmpl);
+        fflush(stdout);
+        const int saved = dup(1);
+        dup2(tf, 1);
+        if (chdir(cwd.c_str()) != 0) { /* paths relative to an unreachable cwd will simply fail to open */ }
+        std::vector<char *> av;
+        for (auto &s : args) av.push_back(&s[0]);
+        av.push_back(nullptr);
+        uint32_t code = 0;
+        try {
+            code = (uint32_t)run_job((int)args.size(), av.data(), eng, true);
+        } catch (const JobExit &e) {
+            code = (uint32_t)e.code;
+            fatal = e.fatal;
+        }
+        fflush(stdout);
+        dup2(saved, 1);
+        close(saved);
+        const off_t len = lseek(tf, 0, SEEK_END);
+        lseek(tf, 0, SEEK_SET);
+        std::string out((size_t)std::max<off_t>(len, 0), '\0');
+        if (len > 0) read_all(tf, &out[0], (size_t)len);
+        close(tf);
+        const uint64_t olen = out.size();
+        write_all(c, &code, 4);
+        write_all(c, &olen, 8);
+        write_all(c, out.data(), out.size());
+        close(c);
+    }
+    close(ls);
+    unlink(path.c_str());
+    eng.close();
+    _exit(0);
+}
+
+// returns -1 when the server route is unavailable (caller then runs the job in-process)
+int run_via_server(int argc, char *argv[]) {
+    const std::string path = server_socket_path();
+    int fd = connect_server(path);
+    if (fd < 0) {
+        // no server yet (or a stale socket): start one.  fork happens before any CUDA call in this process.
+        unlink(path.c_str());
+        const pid_t pid = fork();
+        if (pid == 0) {
+            setsid();
+            signal(SIGHUP, SIG_IGN);
+            signal(SIGPIPE, SIG_IGN);
+            const int dn = open("/dev/null", O_RDWR);
+            if (dn >= 0) {
+                dup2(dn, 0);
+                dup2(dn, 1);
+                if (!getenv("SA_VERBOSE")) dup2(dn, 2);
+            }
+            for (int f = 3; f < 256; f++) close(f);
+            serve(path);
+        }
+        if (pid < 0) return -1;
+        for (int tries = 0; tries < 600 && fd < 0; tries++) {  // the socket appears before CUDA is initialised
+            usleep(5000);
+            fd = connect_server(path);
+        }
+        if (fd < 0) return -1;
+    }
+    char cwd[4096];
+    if (!getcwd(cwd, sizeof cwd)) cwd[0] = 0;
+    const uint32_t n_args = (uint32_t)argc;
+    bool ok = write_all(fd, &n_args, 4);
+    for (int k = 0; ok && k < argc; k++) ok = send_str(fd, argv[k]);
+    ok = ok && send_str(fd, cwd);
+    uint32_t code = 0;
+    uint64_t olen = 0;
+    ok = ok && read_all(fd, &code, 4) && read_all(fd, &olen, 8) && olen < (1ull << 32);
+    if (!ok) {
+        close(fd);
+        fprintf(stderr, "SegAligner(b200): the resident server went away while running this job\n");
+        return 134;
+    }
+    std::string out((size_t)olen, '\0');
+    if (olen) read_all(fd, &out[0], (size_t)olen);
+    close(fd);
+    fwrite(out.data(), 1, out.size(), stdout);
+    fflush(stdout);
+    return (int)code;
+}
+
+}  // namespace
+
+int main(int argc, char *argv[]) {
+    signal(SIGPIPE, SIG_IGN);
+    const char *sv = getenv("SA_SERVER");
+    if (sv && atoi(sv) != 0) {
+        const int rc = run_via_server(argc, argv);
+        if (rc >= 0) return rc;
+    }
+    Engine eng;
+    try {
+        return run_job(argc, argv, eng, false);
+    } catch (const JobExit &e) {
+        fflush(stdout);
+        return e.code;
+    }
 }

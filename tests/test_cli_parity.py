@@ -75,3 +75,52 @@ def test_cli_degenerate_shapes(tmp_path):
     segs, contigs = cc.make_edge_case(21)
     _run_both(tmp_path, segs, contigs, cc.EDGE_FLAGS)
     _run_both(tmp_path / "loc", segs, contigs, cc.EDGE_FLAGS + ["-local", "-no_tip_aln"])
+
+
+def test_cli_resident_server(tmp_path):
+    """SA_SERVER=1: the first call leaves a server holding the CUDA context on a Unix socket; later calls are
+    forwarded to it.  Outputs (files and stdout) must equal the in-process run; repeated fitting calls -- the
+    OMPathFinder pattern, one process per candidate path -- must be fast once the server is up."""
+    import os
+    import subprocess
+    import time
+    _need_bins()
+    sock = str(tmp_path / "sa.sock")
+    env = dict(os.environ, SA_SERVER="1", SA_SERVER_SOCKET=sock, SA_SERVER_IDLE="60")
+    seg = np.array([0, 5200, 9100, 20500, 31000, 33900, 47000, 47001], dtype=np.float64)
+    contig = np.array([0, 5150, 9300, 15000, 20400, 31200, 34000, 46800, 46801], dtype=np.float64)
+    seg_f, con_f = cc.write_case(tmp_path / "in", {1: seg}, {1: contig})
+    flags = ["-fitting", "-min_labs=0", "-gen=2"]
+    direct = cc.run_bin(cc.NEW_BIN, tmp_path / "direct", seg_f, con_f, flags)
+    assert direct.returncode == 0
+    try:
+        times = []
+        for k in range(6):
+            (tmp_path / f"s{k}").mkdir()
+            t0 = time.perf_counter()
+            p = subprocess.run([str(cc.NEW_BIN), str(seg_f), str(con_f), f"-prefix={tmp_path}/s{k}/SA"] + flags,
+                               capture_output=True, text=True, env=env, timeout=120)
+            times.append(time.perf_counter() - t0)
+            assert p.returncode == 0, p.stderr
+            assert cc.dir_digest(tmp_path / f"s{k}") == cc.dir_digest(tmp_path / "direct")
+            assert p.stdout.splitlines()[:3] == direct.stdout.splitlines()[:3]
+        assert os.path.exists(sock)
+        assert min(times[1:]) < 0.25, f"server round trips too slow: {times}"
+        # a standard run through the server, relative paths resolved against the client's cwd
+        segs, contigs = cc.make_case(seed=1)
+        cc.write_case(tmp_path / "std", segs, contigs)
+        (tmp_path / "std" / "a").mkdir()
+        (tmp_path / "std" / "b").mkdir()
+        f2 = ["-nthreads=3", "-min_labs=10", "-gen=2"]
+        pa = subprocess.run([str(cc.NEW_BIN), "segs.cmap", "contigs.cmap", "-prefix=a/SA"] + f2, cwd=tmp_path / "std",
+                            capture_output=True, text=True, env=env, timeout=300)
+        pb = subprocess.run([str(cc.NEW_BIN), "segs.cmap", "contigs.cmap", "-prefix=b/SA"] + f2, cwd=tmp_path / "std",
+                            capture_output=True, text=True, timeout=300)
+        assert pa.returncode == 0 and pb.returncode == 0, pa.stderr + pb.stderr
+        assert cc.dir_digest(tmp_path / "std" / "a") == cc.dir_digest(tmp_path / "std" / "b")
+        bad = subprocess.run([str(cc.NEW_BIN), "segs.cmap", "contigs.cmap", "-gen=3"], cwd=tmp_path / "std",
+                             capture_output=True, text=True, env=env, timeout=60)
+        assert bad.returncode == 1 and "only valid arguments for -gen" in bad.stdout
+    finally:
+        subprocess.run([str(cc.NEW_BIN), "--server-stop"], env=env, capture_output=True, timeout=60)
+    print("server round-trip times (s):", [round(t, 3) for t in times])
