@@ -5,7 +5,7 @@ the unmodified reference on a subset (byte-compared), and reports both as GCUPS.
 import gzip, os, shutil, subprocess, sys, tempfile, time
 from pathlib import Path
 import numpy as np
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 from ampliconreconstructorom_b200 import capi, synth
 import cli_cases as cc

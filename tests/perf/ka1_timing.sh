@@ -1,7 +1,7 @@
 #!/bin/bash
 # KA-1 (hg19 BspQI detection sweep on shipped data): wall time of the B200 executable vs the reference binary
 set -e
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 D=oracle/_ref/data
 mkdir -p /tmp/ka1/new /tmp/ka1/ref
 gunzip -c $D/hg19_BspQI.cmap.gz > /tmp/ka1/hg19.cmap

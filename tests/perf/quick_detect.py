@@ -2,7 +2,7 @@
 import gzip, shutil, sys, tempfile, time
 from pathlib import Path
 import numpy as np
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from ampliconreconstructorom_b200 import capi, synth
 n_regions = int(sys.argv[1]) if len(sys.argv) > 1 else 8
