@@ -38,7 +38,7 @@ EXPORTS = [
     "sa_plan_create", "sa_plan_destroy", "sa_plan_score", "sa_plan_results", "sa_plan_info", "sa_sync", "sa_align_batch", "sa_detect_batch", "sa_fill_one", "sa_powf12",
     "sa_powf12_range", "sa_get_timing", "sa_measure_fp64_peak", "sa_event_record", "sa_event_elapsed_ms",
     "sa_host_non_collapse_probs", "sa_host_make_reverse", "sa_host_parse_cmap", "sa_host_score_thresholds",
-    "sa_host_format_float",
+    "sa_host_format_float", "sa_digest",
 ]
 
 _lib = None
@@ -76,6 +76,7 @@ def load_library() -> C.CDLL:
     lib.sa_powf12_range.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp]
     lib.sa_get_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.sa_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.sa_digest.argtypes = [vp, vp, i64, C.c_char_p, i32, i32, i64, vp, C.POINTER(i64)]
     lib.sa_event_record.argtypes = [vp, i32]
     lib.sa_event_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.sa_host_non_collapse_probs.argtypes = [i32, vp, vp, i32, vp]
@@ -340,6 +341,22 @@ class Context:
         t = Timing()
         self._check(self.lib.sa_get_timing(self.h, C.byref(t)), "sa_get_timing")
         return t
+
+    def digest(self, seq, motif: str, offset: int) -> np.ndarray:
+        """In-silico digestion (generate_cmap.py:119-123): ascending unique label positions (int64) of `motif` and its
+        reverse complement in `seq` (bytes / uint8 array); offset = the enzyme's cut offset + 1."""
+        buf = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray, memoryview)) else \
+            np.ascontiguousarray(seq, dtype=np.uint8)
+        n_out = C.c_int64()
+        m = motif.encode()
+        self._check(self.lib.sa_digest(self.h, _ptr(buf) if buf.size else None, buf.size, m, len(m), offset, 0, None,
+                                       C.byref(n_out)), "sa_digest") if buf.size else None
+        if buf.size == 0 or n_out.value == 0:
+            return np.zeros(0, dtype=np.int64)
+        out = np.zeros(n_out.value, dtype=np.int64)
+        self._check(self.lib.sa_digest(self.h, _ptr(buf), buf.size, m, len(m), offset, out.size, _ptr(out),
+                                       C.byref(n_out)), "sa_digest")
+        return out[:n_out.value]
 
     def event_record(self, slot: int):
         self._check(self.lib.sa_event_record(self.h, slot), "sa_event_record")

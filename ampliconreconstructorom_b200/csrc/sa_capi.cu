@@ -13,6 +13,9 @@
 
 using namespace sa;
 
+int sa_digest_run(cudaStream_t st, int n_sms, const uint8_t *d_seq, int64_t n, const char *motif, int32_t motif_len, int32_t offset,
+                  long long *d_out, unsigned long long *d_count, int64_t cap);
+
 namespace {
 
 struct DevBuf {
@@ -818,6 +821,43 @@ int sa_get_timing(sa_ctx *ctx, sa_timing *t) {
         ctx->timing.fill_ms = a;
     }
     *t = ctx->timing;
+    return SA_OK;
+}
+
+int sa_digest(sa_ctx *ctx, const char *seq, int64_t n, const char *motif, int32_t motif_len, int32_t offset, int64_t cap,
+              int64_t *pos_out, int64_t *n_out) {
+    if (!ctx || !seq || !motif || !n_out || n < 0 || cap < 0 || (cap > 0 && !pos_out)) return ctx ? fail(ctx, SA_EINVAL, "bad argument") : SA_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    const size_t padded = ((size_t)n + 15) / 16 * 16 + 64;
+    CU(ctx->d_S.reserve(padded));  // sequence bytes (the DP matrices are not live during a digestion)
+    CU(ctx->d_tmp2.reserve(64));
+    const int64_t dev_cap = std::max<int64_t>(cap, 1);
+    CU(ctx->d_path_s.reserve(sizeof(long long) * (size_t)dev_cap));
+    CU(cudaMemsetAsync(reinterpret_cast<char *>(ctx->d_S.p) + ((size_t)n / 16) * 16, 0, padded - ((size_t)n / 16) * 16, ctx->stream));
+    if (n > 0) CU(cudaMemcpyAsync(ctx->d_S.p, seq, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_tmp2.p, 0, 64, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = sa_digest_run(ctx->stream, ctx->n_sms, ctx->d_S.as<uint8_t>(), n, motif, motif_len, offset,
+                           ctx->d_path_s.as<long long>(), ctx->d_tmp2.as<unsigned long long>(), dev_cap);
+    if (rc) return fail(ctx, rc, "sa_digest: motif length must be 4..8");
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    unsigned long long cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, ctx->d_tmp2.p, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->timing = {ms, 0, 1, 0};
+    if ((int64_t)cnt > cap) {  // sizing call (or buffer too small): report the raw match count, an upper bound
+        *n_out = (int64_t)cnt;
+        return SA_OK;
+    }
+    std::vector<long long> v((size_t)cnt);
+    if (cnt) CU(cudaMemcpy(v.data(), ctx->d_path_s.p, sizeof(long long) * (size_t)cnt, cudaMemcpyDeviceToHost));
+    std::sort(v.begin(), v.end());  // sorted(list(set(...)))  (generate_cmap.py:123)
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+    for (size_t k = 0; k < v.size(); k++) pos_out[k] = v[k];
+    *n_out = (int64_t)v.size();
     return SA_OK;
 }
 

@@ -149,6 +149,16 @@ int sa_host_score_thresholds(int64_t n_rows, const int32_t *row_seg, const int32
                              const float *contig_pos, double pvalue, int32_t n_detect_scores, float *thr_out);
 int sa_host_format_float(float v, char *buf, int32_t cap);
 
+/* ---- next row of the scope table: in-silico digestion, the producer of the CMAP inputs ------------
+ * sa_digest replaces the motif scan of generate_cmap.py:119-123: finds every (overlapping) occurrence of `motif`
+ * (4..8 letters ACGT, case-insensitive sequence) and of its reverse complement in seq[0..n), converts match starts
+ * to label positions (start + offset on the forward strand, start + motif_len - offset on the reverse strand;
+ * `offset` is the enzyme's cut offset + 1 as makeCMAP uses it) and returns them ascending and de-duplicated
+ * (sorted(set(...))).  Positions can be < 0 or > n, exactly as in the reference.  Two-call sizing: with cap == 0 (or
+ * too small) only *n_out is set, to an upper bound (raw match count).  Host buffers; H2D/D2H inside. */
+int sa_digest(sa_ctx *ctx, const char *seq, int64_t n, const char *motif, int32_t motif_len, int32_t offset, int64_t cap,
+              int64_t *pos_out, int64_t *n_out);
+
 /* Device-time bracket on the context's stream (CUDA events): record slot 0 / 1, then read the elapsed ms. */
 int sa_event_record(sa_ctx *ctx, int32_t slot);
 int sa_event_elapsed_ms(sa_ctx *ctx, float *ms);
