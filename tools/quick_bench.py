@@ -4,7 +4,10 @@ from pathlib import Path
 import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
+import os
 from ampliconreconstructorom_b200 import capi, synth
+if os.environ.get("SA_LIB"):  # developer A/B builds from tools/build_variants.sh
+    capi.LIB_PATH = Path(os.environ["SA_LIB"]).resolve()
 
 n_segs = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 n_contigs = int(sys.argv[2]) if len(sys.argv) > 2 else 100
