@@ -811,6 +811,28 @@ int sa_powf12_range(sa_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, float *out_
     return SA_OK;
 }
 
+int sa_check_prune_bound(sa_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, uint64_t *n_violations, float *min_ratio) {
+    if (!ctx || !n_violations || !min_ratio) return SA_EINVAL;
+    *n_violations = 0;
+    *min_ratio = 2.0f;
+    if (hi_bits <= lo_bits) return SA_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->d_tmp0.reserve(16));
+    unsigned long long *d_n = ctx->d_tmp0.as<unsigned long long>();
+    float *d_r = reinterpret_cast<float *>(d_n + 1);
+    const float two = 2.0f;
+    CU(cudaMemsetAsync(d_n, 0, 8, ctx->stream));
+    CU(cudaMemcpyAsync(d_r, &two, 4, cudaMemcpyHostToDevice, ctx->stream));
+    launch_prune_bound(lo_bits, hi_bits, d_n, d_r, ctx->stream);
+    CU(cudaGetLastError());
+    unsigned long long h_n = 0;
+    CU(cudaMemcpyAsync(&h_n, d_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(min_ratio, d_r, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *n_violations = h_n;
+    return SA_OK;
+}
+
 int sa_get_timing(sa_ctx *ctx, sa_timing *t) {
     if (!ctx || !t) return SA_EINVAL;
     if (ctx->timing.fill_ms < 0) {

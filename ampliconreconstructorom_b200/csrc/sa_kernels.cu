@@ -35,9 +35,30 @@ __constant__ unsigned long long c_exptab[32] = {SA_EXP2F_TAB};
 __constant__ double c_pk[12] = {SA_POWF_A0, SA_POWF_A1, SA_POWF_A2, SA_POWF_A3, SA_POWF_A4, SA_Y12,
                                 SA_EXP2F_C0, SA_EXP2F_C1, SA_EXP2F_C2, SA_EXP2F_SHIFT, -SA_EXP2F_SHIFT, 0.0};
 
-// fast-path domain of the delta term: 2^-20*1.4 <= discrep < 2^32*0.7 (52 binades starting at OFF - 20*2^23)
-constexpr uint32_t IX_LO = SA_POWF_OFF - (20u << 23);
-constexpr uint32_t IX_RANGE = 52u << 23;
+// ---- shared-memory tables of the powf replay -----------------------------------------------------------------
+// Variant knob (compile time, both measured on B200 -- see DESIGN.md 4.1):
+//   SA_TAB2D 3 (default): LANE-REPLICATED, bank-conflict-free tables.  The log table {invc_i, logc_i + (double)k}
+//                 holds 32 binades x 16 entries, each entry stored 8 times (16 B x 8 = one 128-byte bank row), and lane
+//                 l reads copy l & 7: the 8 lanes of an LDS.128 quarter-warp phase always hit 8 different 16-byte bank
+//                 groups => exactly 4 shared-memory wavefronts per LDS.128 whatever the indices.  The exp2 table holds
+//                 its 32 u64 entries 16 times (8 B x 16 = one bank row), lane l reads copy l & 15 => exactly 2
+//                 wavefronts per LDS.64.  64 KB + 4 KB per CTA, so the kernels run one CTA per SM.
+//   SA_TAB2D 1:   one copy: 52 x 16 entries of 16 B + 32 x u64 (13.4 wavefronts per evaluation instead of 7: random
+//                 indices conflict 2-3 ways per phase); 16 KB, 3 CTAs per SM.
+#ifndef SA_BREADTH
+#define SA_BREADTH 1  // breadth-first scheduling of the 6 powf chains of a look-back row
+#endif
+
+// fast-path domain of the delta term: discrep in [0.7 * 2^-KLO, 0.7 * 2^(KBIN-KLO)); anything else (exact 0, tiny,
+// huge, inf, NaN) is flagged and the cell is redone through the generic path
+#if SA_TAB2D == 3
+constexpr int KLO = 9, KBIN = 32;  // 1.4e-3 <= discrep < 5.9e6 bp
+#else
+constexpr int KLO = 20, KBIN = 52;
+#endif
+constexpr uint32_t IX_LO = SA_POWF_OFF - ((uint32_t)KLO << 23);
+constexpr uint32_t IX_RANGE = (uint32_t)KBIN << 23;
+constexpr int TAB2D_N = KBIN * 16;  // entry (k + KLO) * 16 + i
 
 #define NEG_INF_F (__int_as_float(0xff800000))
 __device__ __noinline__ float powf12_slow(float ax) {
@@ -52,139 +73,127 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+#ifndef SA_VOL_LDS
+#define SA_VOL_LDS 0  // 1: table loads are volatile asm => they keep their source order (pins the software pipeline)
+#endif
+#if SA_VOL_LDS
+#define SA_ASM_TAB asm volatile
+#else
+#define SA_ASM_TAB asm
+#endif
 __device__ __forceinline__ void lds_f64x2(uint32_t addr, double &a, double &b) {
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+    SA_ASM_TAB("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
 }
 __device__ __forceinline__ void lds_u32x2(uint32_t addr, uint32_t &lo, uint32_t &hi) {
-    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
+    SA_ASM_TAB("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
 }
 
-// ---- shared-memory tables of the powf replay -----------------------------------------------------------------
-// Variant knobs (compile time, measured on B200 -- see DESIGN.md 4.1):
-//   SA_TAB2D   1: one LDS.128 fetches {invc_i, logc_i + (double)k} from a 52x16-entry table indexed by the top
-//                 bits of (ix - IX_LO); removes LEA.HI + I2F.F64 + DADD per evaluation (y0 is the same IEEE sum,
-//                 computed once per table entry).  0: 16-entry invc/logc tables (conflict free) + I2F + DADD.
-//   SA_EXP64   1: exp2 table as 32 x u64, one LDS.64 (entries e, e+16 share banks).  0: split hi/lo, 2 LDS.32.
-#ifndef SA_TAB2D
-#define SA_TAB2D 1
-#endif
-#ifndef SA_EXP64
-#define SA_EXP64 1
-#endif
-#ifndef SA_BREADTH
-#define SA_BREADTH 1  // breadth-first scheduling of the 6 powf chains of a look-back row
-#endif
-
-#if SA_TAB2D == 1
-constexpr int TAB2D_N = 52 * 16;  // (k + 20) * 16 + i
+#if SA_TAB2D == 3
+constexpr int T2D_COPIES = 8, EXP_COPIES = 16;
+struct __align__(16) PowTabSmem {  // placed so that t2d sits at a 64 KB-aligned SHARED address (tab_place)
+    unsigned long long exp64[32 * EXP_COPIES];  // 4 KB, [entry][copy]
+    double2 t2d[TAB2D_N * T2D_COPIES];          // 64 KB, [entry][copy] = {invc, y0}
+};
+static_assert(sizeof(PowTabSmem) == 4096 + 65536, "PowTabSmem layout");
+constexpr uint32_t TAB_ALIGN = 65536, TAB_LEAD = 4096;
+constexpr uint32_t T2D_SHIFT = 12, T2D_MASK = 0xFF80u;  // byte offset of entry u >> 19: (u >> 12) & 0xFF80
+constexpr uint32_t EXP_SHIFT = 7, EXP_MASK = 0xF80u;    // byte offset of entry ki & 31: (ki << 7) & 0xF80
+#else
 struct __align__(16) PowTabSmem {  // placed at a 16 KB-aligned SHARED address by the kernels (tab_place)
     double2 t2d[TAB2D_N];           // {invc, y0}; byte offset = ((u >> 15) & 0x3FF0) stays inside this struct
     unsigned long long exp64[32];   // at byte 13312
-    uint32_t exp_lo[32];
-    uint32_t exp_hi[32];
-    unsigned char pad[16384 - TAB2D_N * 16 - 256 - 256];
+    unsigned char pad[16384 - TAB2D_N * 16 - 256];
 };
 static_assert(sizeof(PowTabSmem) == 16384, "PowTabSmem layout");
-constexpr uint32_t TAB_EXP_OFF = TAB2D_N * 16;
-#elif SA_TAB2D == 2
-// y0 = logc_i + k from an 8-byte 2-D table (byte offset (u >> 16) & 0x1FF8), invc from the conflict-free 16-entry
-// table: two LDS.64 instead of one LDS.128 -- fewer shared-memory wavefronts (the 16-byte 2-D entries conflict
-// 2-3 ways per quarter-warp), one more instruction.
-constexpr int TAB2D_N = 52 * 16;
-struct __align__(16) PowTabSmem {
-    double y0[1024];                // 8 KB (832 used)
-    double invc[16];                // at 8192
-    unsigned char pad0[128];
-    unsigned long long exp64[32];   // at 8448
-    uint32_t exp_lo[32];
-    uint32_t exp_hi[32];
-    unsigned char pad[16384 - 8192 - 256 - 256 - 256];
-};
-static_assert(sizeof(PowTabSmem) == 16384, "PowTabSmem layout");
-constexpr uint32_t TAB_EXP_OFF = 8448;
-#else
-struct __align__(1024) PowTabSmem {
-    double invc[16];
-    double logc[16];
-    unsigned long long exp64[32];  // at byte 256
-    uint32_t exp_lo[32];
-    uint32_t exp_hi[32];
-    unsigned char pad[256];
-};
-static_assert(sizeof(PowTabSmem) == 1024, "PowTabSmem layout");
-constexpr uint32_t TAB_EXP_OFF = 256;
+constexpr uint32_t TAB_ALIGN = 16384, TAB_LEAD = 0;
+constexpr uint32_t T2D_SHIFT = 15, T2D_MASK = 0x3FF0u;
+constexpr uint32_t EXP_SHIFT = 3, EXP_MASK = 0xF8u;
 #endif
 
-// The `stab | offset` addressing needs the table at a shared-window address aligned to its size; static shared
-// variables start at a toolchain-chosen offset, so kernels over-allocate dynamic shared memory and align here.
-constexpr uint32_t TAB_ALIGN = sizeof(PowTabSmem);
-constexpr uint32_t TAB_SMEM_BYTES = 2 * TAB_ALIGN;  // what a kernel must reserve in front of its own buffers
+// The `base | offset` addressing needs the log table at a shared-window address aligned to its (power-of-two) size;
+// static shared variables start at a toolchain-chosen offset, so kernels over-allocate dynamic shared memory and
+// align here.  TAB_SMEM_BYTES is what a kernel must reserve (the struct lands somewhere inside it).
+constexpr uint32_t TAB_SMEM_BYTES = (uint32_t)sizeof(PowTabSmem) + TAB_ALIGN;
 __device__ __forceinline__ PowTabSmem *tab_place(unsigned char *dyn) {
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(dyn);
-    return reinterpret_cast<PowTabSmem *>(dyn + ((TAB_ALIGN - (base & (TAB_ALIGN - 1))) & (TAB_ALIGN - 1)));
+    const uint32_t a = (base + TAB_LEAD + TAB_ALIGN - 1) & ~(TAB_ALIGN - 1);  // shared address of t2d
+    return reinterpret_cast<PowTabSmem *>(dyn + (a - TAB_LEAD - base));
+}
+
+// Exact fp32 <-> fp64 conversions with integer ALU instructions.  On B200 the XU conversions (F2F) share an issue
+// path with the fp64 pipe and the LSU -- measured (tools/ubench6.cu): every F2F costs ~5.5 and every LDS ~8.4
+// sub-partition cycles ON TOP of the fp64 time, while ALU/FMA-pipe instructions overlap with it for free.
+#ifndef SA_INT_CVT
+#define SA_INT_CVT 1
+#endif
+// widen a NORMAL fp32 bit pattern (here: iz in [0x3f330000, 0x3fb30000)) to fp64
+__device__ __forceinline__ double f2d_normal(uint32_t fbits) {
+#if SA_INT_CVT
+    return __hiloint2double((int)((fbits >> 3) + 0x38000000u), (int)(fbits << 29));
+#else
+    return (double)__uint_as_float(fbits);
+#endif
+}
+// round a positive fp64 whose value lies in the NORMAL fp32 range to fp32, round-to-nearest-even (== cvt.rn.f32.f64)
+__device__ __forceinline__ float d2f_normal(double y) {
+#if SA_INT_CVT
+    const uint32_t hi = (uint32_t)__double2hiint(y), lo = (uint32_t)__double2loint(y);
+    const uint32_t shf = __funnelshift_l(lo, hi, 3);  // drops sign + 2 exponent bits, keeps 29 + 3 mantissa bits
+    const uint32_t rem = lo & 0x1FFFFFFFu;            // the 29 bits below the fp32 mantissa
+    const uint32_t inc = (rem + 0x0FFFFFFFu + (shf & 1u)) >> 29;  // 1 iff rem > half, or == half and lsb odd
+    return __uint_as_float(shf + 0x40000000u + inc);  // + 0x80 on the 9 kept exponent bits == exponent - 896
+#else
+    return __double2float_rn(y);
+#endif
+}
+
+// Per-lane base addresses (32-bit shared window) of the two tables, lane copy folded in.
+struct TabAddr {
+    uint32_t t2d, exp;
+};
+__device__ __forceinline__ TabAddr tab_addr(const PowTabSmem &t) {
+    TabAddr a;
+    const uint32_t lane = threadIdx.x & 31;
+    a.t2d = (uint32_t)__cvta_generic_to_shared(&t.t2d[0]);
+    a.exp = (uint32_t)__cvta_generic_to_shared(&t.exp64[0]);
+#if SA_TAB2D == 3
+    a.t2d |= (lane & (T2D_COPIES - 1)) << 4;
+    a.exp |= (lane & (EXP_COPIES - 1)) << 3;
+#else
+    (void)lane;
+#endif
+    return a;
 }
 
 __device__ __forceinline__ void powtab_init(PowTabSmem &t) {
-#if SA_TAB2D == 1
-    for (int e = threadIdx.x; e < TAB2D_N; e += blockDim.x) {
-        const int k = (e >> 4) - 20, i = e & 15;
+#if SA_TAB2D == 3
+    for (int e = threadIdx.x; e < TAB2D_N * T2D_COPIES; e += blockDim.x) {
+        const int ent = e / T2D_COPIES, k = (ent >> 4) - KLO, i = ent & 15;
         t.t2d[e] = make_double2(c_logtab[i].invc, __dadd_rn(c_logtab[i].logc, (double)k));
     }
-#elif SA_TAB2D == 2
-    for (int e = threadIdx.x; e < 1024; e += blockDim.x) {
-        const int k = (e >> 4) - 20, i = e & 15;
-        t.y0[e] = e < TAB2D_N ? __dadd_rn(c_logtab[i].logc, (double)k) : 0.0;
-    }
-    if (threadIdx.x < 16) t.invc[threadIdx.x] = c_logtab[threadIdx.x].invc;
+    for (int e = threadIdx.x; e < 32 * EXP_COPIES; e += blockDim.x) t.exp64[e] = c_exptab[e / EXP_COPIES];
 #else
-    if (threadIdx.x < 16) {
-        t.invc[threadIdx.x] = c_logtab[threadIdx.x].invc;
-        t.logc[threadIdx.x] = c_logtab[threadIdx.x].logc;
+    for (int e = threadIdx.x; e < TAB2D_N; e += blockDim.x) {
+        const int k = (e >> 4) - KLO, i = e & 15;
+        t.t2d[e] = make_double2(c_logtab[i].invc, __dadd_rn(c_logtab[i].logc, (double)k));
     }
+    if (threadIdx.x < 32) t.exp64[threadIdx.x] = c_exptab[threadIdx.x];
 #endif
-    if (threadIdx.x >= 32 && threadIdx.x < 64) {
-        const unsigned long long v = c_exptab[threadIdx.x - 32];
-        t.exp_lo[threadIdx.x - 32] = (uint32_t)v;
-        t.exp_hi[threadIdx.x - 32] = (uint32_t)(v >> 32);
-        t.exp64[threadIdx.x - 32] = v;
-    }
-}
-
-__device__ __forceinline__ double lds_f64(uint32_t addr) {
-    double v;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
 }
 
 // Branch-free replay of powf(ax, 1.2f) for ax inside the fast domain; outside it the result is garbage but the
 // code is still memory-safe (every table index is masked), so callers evaluate unconditionally and patch the
-// rare out-of-domain lanes afterwards (u_out >= IX_RANGE tells which).  stab = 32-bit shared address of a
-// PowTabSmem (aligned to its size, so `stab | offset` == `stab + offset`).
-__device__ __forceinline__ float powf12_fast(float ax, uint32_t stab, const double (&pk)[12], uint32_t &u_out) {
+// rare out-of-domain lanes afterwards (u_out >= IX_RANGE tells which).  ta = per-lane table addresses (tab_addr);
+// the tables are aligned to their size, so `base | offset` == `base + offset` (one LOP3 per address).
+__device__ __forceinline__ float powf12_fast(float ax, const TabAddr ta, const double (&pk)[12], uint32_t &u_out) {
     const uint32_t ix = __float_as_uint(ax);
     const uint32_t u = ix - IX_LO;
     u_out = u;
     const uint32_t kb = u & 0xff800000u;
-    const uint32_t iz = ix - kb + (20u << 23);
+    const uint32_t iz = ix - kb + ((uint32_t)KLO << 23);
     double invc, y0;
-#if SA_TAB2D == 1
-    lds_f64x2(stab | ((u >> 15) & 0x3FF0u), invc, y0);
-#elif SA_TAB2D == 2
-    const uint32_t t16 = u >> 16;
-    y0 = lds_f64(stab | (t16 & 0x1FF8u));
-    invc = lds_f64((stab + 8192u) | (t16 & 0x78u));
-#else
-    const int k = (int)(u >> 23) - 20;
-    const uint32_t a_i = stab | ((u >> 16) & 0x78u);  // 8 * ((u >> 19) & 15)
-    invc = lds_f64(a_i);
-    y0 = __dadd_rn(lds_f64(a_i + 128), (double)k);
-#endif
-    // log2: 8 fp64 ops (+ the logc + k sum, folded into the table when SA_TAB2D), then y*log2(x)
+    lds_f64x2(ta.t2d | ((u >> T2D_SHIFT) & T2D_MASK), invc, y0);
+    // log2: 8 fp64 ops (the logc + k sum is folded into the table), then y*log2(x)
     const double z = (double)__uint_as_float(iz);
     const double r = __fma_rn(z, invc, -1.0);
     double y = __fma_rn(r, pk[0], pk[1]);
@@ -201,13 +210,7 @@ __device__ __forceinline__ float powf12_fast(float ax, uint32_t stab, const doub
     kd = __dadd_rn(kd, pk[10]);
     const double rr = __dadd_rn(xd, -kd);
     uint32_t tlo, thi;
-#if SA_EXP64
-    lds_u32x2((stab + TAB_EXP_OFF) | ((ki << 3) & 0xF8u), tlo, thi);
-#else
-    const uint32_t a_e = (stab + TAB_EXP_OFF + 256u) | ((ki << 2) & 0x7Cu);
-    tlo = lds_u32(a_e);
-    thi = lds_u32(a_e + 128);
-#endif
+    lds_u32x2(ta.exp | ((ki << EXP_SHIFT) & EXP_MASK), tlo, thi);
     thi += ki << 15;  // t += ki << 47
     const double sc = __hiloint2double((int)thi, (int)tlo);
     const double zz = __fma_rn(rr, pk[6], pk[7]);
@@ -218,43 +221,70 @@ __device__ __forceinline__ float powf12_fast(float ax, uint32_t stab, const doub
     return __double2float_rn(yy);
 }
 
-// Breadth-first replay of NC independent powf(ax,1.2f) chains: every stage is applied to all chains before the
-// next one, so that dependent fp64 instructions of one chain are NC issue slots apart (DFMA latency ~10 cycles,
-// one fp64 warp-instruction per 2 cycles per SM sub-partition).  Same arithmetic as powf12_fast.
-template <int NC>
-__device__ __forceinline__ void powf12_fastN(const float (&ax)[NC], uint32_t stab, const double (&pk)[12],
-                                             float (&out)[NC], uint32_t (&uo)[NC]) {
-    uint32_t iz[NC], ki[NC], tlo[NC], thi[NC];
-    double invc[NC], y0[NC], r[NC], y[NC], p[NC], r2[NC], q[NC], xd[NC], kd[NC], rr[NC], zz[NC], yy[NC];
+// ---- the look-back row pipeline ---------------------------------------------------------------------------------
+// One look-back row = the LB candidates (dq = 1..LB) of one dj: LB independent powf(discrep, 1.2f) chains, replayed
+// BREADTH-FIRST (every stage applied to all chains before the next one) so that dependent fp64 instructions of a
+// chain are LB issue slots apart (DFMA latency ~10 cycles, one fp64 warp-instruction per 2 cycles per SM
+// sub-partition).  The row is split in two so that the kernel can software-pipeline rows: row_prefetch() turns the
+// discrepancies into table operands (address chain + LDS.128 + F2F, ~35 cycles of latency) one row AHEAD of
+// row_powf(), which is pure fp64 work on operands that are already in registers.  Same arithmetic as powf12_fast.
+struct PowRow {
+    double z[LB], invc[LB], y0[LB];
+};
+
+// db_row = this lane's b[j] - b[j-dj] (or x-side value when the maps are swapped by the caller -- they are not:
+// swap only changes the fn/fp terms); dx[c] = x[q] - x[q-1-c].  umax accumulates the out-of-domain flag.
+__device__ __forceinline__ void row_prefetch(PowRow &n, float db_row, const float (&dx)[LB], const TabAddr ta,
+                                             uint32_t &umax) {
+    uint32_t u[LB];
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-        const uint32_t ix = __float_as_uint(ax[c]);
-        const uint32_t u = ix - IX_LO;
-        uo[c] = u;
-        iz[c] = ix - (u & 0xff800000u) + (20u << 23);
-#if SA_TAB2D == 1
-        lds_f64x2(stab | ((u >> 15) & 0x3FF0u), invc[c], y0[c]);
-#elif SA_TAB2D == 2
-        const uint32_t t16 = u >> 16;
-        y0[c] = lds_f64(stab | (t16 & 0x1FF8u));
-        invc[c] = lds_f64((stab + 8192u) | (t16 & 0x78u));
+    for (int c = 0; c < LB; c++) {
+        const uint32_t ix = __float_as_uint(fabsf(__fsub_rn(db_row, dx[c])));
+        u[c] = ix - IX_LO;
+        const uint32_t iz = ix - (u[c] & 0xff800000u) + ((uint32_t)KLO << 23);
+#ifdef SA_KO_T2D
+        n.invc[c] = __hiloint2double(0x3ff00000, (int)u[c]), n.y0[c] = __hiloint2double(0x3ff00000, (int)ix);
 #else
-        const int k = (int)(u >> 23) - 20;
-        const uint32_t a_i = stab | ((u >> 16) & 0x78u);
-        invc[c] = lds_f64(a_i);
-        y0[c] = __dadd_rn(lds_f64(a_i + 128), (double)k);
+        lds_f64x2(ta.t2d | ((u[c] >> T2D_SHIFT) & T2D_MASK), n.invc[c], n.y0[c]);
+#endif
+#ifdef SA_KO_F2F_IN
+        n.z[c] = __hiloint2double((int)iz, (int)ix);
+#else
+        n.z[c] = f2d_normal(iz);
 #endif
     }
+    umax = __vimax3_u32(umax, __vimax3_u32(u[0], u[1], u[2]), __vimax3_u32(u[3], u[4], u[5]));
+}
+
+// Where the fp64 constants of the replay come from: SA_PK_LIT 1 = literals (ptxas picks immediates / uniform registers /
+// its literal constant bank), 0 = the kernel-parameter array pk[] (constant bank 0).
+#ifndef SA_PK_LIT
+#define SA_PK_LIT 1
+#endif
+#if SA_PK_LIT
+__device__ __forceinline__ constexpr double pk_lit(int i) {
+    return i == 0 ? SA_POWF_A0 : i == 1 ? SA_POWF_A1 : i == 2 ? SA_POWF_A2 : i == 3 ? SA_POWF_A3 : i == 4 ? SA_POWF_A4
+         : i == 5 ? SA_Y12 : i == 6 ? SA_EXP2F_C0 : i == 7 ? SA_EXP2F_C1 : i == 8 ? SA_EXP2F_C2
+         : i == 9 ? SA_EXP2F_SHIFT : -SA_EXP2F_SHIFT;
+}
+#define PK(i) pk_lit(i)
+#else
+#define PK(i) pk[i]
+#endif
+__device__ __forceinline__ void row_powf(const PowRow &w, const TabAddr ta, const double (&pk)[12], float (&out)[LB]) {
+    constexpr int NC = LB;
+    uint32_t ki[NC], tlo[NC], thi[NC];
+    double r[NC], y[NC], p[NC], r2[NC], q[NC], xd[NC], kd[NC], rr[NC], zz[NC], yy[NC];
 #pragma unroll
-    for (int c = 0; c < NC; c++) r[c] = __fma_rn((double)__uint_as_float(iz[c]), invc[c], -1.0);
+    for (int c = 0; c < NC; c++) r[c] = __fma_rn(w.z[c], w.invc[c], -1.0);
 #pragma unroll
-    for (int c = 0; c < NC; c++) y[c] = __fma_rn(r[c], pk[0], pk[1]);
+    for (int c = 0; c < NC; c++) y[c] = __fma_rn(r[c], PK(0), PK(1));
 #pragma unroll
-    for (int c = 0; c < NC; c++) p[c] = __fma_rn(r[c], pk[2], pk[3]);
+    for (int c = 0; c < NC; c++) p[c] = __fma_rn(r[c], PK(2), PK(3));
 #pragma unroll
     for (int c = 0; c < NC; c++) r2[c] = __dmul_rn(r[c], r[c]);
 #pragma unroll
-    for (int c = 0; c < NC; c++) q[c] = __fma_rn(r[c], pk[4], y0[c]);
+    for (int c = 0; c < NC; c++) q[c] = __fma_rn(r[c], PK(4), w.y0[c]);
 #pragma unroll
     for (int c = 0; c < NC; c++) q[c] = __fma_rn(r2[c], p[c], q[c]);
 #pragma unroll
@@ -262,28 +292,26 @@ __device__ __forceinline__ void powf12_fastN(const float (&ax)[NC], uint32_t sta
 #pragma unroll
     for (int c = 0; c < NC; c++) y[c] = __fma_rn(y[c], r2[c], q[c]);
 #pragma unroll
-    for (int c = 0; c < NC; c++) xd[c] = __dmul_rn(pk[5], y[c]);
+    for (int c = 0; c < NC; c++) xd[c] = __dmul_rn(PK(5), y[c]);
 #pragma unroll
-    for (int c = 0; c < NC; c++) kd[c] = __dadd_rn(xd[c], pk[9]);
+    for (int c = 0; c < NC; c++) kd[c] = __dadd_rn(xd[c], PK(9));
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         ki[c] = (uint32_t)__double2loint(kd[c]);
-#if SA_EXP64
-        lds_u32x2((stab + TAB_EXP_OFF) | ((ki[c] << 3) & 0xF8u), tlo[c], thi[c]);
+#ifdef SA_KO_EXP
+        tlo[c] = ki[c], thi[c] = 0x3ff00000u;
 #else
-        const uint32_t a_e = (stab + TAB_EXP_OFF + 256u) | ((ki[c] << 2) & 0x7Cu);
-        tlo[c] = lds_u32(a_e);
-        thi[c] = lds_u32(a_e + 128);
+        lds_u32x2(ta.exp | ((ki[c] << EXP_SHIFT) & EXP_MASK), tlo[c], thi[c]);
 #endif
     }
 #pragma unroll
-    for (int c = 0; c < NC; c++) kd[c] = __dadd_rn(kd[c], pk[10]);
+    for (int c = 0; c < NC; c++) kd[c] = __dadd_rn(kd[c], PK(10));
 #pragma unroll
     for (int c = 0; c < NC; c++) rr[c] = __dadd_rn(xd[c], -kd[c]);
 #pragma unroll
-    for (int c = 0; c < NC; c++) zz[c] = __fma_rn(rr[c], pk[6], pk[7]);
+    for (int c = 0; c < NC; c++) zz[c] = __fma_rn(rr[c], PK(6), PK(7));
 #pragma unroll
-    for (int c = 0; c < NC; c++) yy[c] = __fma_rn(rr[c], pk[8], 1.0);
+    for (int c = 0; c < NC; c++) yy[c] = __fma_rn(rr[c], PK(8), 1.0);
 #pragma unroll
     for (int c = 0; c < NC; c++) rr[c] = __dmul_rn(rr[c], rr[c]);
 #pragma unroll
@@ -291,38 +319,86 @@ __device__ __forceinline__ void powf12_fastN(const float (&ax)[NC], uint32_t sta
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         const double sc = __hiloint2double((int)(thi[c] + (ki[c] << 15)), (int)tlo[c]);
-        out[c] = __double2float_rn(__dmul_rn(yy[c], sc));
+#ifdef SA_KO_F2F_OUT
+        out[c] = __int_as_float(__double2hiint(__dmul_rn(yy[c], sc)));
+#else
+        out[c] = d2f_normal(__dmul_rn(yy[c], sc));
+#endif
     }
 }
 
-// Whole-cell evaluation through the generic powf path, same candidate order and tie rule as the fast path.
-// f[k] = fx[k] (non-swap: fp_t by column look-back) or fb[k] (swap: fp_t by row look-back).
-__device__ __noinline__ float cell_slow(bool swap, float db0, float db1, float db2, float db3, float db4, float db5,
-                                        float dx0, float dx1, float dx2, float dx3, float dx4, float dx5, float f0,
-                                        float f1, float f2, float f3, float f4, float f5, uint32_t pc0, uint32_t pc1,
-                                        uint32_t pc2, uint32_t pc3, uint32_t pc4, uint32_t pc5, int *code_out) {
-    const float db[LB] = {db0, db1, db2, db3, db4, db5};
+// powf(ax, 1.2f) for any ax >= 0: the table replay inside the fast domain, the generic path outside it.
+__device__ __noinline__ float powf12_any(float ax, uint32_t t2d, uint32_t exp) {
+    TabAddr ta;
+    ta.t2d = t2d, ta.exp = exp;
+    uint32_t u;
+    const float f = powf12_fast(ax, ta, c_pk, u);
+    return (u < IX_RANGE) ? f : powf12_generic(ax, c_logtab, reinterpret_cast<const uint64_t *>(c_exptab));
+}
+
+// ---- exact pruning -------------------------------------------------------------------------------------------------
+// Only the maximum over the 36 candidates of a cell is needed (SegAligner.cpp:123-127), and it is needed bit-exactly.
+// Every fp32 operation of `S[i][p] + (10000 - ((fn + fp) + delta))` is monotone in delta, so a LOWER bound of
+// delta gives an UPPER bound `hi` of the candidate's exact score with no error analysis.  Per cell:
+//   1. all 36 candidates get `hi` from delta_lo(d) = ex2.approx(1.2 * lg2.approx(d) - PRUNE_C) (two MUFU, fp32 only;
+//      delta_lo <= the bit-exact powf replay for EVERY float, certified exhaustively on the GPU by sa_check_prune);
+//      the two largest `hi` are tracked, the candidate index rides in the low 3 mantissa bits of the key;
+//   2. the candidate with the largest `hi` is evaluated exactly (the one fp64 replay of the cell);
+//   3. if its exact score is larger than the second largest `hi` (+ the key perturbation) it is the strict maximum and
+//      the cell is done; otherwise (ties and near-ties: rare) the whole cell is redone exactly by cell_slow().
+// Measured on the C2 workload: the second step settles > 99.9 % of the cells.
+constexpr float PRUNE_C = 0x1p-14f;  // log2-domain safety margin of delta_lo (MUFU errors are ~2^-22)
+__device__ __forceinline__ float delta_lo_approx(float d) {
+    float a, e;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(fabsf(d)));
+    const float t = __fmaf_rn(a, 1.2f, -PRUNE_C);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return e;
+}
+
+// powf(ax, 1.2f), inline fast path with the generic path behind a (rare) branch
+__device__ __forceinline__ float powf12_exact(float ax, const TabAddr ta, const double (&pk)[12]) {
+    uint32_t u;
+    float f = powf12_fast(ax, ta, pk, u);
+    if (u >= IX_RANGE) f = powf12_slow(ax);
+    return f;
+}
+
+// Whole-cell re-evaluation for cells with an out-of-domain discrepancy (exact 0 mostly), same candidate order and
+// tie rule as the pipeline.  a_row = shared address of this lane's row operands (db[0..5], fb[0..5], 128 B apart);
+// f[] = fx (non-swap: fp_t by column look-back; with swap the row-side fb is read from a_row).
+struct CellRes {
+    float best;
+    int code;
+};
+__device__ __noinline__ CellRes cell_slow(bool swap, uint32_t a_row, float dx0, float dx1, float dx2, float dx3,
+                                          float dx4, float dx5, float f0, float f1, float f2, float f3, float f4,
+                                          float f5, uint32_t pc0, uint32_t pc1, uint32_t pc2, uint32_t pc3, uint32_t pc4,
+                                          uint32_t pc5, uint32_t t2d, uint32_t exp) {
     const float dx[LB] = {dx0, dx1, dx2, dx3, dx4, dx5};
     const float f[LB] = {f0, f1, f2, f3, f4, f5};
     const uint32_t pc[LB] = {pc0, pc1, pc2, pc3, pc4, pc5};
-    float best = NEG_INF_F;
-    int code = 0;
-    for (int dj = 1; dj <= LB; dj++)
+    CellRes res;
+    res.best = NEG_INF_F;
+    res.code = 0;
+    for (int dj = 1; dj <= LB; dj++) {
+        const float dbv = lds_f32(a_row + (dj - 1) * 128);
+        const float fbv = swap ? lds_f32(a_row + (LB + dj - 1) * 128) : 0.0f;
         for (int dq = 1; dq <= LB; dq++) {
             const float sc = lds_f32(pc[dq - 1] - dj * 4);
-            const float discrep = fabsf(__fsub_rn(db[dj - 1], dx[dq - 1]));
-            const float delta = powf12_slow(discrep);
+            const float discrep = fabsf(__fsub_rn(dbv, dx[dq - 1]));
+            const float delta = powf12_any(discrep, t2d, exp);
             const float fn = 5000.0f * (float)((swap ? dq : dj) - 1);
-            const float fp = swap ? f[dj - 1] : f[dq - 1];
+            const float fp = swap ? fbv : f[dq - 1];
             const float r = __fsub_rn(10000.0f, __fadd_rn(__fadd_rn(fn, fp), delta));
             const float ns = __fadd_rn(sc, r);
-            if (ns >= best) {
-                best = ns;
-                code = 1 + (dj - 1) * LB + (dq - 1);
+            if (ns >= res.best) {
+                res.best = ns;
+                res.code = 1 + (dj - 1) * LB + (dq - 1);
             }
         }
-    *code_out = code;
-    return best;
+    }
+    return res;
 }
 
 constexpr int RING_W = 40;  // 6 halo rows + 32 lanes + 2 pad
@@ -347,6 +423,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
     extern __shared__ unsigned char s_dyn[];
     PowTabSmem &s_tab = *tab_place(s_dyn);
     __shared__ float s_ring[WPC][LB][RING_W];
+    __shared__ float s_rowop[WPC][2 * LB][32];  // per lane: db[0..5], fb[0..5] of its row (LabelOps), lane-private
     __shared__ float s_xbuf[WPC][2][8];
     __shared__ unsigned long long s_next;
     __shared__ float s_red_s[WPC];
@@ -357,10 +434,11 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
     const int warp = threadIdx.x >> 5;
     powtab_init(s_tab);
     __syncthreads();
-    const uint32_t a_tab = (uint32_t)__cvta_generic_to_shared(&s_tab);
+    const TabAddr a_tab = tab_addr(s_tab);
     // byte address of this lane's own entry in ring slot 0
     const uint32_t a_my = (uint32_t)__cvta_generic_to_shared(&s_ring[warp][0][6 + lane]);
     const uint32_t a_halo = (uint32_t)__cvta_generic_to_shared(&s_ring[warp][0][lane]);  // lanes 0..5 only
+    const uint32_t a_row = (uint32_t)__cvta_generic_to_shared(&s_rowop[warp][0][lane]);
 
     const long long gunit = (NW == 1) ? ((long long)blockIdx.x * FILL_WARPS + warp) : (long long)(blockIdx.x / CS);
     float *halo = P.halo + gunit * P.halo_stride;
@@ -421,17 +499,12 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         int q = 0;  // column within the current round (>= nx: idle tail of a short round)
         int j = 0, jc = 0;
         bool row_ok = false, row_used = false;
-        float db[LB], fb[LB];
         uint32_t pc[LB];
         int slot = 0;
         float rm_s = 0.0f;  // detection: best positive score of this lane's row, ties -> larger q
         int rm_q = -1;
 #pragma unroll
-        for (int d = 0; d < LB; d++) {
-            db[d] = 0.0f;
-            fb[d] = 0.0f;
-            pc[d] = a_my;
-        }
+        for (int d = 0; d < LB; d++) pc[d] = a_my;
 
         for (long long t = 0; t < T; t++) {
             const bool active = (t >= w) && (strip < nstrips) && (q < nx);
@@ -444,8 +517,13 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     jc = row_ok ? j : nb - 1;
                     const float4 *src = reinterpret_cast<const float4 *>(bops + jc);
                     const float4 a = __ldg(src), b4 = __ldg(src + 1), c4 = __ldg(src + 2);
-                    db[0] = a.x, db[1] = a.y, db[2] = a.z, db[3] = a.w, db[4] = b4.x, db[5] = b4.y;
-                    fb[0] = b4.z, fb[1] = b4.w, fb[2] = c4.x, fb[3] = c4.y, fb[4] = c4.z, fb[5] = c4.w;
+                    // row operands go to lane-private shared memory: the look-back rows are a rolled loop (dynamic dj)
+                    sts_f32(a_row + 0 * 128, a.x), sts_f32(a_row + 1 * 128, a.y), sts_f32(a_row + 2 * 128, a.z);
+                    sts_f32(a_row + 3 * 128, a.w), sts_f32(a_row + 4 * 128, b4.x), sts_f32(a_row + 5 * 128, b4.y);
+                    if (SWAP) {
+                        sts_f32(a_row + 6 * 128, b4.z), sts_f32(a_row + 7 * 128, b4.w), sts_f32(a_row + 8 * 128, c4.x);
+                        sts_f32(a_row + 9 * 128, c4.y), sts_f32(a_row + 10 * 128, c4.z), sts_f32(a_row + 11 * 128, c4.w);
+                    }
                     row_used = used ? ((used[jc >> 5] >> (jc & 31)) & 1u) : false;
                     __syncwarp();
 #pragma unroll
@@ -483,50 +561,145 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                 else if (P.init_mode == SA_INIT_LOCAL) init = 0.0f;
                 else init = (j == 0 || q == 0) ? 0.0f : NEG_INF;
 
+#if SA_PRUNE
+                float best = NEG_INF;
+                {
+                    // pass 1: upper bounds of all 36 candidates, two largest keys (candidate column index in bits 0..2)
+                    float m1 = NEG_INF, m2 = NEG_INF;
+                    int rowsel = 1;
+#pragma unroll 1
+                    for (int dj = 1; dj <= LB; dj++) {
+                        const float dbv = lds_f32(a_row + (dj - 1) * 128);
+                        const float fn = 5000.0f * (float)(dj - 1);
+                        float fbv = 0.0f;
+                        if (SWAP) fbv = lds_f32(a_row + (LB + dj - 1) * 128);
+                        float key[LB];
+#pragma unroll
+                        for (int c = 0; c < LB; c++) {
+                            const float sc = lds_f32(pc[c] - dj * 4);
+                            const float e = delta_lo_approx(__fsub_rn(dbv, dx[c]));
+                            float fnfp;
+                            if (!SWAP) fnfp = __fadd_rn(fn, fx[c]);
+                            else fnfp = (c == 0) ? fbv : __fadd_rn(5000.0f * (float)c, fbv);
+                            const float hi = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, e)));
+                            // -inf | c is a NaN for c != 0: fmaxf/fminf drop NaNs, which is what we want for -inf
+                            key[c] = __uint_as_float((__float_as_uint(hi) & 0xFFFFFFF8u) | (uint32_t)c);
+                        }
+                        const float m1_before = m1;
+#pragma unroll
+                        for (int c = 0; c < LB; c += 2) {
+                            const float mx = fmaxf(key[c], key[c + 1]), mn = fminf(key[c], key[c + 1]);
+                            const float t = fminf(m1, mx);
+                            m1 = fmaxf(m1, mx);
+                            m2 = fmaxf(m2, fmaxf(mn, t));
+                        }
+                        if (m1 > m1_before) rowsel = dj;
+                    }
+                    if (m1 > NEG_INF) {
+                        // pass 2: the exact score of the best-looking candidate (dj, c) of this lane
+                        const int c = (int)(__float_as_uint(m1) & 7u), dj = rowsel;
+                        const float dbv = lds_f32(a_row + (dj - 1) * 128);
+                        const float dxv = __ldg(reinterpret_cast<const float *>(xops + q) + c);
+                        // ring slot of column q-1-c: the slots rotate, slot of column q-1 is `slot`-1 (mod 6)
+                        int sl = slot - 1 - c;
+                        sl += (sl < 0) ? LB : 0;
+                        const float sc = lds_f32(a_my + sl * (RING_W * 4) - dj * 4);
+                        const float delta = powf12_exact(fabsf(__fsub_rn(dbv, dxv)), a_tab, P.pk);
+                        float fnfp;
+                        if (!SWAP) {
+                            const float fxv = __ldg(reinterpret_cast<const float *>(xops + q) + LB + c);
+                            fnfp = __fadd_rn(5000.0f * (float)(dj - 1), fxv);
+                        } else {
+                            const float fbv = lds_f32(a_row + (LB + dj - 1) * 128);
+                            fnfp = (c == 0) ? fbv : __fadd_rn(5000.0f * (float)c, fbv);
+                        }
+                        best = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, delta)));
+                        code = 1 + (dj - 1) * LB + c;
+                        // every other candidate's exact score is <= its hi <= key + 8 ulp <= m2 + 2^-19 |m2|
+                        const float m2_up = __fmaf_ru(fabsf(m2), 0x1p-19f, m2);
+                        if (!(best > m2_up)) {
+                            // rare: a tie or near-tie -> redo the whole cell exactly, in the reference's tie order
+                            const CellRes cr = cell_slow(SWAP, a_row, dx[0], dx[1], dx[2], dx[3], dx[4], dx[5],
+                                                         SWAP ? 0.0f : fx[0], SWAP ? 0.0f : fx[1], SWAP ? 0.0f : fx[2],
+                                                         SWAP ? 0.0f : fx[3], SWAP ? 0.0f : fx[4], SWAP ? 0.0f : fx[5],
+                                                         pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], a_tab.t2d, a_tab.exp);
+                            best = cr.best;
+                            code = cr.code;
+                        }
+                    }
+                }
+#else
                 float best = NEG_INF;
                 uint32_t umax = 0;
+                // Look-back rows dj = 1..6 as a rolled loop over row PAIRS with ping-pong operand buffers: while the
+                // fp64 replay of row dj runs, the table operands of row dj+1 are already being fetched.
+                PowRow rowA, rowB;
+                row_prefetch(rowA, lds_f32(a_row), dx, a_tab, umax);
+#pragma unroll 1
+                for (int i = 0; i < LB / 2; i++) {
+                    const int dj = 2 * i + 1;
+                    row_prefetch(rowB, lds_f32(a_row + dj * 128), dx, a_tab, umax);  // row dj+1
 #pragma unroll
-                for (int dj = 1; dj <= LB; dj++) {
-                    float delta[LB], sc[LB], discrep[LB];
-                    uint32_t u[LB];
+                    for (int h = 0; h < 2; h++) {
+                        const int djh = dj + h;
+                        float delta[LB], sc[LB], ns[LB];
 #pragma unroll
-                    for (int dq = 1; dq <= LB; dq++) {
-                        sc[dq - 1] = lds_f32(pc[dq - 1] - dj * 4);
-                        discrep[dq - 1] = fabsf(__fsub_rn(db[dj - 1], dx[dq - 1]));
-                    }
-#if SA_BREADTH
-                    powf12_fastN<LB>(discrep, a_tab, P.pk, delta, u);
+                        for (int c = 0; c < LB; c++) {
+#ifdef SA_KO_PRED
+                            sc[c] = __uint_as_float(pc[c] - djh * 4);
 #else
-#pragma unroll
-                    for (int dq = 1; dq <= LB; dq++) delta[dq - 1] = powf12_fast(discrep[dq - 1], a_tab, P.pk, u[dq - 1]);
+                            sc[c] = lds_f32(pc[c] - djh * 4);
 #endif
-                    umax = __vimax3_u32(umax, __vimax3_u32(u[0], u[1], u[2]), __vimax3_u32(u[3], u[4], u[5]));
+                        }
+                        if (h == 0) {
+                            row_powf(rowA, a_tab, P.pk, delta);
+                            if (i < LB / 2 - 1) row_prefetch(rowA, lds_f32(a_row + (dj + 1) * 128), dx, a_tab, umax);  // row dj+2
+                        } else {
+                            row_powf(rowB, a_tab, P.pk, delta);
+                        }
+                        // fn_t + fp_t (SegAligner.cpp:89-91); with swap_b_x the maps exchange roles (:119).
+                        // fn_t = 5000*(dj-1) resp. 5000*(dq-1) is exact; 0 + fp_t == fp_t bit for bit (fp_t >= +0).
+                        const float fn = 5000.0f * (float)(djh - 1);
+                        float fbv = 0.0f;
+                        if (SWAP) fbv = lds_f32(a_row + (LB + djh - 1) * 128);
 #pragma unroll
-                    for (int dq = 1; dq <= LB; dq++) {
-                        // fn_t + fp_t (SegAligner.cpp:89-91); with swap_b_x the maps exchange roles (:119)
-                        float fnfp;
-                        if (!SWAP) fnfp = (dj == 1) ? fx[dq - 1] : __fadd_rn(5000.0f * (float)(dj - 1), fx[dq - 1]);
-                        else fnfp = (dq == 1) ? fb[dj - 1] : __fadd_rn(5000.0f * (float)(dq - 1), fb[dj - 1]);
-                        const float r = __fsub_rn(10000.0f, __fadd_rn(fnfp, delta[dq - 1]));
-                        const float ns = __fadd_rn(sc[dq - 1], r);
-                        if (STORE) {
-                            if (ns >= best) {
-                                best = ns;
-                                code = 1 + (dj - 1) * LB + (dq - 1);
+                        for (int c = 0; c < LB; c++) {
+                            float fnfp;
+                            if (!SWAP) fnfp = __fadd_rn(fn, fx[c]);
+                            else fnfp = (c == 0) ? fbv : __fadd_rn(5000.0f * (float)c, fbv);
+                            const float r = __fsub_rn(10000.0f, __fadd_rn(fnfp, delta[c]));
+                            ns[c] = __fadd_rn(sc[c], r);
+                        }
+                        if (STORE) {  // last maximum in scan order (dj ascending, dq ascending) == first in the reference's
+                            float rb = ns[0];
+                            int rc = 0;
+#pragma unroll
+                            for (int c = 1; c < LB; c++)
+                                if (ns[c] >= rb) {
+                                    rb = ns[c];
+                                    rc = c;
+                                }
+                            if (rb >= best) {
+                                best = rb;
+                                code = 1 + (djh - 1) * LB + rc;
                             }
                         } else {
-                            best = fmaxf(best, ns);
+#pragma unroll
+                            for (int c = 0; c < LB; c++) best = fmaxf(best, ns[c]);
                         }
                     }
                 }
                 if (umax >= IX_RANGE) {
-                    // rare: some discrepancy of this cell is exactly 0, subnormal-tiny, huge, inf or NaN, where the
-                    // branch-free replay is undefined -> redo the whole cell through the generic powf path
-                    best = cell_slow(SWAP, db[0], db[1], db[2], db[3], db[4], db[5], dx[0], dx[1], dx[2], dx[3], dx[4],
-                                     dx[5], SWAP ? fb[0] : fx[0], SWAP ? fb[1] : fx[1], SWAP ? fb[2] : fx[2],
-                                     SWAP ? fb[3] : fx[3], SWAP ? fb[4] : fx[4], SWAP ? fb[5] : fx[5], pc[0], pc[1],
-                                     pc[2], pc[3], pc[4], pc[5], &code);
+                    // rare: some discrepancy of this cell is exactly 0, tiny, huge, inf or NaN, where the branch-free
+                    // replay is undefined -> redo the whole cell, candidate by candidate
+                    const CellRes cr = cell_slow(SWAP, a_row, dx[0], dx[1], dx[2], dx[3], dx[4], dx[5], SWAP ? 0.0f : fx[0],
+                                                 SWAP ? 0.0f : fx[1], SWAP ? 0.0f : fx[2], SWAP ? 0.0f : fx[3],
+                                                 SWAP ? 0.0f : fx[4], SWAP ? 0.0f : fx[5], pc[0], pc[1], pc[2], pc[3], pc[4],
+                                                 pc[5], a_tab.t2d, a_tab.exp);
+                    best = cr.best;
+                    code = cr.code;
                 }
+#endif
                 val = init;
                 if (best > init && !row_used) val = best;
                 else code = 0;
@@ -993,7 +1166,7 @@ __global__ void powf12_kernel(const float *x, long long n, float *out, int fast)
     PowTabSmem &s_tab = *tab_place(s_dyn);
     powtab_init(s_tab);
     __syncthreads();
-    const uint32_t a_tab = (uint32_t)__cvta_generic_to_shared(&s_tab);
+    const TabAddr a_tab = tab_addr(s_tab);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float ax = fabsf(x[i]);
         uint32_t u;
@@ -1007,7 +1180,7 @@ __global__ void powf12_range_kernel(uint32_t lo, uint32_t hi, float *out_fast, f
     PowTabSmem &s_tab = *tab_place(s_dyn);
     powtab_init(s_tab);
     __syncthreads();
-    const uint32_t a_tab = (uint32_t)__cvta_generic_to_shared(&s_tab);
+    const TabAddr a_tab = tab_addr(s_tab);
     const unsigned long long n = (unsigned long long)hi - lo;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -1018,6 +1191,31 @@ __global__ void powf12_range_kernel(uint32_t lo, uint32_t hi, float *out_fast, f
         out_fast[i] = (u >= IX_RANGE) ? g : f;
         out_generic[i] = g;
     }
+}
+
+// Certification of the pruning bound: counts the bit patterns x in [lo, hi) for which delta_lo_approx(x) is NOT a lower
+// bound of the bit-exact powf(x, 1.2f) (must be 0 for the pruning to be exact), and returns the smallest slack seen.
+__global__ void prune_bound_kernel(uint32_t lo, uint32_t hi, unsigned long long *n_viol, float *min_ratio) {
+    extern __shared__ unsigned char s_dyn[];
+    PowTabSmem &s_tab = *tab_place(s_dyn);
+    powtab_init(s_tab);
+    __syncthreads();
+    const TabAddr a_tab = tab_addr(s_tab);
+    const unsigned long long n = (unsigned long long)hi - lo;
+    unsigned long long viol = 0;
+    float mr = 2.0f;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float ax = __uint_as_float(lo + (uint32_t)i);
+        const float exact = powf12_exact(ax, a_tab, c_pk);
+        const float lob = delta_lo_approx(ax);
+        const float lob_neg = delta_lo_approx(-ax);  // the kernel feeds the signed difference; |.| is inside
+        if (!(lob <= exact) || lob != lob_neg) viol++;
+        if (exact > 0.0f && exact < CUDART_INF_F) mr = fminf(mr, exact / lob);
+    }
+    if (viol) atomicAdd(n_viol, viol);
+    // positive floats order like their bit patterns
+    atomicMin(reinterpret_cast<int *>(min_ratio), __float_as_int(mr));
 }
 
 // Sustained DFMA issue rate: 8 independent chains per thread, 1024 threads per SM.
@@ -1097,10 +1295,16 @@ void launch_detect(const DetectParams &p, cudaStream_t st) {
     if (p.n_problems > 0) detect_kernel<<<(unsigned)p.n_problems, 256, 0, st>>>(p);
 }
 void launch_powf12(const float *x, long long n, float *out, int fast, cudaStream_t st) {
+    cudaFuncSetAttribute(powf12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAB_SMEM_BYTES);
     powf12_kernel<<<148 * 4, 256, TAB_SMEM_BYTES, st>>>(x, n, out, fast);
 }
 void launch_powf12_range(uint32_t lo, uint32_t hi, float *out_fast, float *out_generic, cudaStream_t st) {
+    cudaFuncSetAttribute(powf12_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAB_SMEM_BYTES);
     powf12_range_kernel<<<148 * 4, 256, TAB_SMEM_BYTES, st>>>(lo, hi, out_fast, out_generic);
+}
+void launch_prune_bound(uint32_t lo, uint32_t hi, unsigned long long *n_viol, float *min_ratio, cudaStream_t st) {
+    cudaFuncSetAttribute(prune_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAB_SMEM_BYTES);
+    prune_bound_kernel<<<148 * 4, 256, TAB_SMEM_BYTES, st>>>(lo, hi, n_viol, min_ratio);
 }
 void launch_dfma_peak(double *sink, int iters, int n_ctas, cudaStream_t st) {
     dfma_peak_kernel<<<n_ctas, 256, 0, st>>>(sink, iters);
@@ -1128,6 +1332,8 @@ int max_clusters() {
 }
 int fill_ctas_per_sm() {
     int n = 0;
+    cudaFuncSetAttribute(fill_kernel<false, false, 1, FILL_MINB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)TAB_SMEM_BYTES);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<false, false, 1, FILL_MINB, 1>, FILL_WARPS * 32, TAB_SMEM_BYTES);
     return n > 0 ? n : 1;
 }

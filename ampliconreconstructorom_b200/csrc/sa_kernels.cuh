@@ -86,16 +86,31 @@ void launch_fill_unbanded(const FillParams &p, int32_t *prev32, bool swap, int n
 void launch_traceback(const TraceParams &p, cudaStream_t st);
 void launch_powf12(const float *x, long long n, float *out, int fast, cudaStream_t st);
 void launch_powf12_range(uint32_t lo, uint32_t hi, float *out_fast, float *out_generic, cudaStream_t st);
+void launch_prune_bound(uint32_t lo, uint32_t hi, unsigned long long *n_viol, float *min_ratio, cudaStream_t st);
 void launch_dfma_peak(double *sink, int iters, int n_ctas, cudaStream_t st);
 int fill_ctas_per_sm();
 void fill_powf_constants(double *pk);
-#ifndef SA_FILL_MINB
-#define SA_FILL_MINB 3  // 168 registers: lets ptxas interleave the 6 powf chains (measured best on B200)
+// Layout of the powf tables in shared memory (see sa_kernels.cu): 3 = lane-replicated, bank-conflict free, 68 KB per
+// CTA => one 12-warp CTA per SM; 1 = single copy, 16 KB, three 4-warp CTAs per SM.  Either way 12 warps x 168
+// registers per SM (168 lets ptxas interleave the 6 powf chains of a look-back row; measured best on B200).
+// SA_PRUNE 1 (default): exact pruning -- fp32 upper bounds for all 36 candidates of a cell, ONE bit-exact fp64 replay
+// for the winner, whole-cell exact fallback on (near-)ties.  0: the dense kernel (36 replays per cell).
+#ifndef SA_PRUNE
+#define SA_PRUNE 1
 #endif
-constexpr int FILL_MINB = SA_FILL_MINB;   // resident CTAs per SM the fill kernel is compiled for (register budget 128)
+#ifndef SA_TAB2D
+#define SA_TAB2D (SA_PRUNE ? 1 : 3)
+#endif
+#ifndef SA_FILL_MINB
+#define SA_FILL_MINB (SA_PRUNE ? 4 : (SA_TAB2D == 3 ? 1 : 3))
+#endif
+#ifndef SA_FILL_WARPS
+#define SA_FILL_WARPS (SA_TAB2D == 3 ? 12 : 4)
+#endif
+constexpr int FILL_MINB = SA_FILL_MINB;   // resident CTAs per SM the fill kernel is compiled for
 constexpr int CLUSTER_CTAS = 8;   // CTAs (SMs) per cluster of the cluster-cooperative variant used for huge problems
 constexpr int CLUSTER_MAIL_FLOATS = 16 + CLUSTER_CTAS * 16 + CLUSTER_CTAS * 8;  // per-cluster L2 mailbox
 constexpr int COOP_WARPS = 16;  // warps of the cooperative (one problem per CTA) variant used for large problems
-constexpr int FILL_WARPS = 4;  // warps per CTA of the fill kernel (one problem per warp at a time)
+constexpr int FILL_WARPS = SA_FILL_WARPS;  // warps per CTA of the fill kernel (one problem per warp at a time)
 
 }  // namespace sa

@@ -117,6 +117,10 @@ int sa_powf12(sa_ctx *ctx, const float *x, int64_t n, float *out, int use_fast_p
 /* Exhaustive device check: evaluates both device paths for every float bit pattern in [lo_bits, hi_bits) and
  * counts results that differ from `expected` (host libm powf supplied by the caller), chunk by chunk. */
 int sa_powf12_range(sa_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, float *out_fast, float *out_generic);
+/* Certification of the exact-pruning bound of the fill kernel: for every float bit pattern x in [lo_bits, hi_bits)
+ * checks on the device that the fp32 lower bound of powf(x, 1.2f) used to prune candidates really is <= the bit-exact
+ * replay (SegAligner.cpp:88).  *n_violations must come back 0; *min_ratio = smallest exact/bound seen (slack). */
+int sa_check_prune_bound(sa_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, uint64_t *n_violations, float *min_ratio);
 
 /* Last kernel timings of the most recent batch call on this context, in milliseconds (CUDA events). */
 typedef struct sa_timing {

@@ -164,6 +164,22 @@ def test_powf12_device_matches_host_libm(ctx, oracle):
     assert np.array_equal(bits(fast[samp]), bits(ref))
 
 
+def test_prune_bound_holds_for_every_float(ctx):
+    """The fill kernel prunes candidates with an fp32 lower bound of powf(d, 1.2f) (two MUFU approximations); the
+    pruning is exact only if that bound never exceeds the bit-exact replay.  Checked for EVERY non-negative float
+    (zero, subnormals, the whole normal range, +inf) on the device, 2^31 evaluations."""
+    total = 0
+    worst = 2.0
+    step = 1 << 28
+    for lo in range(0, 0x7f800001, step):
+        hi = min(lo + step, 0x7f800001)
+        n, r = ctx.check_prune_bound(lo, hi)
+        total += n
+        worst = min(worst, r)
+    assert total == 0, f"{total} floats where the pruning bound exceeds the exact powf"
+    assert worst > 1.0  # strict slack everywhere (the margin PRUNE_C is 2^-14 in the log2 domain)
+
+
 def test_unbanded_lookback_nl(ctx, oracle):
     """-nl: lookback = 9999999 (main.cpp:475-478) through the generic kernel, all modes."""
     rng = np.random.default_rng(31)
