@@ -347,7 +347,10 @@ __device__ __noinline__ float powf12_any(float ax, uint32_t t2d, uint32_t exp) {
 //   3. if its exact score is larger than the second largest `hi` (+ the key perturbation) it is the strict maximum and
 //      the cell is done; otherwise (ties and near-ties: rare) the whole cell is redone exactly by cell_slow().
 // Measured on the C2 workload: the second step settles > 99.9 % of the cells.
-constexpr float PRUNE_C = 0x1p-14f;  // log2-domain safety margin of delta_lo (MUFU errors are ~2^-22)
+#ifndef SA_PRUNE_C
+#define SA_PRUNE_C 0x1p-16f  // >= 1.316e-5 needed for every float (measured, tools/chk_prune.py); 2^-16 = 1.526e-5
+#endif
+constexpr float PRUNE_C = SA_PRUNE_C;  // log2-domain safety margin of delta_lo (MUFU errors are ~2^-22)
 __device__ __forceinline__ float delta_lo_approx(float d) {
     float a, e;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(fabsf(d)));
@@ -364,9 +367,12 @@ __device__ __forceinline__ float powf12_exact(float ax, const TabAddr ta, const 
     return f;
 }
 
-// Whole-cell re-evaluation for cells with an out-of-domain discrepancy (exact 0 mostly), same candidate order and
-// tie rule as the pipeline.  a_row = shared address of this lane's row operands (db[0..5], fb[0..5], 128 B apart);
-// f[] = fx (non-swap: fp_t by column look-back; with swap the row-side fb is read from a_row).
+// Whole-cell exact evaluation in the reference's candidate order and tie rule (scan dj, dq ascending, replace on >=:
+// the maximum, ties -> the LAST candidate in scan order).  Used by the dense kernel for cells with an out-of-domain
+// discrepancy and by the pruning kernel for (near-)ties; starts from an already exact (best, code) when the caller
+// has one and then skips the fp64 replay of every candidate whose upper bound cannot reach the running maximum.
+// a_row = shared address of this lane's row operands (db[0..5], fb[0..5], 128 B apart); f[] = fx (non-swap: fp_t by
+// column look-back; with swap the row-side fb is read from a_row).
 struct CellRes {
     float best;
     int code;
@@ -374,27 +380,32 @@ struct CellRes {
 __device__ __noinline__ CellRes cell_slow(bool swap, uint32_t a_row, float dx0, float dx1, float dx2, float dx3,
                                           float dx4, float dx5, float f0, float f1, float f2, float f3, float f4,
                                           float f5, uint32_t pc0, uint32_t pc1, uint32_t pc2, uint32_t pc3, uint32_t pc4,
-                                          uint32_t pc5, uint32_t t2d, uint32_t exp) {
+                                          uint32_t pc5, uint32_t t2d, uint32_t exp, float best0, int code0) {
     const float dx[LB] = {dx0, dx1, dx2, dx3, dx4, dx5};
     const float f[LB] = {f0, f1, f2, f3, f4, f5};
     const uint32_t pc[LB] = {pc0, pc1, pc2, pc3, pc4, pc5};
     CellRes res;
-    res.best = NEG_INF_F;
-    res.code = 0;
+    res.best = best0;
+    res.code = code0;
     for (int dj = 1; dj <= LB; dj++) {
         const float dbv = lds_f32(a_row + (dj - 1) * 128);
         const float fbv = swap ? lds_f32(a_row + (LB + dj - 1) * 128) : 0.0f;
         for (int dq = 1; dq <= LB; dq++) {
             const float sc = lds_f32(pc[dq - 1] - dj * 4);
-            const float discrep = fabsf(__fsub_rn(dbv, dx[dq - 1]));
-            const float delta = powf12_any(discrep, t2d, exp);
+            const float d = __fsub_rn(dbv, dx[dq - 1]);
             const float fn = 5000.0f * (float)((swap ? dq : dj) - 1);
             const float fp = swap ? fbv : f[dq - 1];
-            const float r = __fsub_rn(10000.0f, __fadd_rn(__fadd_rn(fn, fp), delta));
-            const float ns = __fadd_rn(sc, r);
-            if (ns >= res.best) {
+            const float fnfp = __fadd_rn(fn, fp);
+#if SA_PRUNE
+            const float hi = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, delta_lo_approx(d))));
+            if (!(hi >= res.best)) continue;  // its exact score is <= hi < the running maximum
+#endif
+            const float delta = powf12_any(fabsf(d), t2d, exp);
+            const float ns = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, delta)));
+            const int ck = 1 + (dj - 1) * LB + (dq - 1);
+            if (ns > res.best || (ns == res.best && ck >= res.code)) {
                 res.best = ns;
-                res.code = 1 + (dj - 1) * LB + (dq - 1);
+                res.code = ck;
             }
         }
     }
@@ -499,6 +510,11 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         int q = 0;  // column within the current round (>= nx: idle tail of a short round)
         int j = 0, jc = 0;
         bool row_ok = false, row_used = false;
+#if SA_PRUNE
+        float db[LB], fb[LB];  // row operands also in registers (pass 1 is fully unrolled; pass 2 reads the shared copy)
+#pragma unroll
+        for (int d = 0; d < LB; d++) db[d] = 0.0f, fb[d] = 0.0f;
+#endif
         uint32_t pc[LB];
         int slot = 0;
         float rm_s = 0.0f;  // detection: best positive score of this lane's row, ties -> larger q
@@ -517,6 +533,10 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     jc = row_ok ? j : nb - 1;
                     const float4 *src = reinterpret_cast<const float4 *>(bops + jc);
                     const float4 a = __ldg(src), b4 = __ldg(src + 1), c4 = __ldg(src + 2);
+#if SA_PRUNE
+                    db[0] = a.x, db[1] = a.y, db[2] = a.z, db[3] = a.w, db[4] = b4.x, db[5] = b4.y;
+                    fb[0] = b4.z, fb[1] = b4.w, fb[2] = c4.x, fb[3] = c4.y, fb[4] = c4.z, fb[5] = c4.w;
+#endif
                     // row operands go to lane-private shared memory: the look-back rows are a rolled loop (dynamic dj)
                     sts_f32(a_row + 0 * 128, a.x), sts_f32(a_row + 1 * 128, a.y), sts_f32(a_row + 2 * 128, a.z);
                     sts_f32(a_row + 3 * 128, a.w), sts_f32(a_row + 4 * 128, b4.x), sts_f32(a_row + 5 * 128, b4.y);
@@ -564,28 +584,24 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
 #if SA_PRUNE
                 float best = NEG_INF;
                 {
-                    // pass 1: upper bounds of all 36 candidates, two largest keys (candidate column index in bits 0..2)
+                    // pass 1: upper bounds `hi` of all 36 candidates; the two largest are tracked as keys whose low 6
+                    // mantissa bits carry the candidate number (-inf | code is a NaN, which fmaxf/fminf drop -- exactly
+                    // what a -inf candidate deserves; a perturbation of < 64 ulp is covered by the margin of step 3)
                     float m1 = NEG_INF, m2 = NEG_INF;
-                    int rowsel = 1;
-#pragma unroll 1
+                    const uint32_t kmask = P.key_mask;  // 0xFFFFFFC0 as a kernel parameter: one LOP3 per key
+#pragma unroll
                     for (int dj = 1; dj <= LB; dj++) {
-                        const float dbv = lds_f32(a_row + (dj - 1) * 128);
-                        const float fn = 5000.0f * (float)(dj - 1);
-                        float fbv = 0.0f;
-                        if (SWAP) fbv = lds_f32(a_row + (LB + dj - 1) * 128);
                         float key[LB];
 #pragma unroll
                         for (int c = 0; c < LB; c++) {
                             const float sc = lds_f32(pc[c] - dj * 4);
-                            const float e = delta_lo_approx(__fsub_rn(dbv, dx[c]));
-                            float fnfp;
-                            if (!SWAP) fnfp = __fadd_rn(fn, fx[c]);
-                            else fnfp = (c == 0) ? fbv : __fadd_rn(5000.0f * (float)c, fbv);
+                            const float e = delta_lo_approx(__fsub_rn(db[dj - 1], dx[c]));
+                            float fnfp;  // fn_t + fp_t (SegAligner.cpp:89-91); 0 + fp_t == fp_t bit for bit (fp_t >= +0)
+                            if (!SWAP) fnfp = (dj == 1) ? fx[c] : __fadd_rn(5000.0f * (float)(dj - 1), fx[c]);
+                            else fnfp = (c == 0) ? fb[dj - 1] : __fadd_rn(5000.0f * (float)c, fb[dj - 1]);
                             const float hi = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, e)));
-                            // -inf | c is a NaN for c != 0: fmaxf/fminf drop NaNs, which is what we want for -inf
-                            key[c] = __uint_as_float((__float_as_uint(hi) & 0xFFFFFFF8u) | (uint32_t)c);
+                            key[c] = __uint_as_float((__float_as_uint(hi) & kmask) | (uint32_t)((dj - 1) * LB + c));
                         }
-                        const float m1_before = m1;
 #pragma unroll
                         for (int c = 0; c < LB; c += 2) {
                             const float mx = fmaxf(key[c], key[c + 1]), mn = fminf(key[c], key[c + 1]);
@@ -593,14 +609,14 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                             m1 = fmaxf(m1, mx);
                             m2 = fmaxf(m2, fmaxf(mn, t));
                         }
-                        if (m1 > m1_before) rowsel = dj;
                     }
                     if (m1 > NEG_INF) {
                         // pass 2: the exact score of the best-looking candidate (dj, c) of this lane
-                        const int c = (int)(__float_as_uint(m1) & 7u), dj = rowsel;
-                        const float dbv = lds_f32(a_row + (dj - 1) * 128);
+                        const int k6 = (int)(__float_as_uint(m1) & 63u);
+                        const int djm = (k6 * 43) >> 8, c = k6 - djm * LB, dj = djm + 1;
+                        const float dbv = lds_f32(a_row + djm * 128);
                         const float dxv = __ldg(reinterpret_cast<const float *>(xops + q) + c);
-                        // ring slot of column q-1-c: the slots rotate, slot of column q-1 is `slot`-1 (mod 6)
+                        // ring slot of column q-1-c: the slots rotate, column q-1 sits in slot `slot`-1 (mod 6)
                         int sl = slot - 1 - c;
                         sl += (sl < 0) ? LB : 0;
                         const float sc = lds_f32(a_my + sl * (RING_W * 4) - dj * 4);
@@ -608,21 +624,22 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                         float fnfp;
                         if (!SWAP) {
                             const float fxv = __ldg(reinterpret_cast<const float *>(xops + q) + LB + c);
-                            fnfp = __fadd_rn(5000.0f * (float)(dj - 1), fxv);
+                            fnfp = __fadd_rn(5000.0f * (float)djm, fxv);
                         } else {
-                            const float fbv = lds_f32(a_row + (LB + dj - 1) * 128);
-                            fnfp = (c == 0) ? fbv : __fadd_rn(5000.0f * (float)c, fbv);
+                            const float fbv = lds_f32(a_row + (LB + djm) * 128);
+                            fnfp = __fadd_rn(5000.0f * (float)c, fbv);
                         }
                         best = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, delta)));
-                        code = 1 + (dj - 1) * LB + c;
-                        // every other candidate's exact score is <= its hi <= key + 8 ulp <= m2 + 2^-19 |m2|
-                        const float m2_up = __fmaf_ru(fabsf(m2), 0x1p-19f, m2);
+                        code = 1 + k6;
+                        // step 3: every other candidate's exact score is <= its hi < key + 64 ulp <= m2 + 2^-16 |m2|
+                        const float m2_up = __fmaf_ru(fabsf(m2), 0x1p-16f, m2);
                         if (!(best > m2_up)) {
-                            // rare: a tie or near-tie -> redo the whole cell exactly, in the reference's tie order
+                            // rare: a tie or near-tie -> exact scan of the cell in the reference's tie order
                             const CellRes cr = cell_slow(SWAP, a_row, dx[0], dx[1], dx[2], dx[3], dx[4], dx[5],
                                                          SWAP ? 0.0f : fx[0], SWAP ? 0.0f : fx[1], SWAP ? 0.0f : fx[2],
                                                          SWAP ? 0.0f : fx[3], SWAP ? 0.0f : fx[4], SWAP ? 0.0f : fx[5],
-                                                         pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], a_tab.t2d, a_tab.exp);
+                                                         pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], a_tab.t2d, a_tab.exp,
+                                                         best, code);
                             best = cr.best;
                             code = cr.code;
                         }
@@ -695,7 +712,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     const CellRes cr = cell_slow(SWAP, a_row, dx[0], dx[1], dx[2], dx[3], dx[4], dx[5], SWAP ? 0.0f : fx[0],
                                                  SWAP ? 0.0f : fx[1], SWAP ? 0.0f : fx[2], SWAP ? 0.0f : fx[3],
                                                  SWAP ? 0.0f : fx[4], SWAP ? 0.0f : fx[5], pc[0], pc[1], pc[2], pc[3], pc[4],
-                                                 pc[5], a_tab.t2d, a_tab.exp);
+                                                 pc[5], a_tab.t2d, a_tab.exp, NEG_INF, 0);
                     best = cr.best;
                     code = cr.code;
                 }
