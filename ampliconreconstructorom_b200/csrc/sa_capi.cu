@@ -231,7 +231,6 @@ int prepare_fill(sa_ctx *ctx, FillParams &P, const sa_mode *mode) {
     P.start_mode = mode->start_mode;
     P.fitting = mode->fitting;
     fill_powf_constants(P.pk);
-    P.key_mask = 0xFFFFFFC0u;
     const long long n_warps = (long long)n_fill_ctas(ctx) * FILL_WARPS;
     P.halo_stride = (long long)std::max(ctx->sides[1].max_labels, 1) * 8;
     CU(ctx->d_halo.reserve(sizeof(float) * (size_t)(n_warps * P.halo_stride)));

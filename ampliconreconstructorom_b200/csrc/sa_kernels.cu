@@ -584,14 +584,13 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
 #if SA_PRUNE
                 float best = NEG_INF;
                 {
-                    // pass 1: upper bounds `hi` of all 36 candidates; the two largest are tracked as keys whose low 6
-                    // mantissa bits carry the candidate number (-inf | code is a NaN, which fmaxf/fminf drop -- exactly
-                    // what a -inf candidate deserves; a perturbation of < 64 ulp is covered by the margin of step 3)
+                    // pass 1: upper bounds `hi` of all 36 candidates; the largest (m1, with its candidate number k6) and
+                    // the second largest (m2) are tracked exactly, two candidates per update
                     float m1 = NEG_INF, m2 = NEG_INF;
-                    const uint32_t kmask = P.key_mask;  // 0xFFFFFFC0 as a kernel parameter: one LOP3 per key
+                    int k6 = 0;
 #pragma unroll
                     for (int dj = 1; dj <= LB; dj++) {
-                        float key[LB];
+                        float hi[LB];
 #pragma unroll
                         for (int c = 0; c < LB; c++) {
                             const float sc = lds_f32(pc[c] - dj * 4);
@@ -599,20 +598,20 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                             float fnfp;  // fn_t + fp_t (SegAligner.cpp:89-91); 0 + fp_t == fp_t bit for bit (fp_t >= +0)
                             if (!SWAP) fnfp = (dj == 1) ? fx[c] : __fadd_rn(5000.0f * (float)(dj - 1), fx[c]);
                             else fnfp = (c == 0) ? fb[dj - 1] : __fadd_rn(5000.0f * (float)c, fb[dj - 1]);
-                            const float hi = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, e)));
-                            key[c] = __uint_as_float((__float_as_uint(hi) & kmask) | (uint32_t)((dj - 1) * LB + c));
+                            hi[c] = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, e)));
                         }
 #pragma unroll
                         for (int c = 0; c < LB; c += 2) {
-                            const float mx = fmaxf(key[c], key[c + 1]), mn = fminf(key[c], key[c + 1]);
+                            const float mx = fmaxf(hi[c], hi[c + 1]), mn = fminf(hi[c], hi[c + 1]);
+                            const int kmx = (hi[c] >= hi[c + 1]) ? (dj - 1) * LB + c : (dj - 1) * LB + c + 1;
                             const float t = fminf(m1, mx);
+                            k6 = (mx > m1) ? kmx : k6;
                             m1 = fmaxf(m1, mx);
                             m2 = fmaxf(m2, fmaxf(mn, t));
                         }
                     }
                     if (m1 > NEG_INF) {
                         // pass 2: the exact score of the best-looking candidate (dj, c) of this lane
-                        const int k6 = (int)(__float_as_uint(m1) & 63u);
                         const int djm = (k6 * 43) >> 8, c = k6 - djm * LB, dj = djm + 1;
                         const float dbv = lds_f32(a_row + djm * 128);
                         const float dxv = __ldg(reinterpret_cast<const float *>(xops + q) + c);
@@ -631,9 +630,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                         }
                         best = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, delta)));
                         code = 1 + k6;
-                        // step 3: every other candidate's exact score is <= its hi < key + 64 ulp <= m2 + 2^-16 |m2|
-                        const float m2_up = __fmaf_ru(fabsf(m2), 0x1p-16f, m2);
-                        if (!(best > m2_up)) {
+                        // step 3: every other candidate's exact score is <= its hi <= m2
+                        if (!(best > m2)) {
                             // rare: a tie or near-tie -> exact scan of the cell in the reference's tie order
                             const CellRes cr = cell_slow(SWAP, a_row, dx[0], dx[1], dx[2], dx[3], dx[4], dx[5],
                                                          SWAP ? 0.0f : fx[0], SWAP ? 0.0f : fx[1], SWAP ? 0.0f : fx[2],

@@ -47,7 +47,6 @@ struct FillParams {
     float *rowmax_s;  // detection only: per-row best positive score / its column (ties -> larger q)
     int32_t *rowmax_q;
     const int64_t *row_off;  // per problem offset into the rowmax arrays
-    uint32_t key_mask;  // 0xFFFFFFC0 (pruning keys: a register operand, so that `(hi & mask) | code` is one LOP3)
     double pk[12];  // fp64 constants of the powf replay (kernel-parameter bank => direct DFMA operands)
 };
 
