@@ -36,7 +36,7 @@ class Timing(C.Structure):
 EXPORTS = [
     "sa_device_count", "sa_ctx_create", "sa_ctx_destroy", "sa_last_error", "sa_set_maps", "sa_score_batch",
     "sa_plan_create", "sa_plan_destroy", "sa_plan_score", "sa_plan_results", "sa_plan_info", "sa_sync", "sa_align_batch", "sa_detect_batch", "sa_fill_one", "sa_powf12",
-    "sa_powf12_range", "sa_check_prune_bound", "sa_get_timing", "sa_measure_fp64_peak", "sa_event_record", "sa_event_elapsed_ms",
+    "sa_powf12_range", "sa_check_prune_bound", "sa_get_timing", "sa_get_prune_stats", "sa_measure_fp64_peak", "sa_event_record", "sa_event_elapsed_ms",
     "sa_host_non_collapse_probs", "sa_host_make_reverse", "sa_host_parse_cmap", "sa_host_score_thresholds",
     "sa_host_format_float", "sa_digest",
 ]
@@ -76,6 +76,7 @@ def load_library() -> C.CDLL:
     lib.sa_powf12_range.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp]
     lib.sa_check_prune_bound.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
     lib.sa_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    lib.sa_get_prune_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.sa_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.sa_digest.argtypes = [vp, vp, i64, C.c_char_p, i32, i32, i64, vp, C.POINTER(i64)]
     lib.sa_event_record.argtypes = [vp, i32]
@@ -330,6 +331,12 @@ class Context:
         out = np.zeros_like(x)
         self._check(self.lib.sa_powf12(self.h, _ptr(x), x.size, _ptr(out), 1 if fast else 0), "sa_powf12")
         return out
+
+    def prune_stats(self):
+        """(bit-exact powf replays, cells rescanned exactly) executed by the fill kernels of the last batch call."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.sa_get_prune_stats(self.h, C.byref(a), C.byref(b)), "sa_get_prune_stats")
+        return int(a.value), int(b.value)
 
     def check_prune_bound(self, lo_bits: int, hi_bits: int):
         """(violations, min exact/bound) of the pruning lower bound over the float bit patterns [lo_bits, hi_bits)."""

@@ -235,7 +235,7 @@ int prepare_fill(sa_ctx *ctx, FillParams &P, const sa_mode *mode) {
     P.halo_stride = (long long)std::max(ctx->sides[1].max_labels, 1) * 8;
     CU(ctx->d_halo.reserve(sizeof(float) * (size_t)(n_warps * P.halo_stride)));
     CU(ctx->d_halo2.reserve(sizeof(float) * (size_t)((long long)ctx->n_sms * P.halo_stride)));
-    CU(ctx->d_counter.reserve(4 * sizeof(unsigned long long)));
+    CU(ctx->d_counter.reserve(8 * sizeof(unsigned long long)));
     if (ctx->n_clusters > 0) {
         CU(ctx->d_halo3.reserve(sizeof(float) * (size_t)((long long)ctx->n_clusters * P.halo_stride)));
         CU(ctx->d_mail.reserve(sizeof(float) * (size_t)ctx->n_clusters * CLUSTER_MAIL_FLOATS));
@@ -248,7 +248,8 @@ int prepare_fill(sa_ctx *ctx, FillParams &P, const sa_mode *mode) {
 int launch_fill_classes(sa_ctx *ctx, FillParams P, const int32_t *d_order, const Plan &plan, bool store, bool swap) {
     const int64_t n_bulk = plan.n_bulk, n_large = plan.n_large, n_huge = plan.n_huge;
     unsigned long long *counters = ctx->d_counter.as<unsigned long long>();
-    CU(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    P.stats = counters + 4;
     int launches = 0;
     if (n_large > 0 || n_huge > 0) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
     if (n_huge > 0) {  // longest first: clusters of CLUSTER_CTAS SMs
@@ -830,6 +831,19 @@ int sa_check_prune_bound(sa_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, uint64
     CU(cudaMemcpyAsync(min_ratio, d_r, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     *n_violations = h_n;
+    return SA_OK;
+}
+
+int sa_get_prune_stats(sa_ctx *ctx, uint64_t *n_replays, uint64_t *n_rescans) {
+    if (!ctx || !n_replays || !n_rescans) return SA_EINVAL;
+    *n_replays = *n_rescans = 0;
+    if (!ctx->d_counter.p) return SA_OK;
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, ctx->d_counter.as<unsigned long long>() + 4, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *n_replays = h[0];
+    *n_rescans = h[1];
     return SA_OK;
 }
 

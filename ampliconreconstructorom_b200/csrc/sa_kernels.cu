@@ -495,6 +495,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
             Cout = P.code + P.cell_off[pidx];
         }
 
+        unsigned n_replay = 0, n_rescan = 0;  // pruning statistics of this lane: fp64 replays, whole-cell rescans
         // backtrack-start tracking (per lane, reduced at the end)
         float st_s = NEG_INF;
         int st_j = -1, st_q = -1;
@@ -630,6 +631,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                         }
                         best = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, delta)));
                         code = 1 + k6;
+                        n_replay++;
                         // step 3: every other candidate's exact score is <= its hi <= m2
                         if (!(best > m2)) {
                             // rare: a tie or near-tie -> exact scan of the cell in the reference's tie order
@@ -640,6 +642,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                                                          best, code);
                             best = cr.best;
                             code = cr.code;
+                            n_rescan++;
                         }
                     }
                 }
@@ -847,6 +850,13 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                         }
                     }
                 }
+            }
+        }
+        if (P.stats) {
+            const unsigned a = __reduce_add_sync(0xffffffffu, n_replay), b = __reduce_add_sync(0xffffffffu, n_rescan);
+            if (lane == 0) {
+                atomicAdd(P.stats, (unsigned long long)a);
+                if (b) atomicAdd(P.stats + 1, (unsigned long long)b);
             }
         }
         if ((NW == 1 && lane == 0) || (NW > 1 && threadIdx.x == 0 && crank == 0)) {

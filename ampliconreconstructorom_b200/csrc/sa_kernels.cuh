@@ -42,6 +42,7 @@ struct FillParams {
     float *halo;    // per work-unit (warp, or CTA in the cooperative variant) scratch: halo_stride floats each
     long long halo_stride;
     unsigned long long *counter;  // work-queue head
+    unsigned long long *stats;    // [0] fp64 replays executed, [1] cells rescanned exactly (pruning kernel), or nullptr
     float *cluster_mail;          // cluster variant: CLUSTER_MAIL_FLOATS floats per cluster
     int init_mode, start_mode, fitting;
     float *rowmax_s;  // detection only: per-row best positive score / its column (ties -> larger q)
@@ -102,10 +103,10 @@ void fill_powf_constants(double *pk);
 #define SA_TAB2D (SA_PRUNE ? 1 : 3)
 #endif
 #ifndef SA_FILL_MINB
-#define SA_FILL_MINB (SA_PRUNE ? 4 : (SA_TAB2D == 3 ? 1 : 3))
+#define SA_FILL_MINB (SA_PRUNE ? 3 : (SA_TAB2D == 3 ? 1 : 3))
 #endif
 #ifndef SA_FILL_WARPS
-#define SA_FILL_WARPS (SA_TAB2D == 3 ? 12 : 4)
+#define SA_FILL_WARPS (SA_PRUNE ? 8 : (SA_TAB2D == 3 ? 12 : 4))
 #endif
 constexpr int FILL_MINB = SA_FILL_MINB;   // resident CTAs per SM the fill kernel is compiled for
 constexpr int CLUSTER_CTAS = 8;   // CTAs (SMs) per cluster of the cluster-cooperative variant used for huge problems

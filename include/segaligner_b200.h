@@ -130,6 +130,10 @@ typedef struct sa_timing {
     int32_t reserved;
 } sa_timing;
 int sa_get_timing(sa_ctx *ctx, sa_timing *t);
+/* Work actually executed by the fill kernels of the last batch call: the fill prunes the 36 predecessor candidates
+ * of a cell (SegAligner.cpp:108-127) with an fp32 bound and replays powf bit-exactly only for the winner.
+ * n_replays = bit-exact powf replays (about one per cell), n_rescans = cells rescanned exactly after a (near-)tie. */
+int sa_get_prune_stats(sa_ctx *ctx, uint64_t *n_replays, uint64_t *n_rescans);
 
 /* Microbenchmark: sustained fp64 FMA issue rate (DFMA instructions/s, whole GPU) used as roofline peak. */
 int sa_measure_fp64_peak(sa_ctx *ctx, double *dfma_per_s);
