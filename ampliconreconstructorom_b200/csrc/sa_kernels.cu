@@ -379,11 +379,9 @@ struct CellRes {
 };
 __device__ __noinline__ CellRes cell_slow(bool swap, uint32_t a_row, float dx0, float dx1, float dx2, float dx3,
                                           float dx4, float dx5, float f0, float f1, float f2, float f3, float f4,
-                                          float f5, uint32_t pc0, uint32_t pc1, uint32_t pc2, uint32_t pc3, uint32_t pc4,
-                                          uint32_t pc5, uint32_t t2d, uint32_t exp, float best0, int code0) {
+                                          float f5, uint32_t pbase, uint32_t t2d, uint32_t exp, float best0, int code0) {
     const float dx[LB] = {dx0, dx1, dx2, dx3, dx4, dx5};
     const float f[LB] = {f0, f1, f2, f3, f4, f5};
-    const uint32_t pc[LB] = {pc0, pc1, pc2, pc3, pc4, pc5};
     CellRes res;
     res.best = best0;
     res.code = code0;
@@ -391,7 +389,7 @@ __device__ __noinline__ CellRes cell_slow(bool swap, uint32_t a_row, float dx0, 
         const float dbv = lds_f32(a_row + (dj - 1) * 128);
         const float fbv = swap ? lds_f32(a_row + (LB + dj - 1) * 128) : 0.0f;
         for (int dq = 1; dq <= LB; dq++) {
-            const float sc = lds_f32(pc[dq - 1] - dj * 4);
+            const float sc = lds_f32(pbase + (LB - dq) * (40 * 4) - dj * 4);  // mirrored ring, see PC() in fill_kernel
             const float d = __fsub_rn(dbv, dx[dq - 1]);
             const float fn = 5000.0f * (float)((swap ? dq : dj) - 1);
             const float fp = swap ? fbv : f[dq - 1];
@@ -433,8 +431,11 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
     const int crank = (CS > 1) ? (int)cg::this_cluster().block_rank() : 0;
     extern __shared__ unsigned char s_dyn[];
     PowTabSmem &s_tab = *tab_place(s_dyn);
-    __shared__ float s_ring[WPC][LB][RING_W];
-    __shared__ float s_rowop[WPC][2 * LB][32];  // per lane: db[0..5], fb[0..5] of its row (LabelOps), lane-private
+    // dynamic shared memory behind the table region: the mirrored ring (column q lives in slots q%6 and q%6+6, see
+    // PC()) and the lane-private row operands db[0..5], fb[0..5] (LabelOps of the lane's row)
+    float(*s_ring)[2 * LB][RING_W] = reinterpret_cast<float(*)[2 * LB][RING_W]>(s_dyn + TAB_SMEM_BYTES);
+    float(*s_rowop)[2 * LB][32] =
+        reinterpret_cast<float(*)[2 * LB][32]>(s_dyn + TAB_SMEM_BYTES + WPC * 2 * LB * RING_W * sizeof(float));
     __shared__ float s_xbuf[WPC][2][8];
     __shared__ unsigned long long s_next;
     __shared__ float s_red_s[WPC];
@@ -516,15 +517,16 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
 #pragma unroll
         for (int d = 0; d < LB; d++) db[d] = 0.0f, fb[d] = 0.0f;
 #endif
-        uint32_t pc[LB];
+        // Mirrored ring: the value of column q is written to slots s = q % 6 AND s + 6, so the six previous columns
+        // q-1-c (c = 0..5) sit at the STATIC offsets (5 - c) from slot s: no pointer rotation, immediate LDS offsets.
+        uint32_t pbase = a_my;  // a_my + slot * RING_W * 4
+#define PC(c) (pbase + (uint32_t)((LB - 1 - (c)) * RING_W * 4))
         int slot = 0;
         float rm_s = 0.0f;  // detection: best positive score of this lane's row, ties -> larger q
         int rm_q = -1;
-#pragma unroll
-        for (int d = 0; d < LB; d++) pc[d] = a_my;
 
         for (long long t = 0; t < T; t++) {
-            const bool active = (t >= w) && (strip < nstrips) && (q < nx);
+            const bool active = (NW == 1) ? true : ((t >= w) && (strip < nstrips) && (q < nx));  // NW==1: T = nstrips*nx
             float val = 0.0f, rv = 0.0f, hv = NEG_INF;
             int code = 0;
             if (active) {
@@ -548,15 +550,13 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     row_used = used ? ((used[jc >> 5] >> (jc & 31)) & 1u) : false;
                     __syncwarp();
 #pragma unroll
-                    for (int s = 0; s < LB; s++) {
+                    for (int s = 0; s < 2 * LB; s++) {
                         sts_f32(a_my + s * RING_W * 4, NEG_INF);
                         if (lane < 6) sts_f32(a_halo + s * RING_W * 4, NEG_INF);
                     }
                     __syncwarp();
-                    // shared addresses of this lane's entry in the slots holding columns q-1..q-6 (pc[0] -> q-1)
-#pragma unroll
-                    for (int d = 0; d < LB; d++) pc[d] = a_my + ((LB - 1 - d) % LB) * RING_W * 4;
                     slot = 0;
+                    pbase = a_my;
                     rm_s = 0.0f;
                     rm_q = -1;
                 }
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                         float hi[LB];
 #pragma unroll
                         for (int c = 0; c < LB; c++) {
-                            const float sc = lds_f32(pc[c] - dj * 4);
+                            const float sc = lds_f32(PC(c) - dj * 4);
                             const float e = delta_lo_approx(__fsub_rn(db[dj - 1], dx[c]));
                             float fnfp;  // fn_t + fp_t (SegAligner.cpp:89-91); 0 + fp_t == fp_t bit for bit (fp_t >= +0)
                             if (!SWAP) fnfp = (dj == 1) ? fx[c] : __fadd_rn(5000.0f * (float)(dj - 1), fx[c]);
@@ -616,10 +616,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                         const int djm = (k6 * 43) >> 8, c = k6 - djm * LB, dj = djm + 1;
                         const float dbv = lds_f32(a_row + djm * 128);
                         const float dxv = __ldg(reinterpret_cast<const float *>(xops + q) + c);
-                        // ring slot of column q-1-c: the slots rotate, column q-1 sits in slot `slot`-1 (mod 6)
-                        int sl = slot - 1 - c;
-                        sl += (sl < 0) ? LB : 0;
-                        const float sc = lds_f32(a_my + sl * (RING_W * 4) - dj * 4);
+                        const float sc = lds_f32(PC(c) - dj * 4);
                         const float delta = powf12_exact(fabsf(__fsub_rn(dbv, dxv)), a_tab, P.pk);
                         float fnfp;
                         if (!SWAP) {
@@ -638,8 +635,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                             const CellRes cr = cell_slow(SWAP, a_row, dx[0], dx[1], dx[2], dx[3], dx[4], dx[5],
                                                          SWAP ? 0.0f : fx[0], SWAP ? 0.0f : fx[1], SWAP ? 0.0f : fx[2],
                                                          SWAP ? 0.0f : fx[3], SWAP ? 0.0f : fx[4], SWAP ? 0.0f : fx[5],
-                                                         pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], a_tab.t2d, a_tab.exp,
-                                                         best, code);
+                                                         pbase, a_tab.t2d, a_tab.exp, best, code);
                             best = cr.best;
                             code = cr.code;
                             n_rescan++;
@@ -664,9 +660,9 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
 #pragma unroll
                         for (int c = 0; c < LB; c++) {
 #ifdef SA_KO_PRED
-                            sc[c] = __uint_as_float(pc[c] - djh * 4);
+                            sc[c] = __uint_as_float(PC(c) - djh * 4);
 #else
-                            sc[c] = lds_f32(pc[c] - djh * 4);
+                            sc[c] = lds_f32(PC(c) - djh * 4);
 #endif
                         }
                         if (h == 0) {
@@ -712,8 +708,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     // replay is undefined -> redo the whole cell, candidate by candidate
                     const CellRes cr = cell_slow(SWAP, a_row, dx[0], dx[1], dx[2], dx[3], dx[4], dx[5], SWAP ? 0.0f : fx[0],
                                                  SWAP ? 0.0f : fx[1], SWAP ? 0.0f : fx[2], SWAP ? 0.0f : fx[3],
-                                                 SWAP ? 0.0f : fx[4], SWAP ? 0.0f : fx[5], pc[0], pc[1], pc[2], pc[3], pc[4],
-                                                 pc[5], a_tab.t2d, a_tab.exp, NEG_INF, 0);
+                                                 SWAP ? 0.0f : fx[4], SWAP ? 0.0f : fx[5], pbase, a_tab.t2d, a_tab.exp,
+                                                 NEG_INF, 0);
                     best = cr.best;
                     code = cr.code;
                 }
@@ -727,8 +723,12 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
             __syncwarp();
             if (active) {
                 // publish column q: own row, the 6 rows above the strip, and our bottom rows for the strip below
-                sts_f32(a_my + slot * RING_W * 4, rv);
-                if (lane < 6) sts_f32(a_halo + slot * RING_W * 4, hv);
+                sts_f32(pbase, rv);
+                sts_f32(pbase + LB * RING_W * 4, rv);
+                if (lane < 6) {
+                    sts_f32(pbase - 24, hv);  // a_halo = a_my - 6 floats
+                    sts_f32(pbase - 24 + LB * RING_W * 4, hv);
+                }
                 if (lane >= 26) {
                     if (NW == 1 || w == NWT - 1) __stcg(halo + (long long)q * 8 + (lane - 26), rv);
                     else if (CS > 1 && warp == NW - 1) __stcg(cmail + 16 + (crank * 2 + (t & 1)) * 8 + (lane - 26), rv);
@@ -760,7 +760,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                             st_j = j;
                             st_q = q;
                         }
-                    } else if (P.start_mode == SA_START_SEMIGLOBAL) {
+                    } else if (P.start_mode == SA_START_SEMIGLOBAL && (q >= nx - 2 || strip == nstrips - 1)) {  // warp-uniform
                         // scan order of sg_aln_backtrack_start: last row by q, then rows by j over the last 2 columns
                         const bool last_row = (j == nb - 1);
                         const bool last_cols = (q >= nx - 2);
@@ -775,13 +775,10 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                         }
                     }
                 }
-                // rotate the column pointers
-#pragma unroll
-                for (int d = LB - 1; d > 0; d--) pc[d] = pc[d - 1];
-                pc[0] = a_my + slot * RING_W * 4;
                 slot = (slot == LB - 1) ? 0 : slot + 1;
+                pbase = a_my + slot * (RING_W * 4);
             }
-            if (t >= w && strip < nstrips) {  // advance within the round (idle steps of a short round included)
+            if (NW == 1 || (t >= w && strip < nstrips)) {  // advance within the round (idle steps of a short round included)
                 q++;
                 if (q == R) {
                     q = 0;
@@ -1264,9 +1261,13 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *sink, int iters)
     if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
 }
 
+// dynamic shared memory of a fill CTA with `wpc` warps: table region + mirrored ring + row operands
+static size_t fill_dyn_smem(int wpc) {
+    return TAB_SMEM_BYTES + (size_t)wpc * (2 * LB * RING_W + 2 * LB * 32) * sizeof(float);
+}
 template <int NW, int MINB, int CS>
 static void launch_fill_t(const FillParams &p, bool store, bool swap, int n_ctas, cudaStream_t st) {
-    const size_t sm = TAB_SMEM_BYTES;
+    const size_t sm = fill_dyn_smem(NW == 1 ? FILL_WARPS : NW);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_ctas);
     cfg.blockDim = dim3((NW == 1 ? FILL_WARPS : NW) * 32);
@@ -1338,7 +1339,7 @@ int max_clusters() {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CLUSTER_CTAS * 64);
     cfg.blockDim = dim3(COOP_WARPS * 32);
-    cfg.dynamicSmemBytes = TAB_SMEM_BYTES;
+    cfg.dynamicSmemBytes = fill_dyn_smem(COOP_WARPS);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CLUSTER_CTAS;
@@ -1347,7 +1348,7 @@ int max_clusters() {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaFuncSetAttribute(fill_kernel<false, false, COOP_WARPS, 1, CLUSTER_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)TAB_SMEM_BYTES);
+                         (int)fill_dyn_smem(COOP_WARPS));
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, fill_kernel<false, false, COOP_WARPS, 1, CLUSTER_CTAS>, &cfg) != cudaSuccess) {
         cudaGetLastError();
@@ -1358,8 +1359,9 @@ int max_clusters() {
 int fill_ctas_per_sm() {
     int n = 0;
     cudaFuncSetAttribute(fill_kernel<false, false, 1, FILL_MINB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)TAB_SMEM_BYTES);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<false, false, 1, FILL_MINB, 1>, FILL_WARPS * 32, TAB_SMEM_BYTES);
+                         (int)fill_dyn_smem(FILL_WARPS));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<false, false, 1, FILL_MINB, 1>, FILL_WARPS * 32,
+                                                  fill_dyn_smem(FILL_WARPS));
     return n > 0 ? n : 1;
 }
 

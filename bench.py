@@ -265,6 +265,7 @@ def main():
     stop.set()
     res = plan.results()
     info = plan.info()
+    n_replays, n_rescans = ctx.prune_stats()  # work the last launch actually executed (exact pruning)
     checksum = float(np.sum(res["score"].astype(np.float64)))
 
     # ---- end to end through the host-buffer C-ABI calls (pinned host memory in, host results out)
@@ -314,7 +315,15 @@ def main():
                          "unit": "T fp64-instr/s (thread-level DFMA/DADD/DMUL)", "frac": achieved / peak,
                          "peak_source": "live DFMA microbenchmark on this GPU (sa_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no fp64 entry",
-                         "algorithmic": "18 fp64 instr per predecessor evaluation x pair evaluations per launch",
+                         "algorithmic": "18 fp64 instr per predecessor evaluation x pair evaluations per launch "
+                                        "(the reference's un-pruned work, SURVEY 8(d)); frac > 1 is possible because the "
+                                        "kernel prunes exactly: fp32 bounds for all candidates, one bit-exact replay per cell",
+                         "executed": {"powf_replays_per_launch": n_replays, "cells_rescanned_per_launch": n_rescans,
+                                      "replays_per_cell": n_replays / cells,
+                                      "fp64_instr_per_s_T": 17.0 * n_replays / (fill_ms[-1] * 1e-3) / 1e12,
+                                      "frac_of_fp64_peak": 17.0 * n_replays / (fill_ms[-1] * 1e-3) / peak,
+                                      "note": "executed work is bound by the XU pipe (2 MUFU per candidate, 16 lanes/clk/SM) "
+                                              "and by issue slots, not by fp64 issue; see DESIGN.md 4.1"},
                          "kernel_ms_per_launch": sum(fill_ms) / K, "traffic": None,
                          "hbm_note": "HBM traffic is O(results): <1e-3 of measured copy bandwidth"},
             "clocks": summarise_clocks(samples),

@@ -2,7 +2,7 @@
 // no DP ring, no problem queue, no step bookkeeping.  Measures sub-partition cycles per predecessor evaluation for
 // 1..4 warps per sub-partition.  Build variants with -DSA_KO_* / -DSA_INT_CVT=.. to see what each piece costs.
 // Developer tool (round 1 cost model); includes the product kernels' source to reuse their device functions.
-#include "../ampliconreconstructorom_b200/csrc/sa_kernels.cu"
+#include "../ampliconreconstructorom_b200/csrc/sa_kernels.cu"  // NOTE: written against the dense pipeline (SA_PRUNE=0 era); row_prefetch/row_powf still exist
 using namespace sa;
 template <int TAIL>
 __global__ void __launch_bounds__(512) evalk(float *out, int steps, const float *dxs, FillParams P) {
