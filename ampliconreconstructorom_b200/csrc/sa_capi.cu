@@ -152,7 +152,7 @@ void build_plan(const sa_ctx *c, const sa_problem *pr, int64_t n, int n_warp_slo
     if (const char *e = getenv("SA_HUGE_MIN_CELLS")) huge_min_cells = atof(e);
     // the cluster wavefront pays a cluster barrier per step and idles when nx < its 128 warps, so it is reserved for
     // problems that would otherwise be the tail: single-SM time > alpha_huge x the batch's ideal makespan
-    double alpha_huge = 2.0;
+    double alpha_huge = 0.7;  // measured on the C3 detection sweep (alignment rounds of ~80 chromosome x region problems)
     if (const char *e = getenv("SA_HUGE_ALPHA")) alpha_huge = atof(e);
     const double thresh_huge =
         (c->n_clusters > 0 && alpha > 0 && !no_cluster) ? std::min(alpha, alpha_huge) * 0 + (alpha < 1e-6 ? alpha : alpha_huge) * total / (double)c->n_sms : 1e300;
@@ -234,7 +234,7 @@ int prepare_fill(sa_ctx *ctx, FillParams &P, const sa_mode *mode) {
     const long long n_warps = (long long)n_fill_ctas(ctx) * FILL_WARPS;
     P.halo_stride = (long long)std::max(ctx->sides[1].max_labels, 1) * 8;
     CU(ctx->d_halo.reserve(sizeof(float) * (size_t)(n_warps * P.halo_stride)));
-    CU(ctx->d_halo2.reserve(sizeof(float) * (size_t)((long long)ctx->n_sms * P.halo_stride)));
+    CU(ctx->d_halo2.reserve(sizeof(float) * (size_t)((long long)ctx->n_sms * COOP_MINB * P.halo_stride)));
     CU(ctx->d_counter.reserve(8 * sizeof(unsigned long long)));
     if (ctx->n_clusters > 0) {
         CU(ctx->d_halo3.reserve(sizeof(float) * (size_t)((long long)ctx->n_clusters * P.halo_stride)));
@@ -273,7 +273,7 @@ int launch_fill_classes(sa_ctx *ctx, FillParams P, const int32_t *d_order, const
         L.n_problems = n_large;
         L.counter = counters + 1;
         L.halo = ctx->d_halo2.as<float>();
-        launch_fill(L, store, swap, 1, (int)std::min<int64_t>(n_large, ctx->n_sms), ctx->stream2);
+        launch_fill(L, store, swap, 1, (int)std::min<int64_t>(n_large, (int64_t)ctx->n_sms * COOP_MINB), ctx->stream2);
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
         launches++;

@@ -741,8 +741,10 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
             if (active) {
                 if (row_ok) {
                     if (STORE) {
+#ifndef SA_KO_STORE
                         Sout[(long long)j * nx + q] = val;
                         Cout[(long long)j * nx + q] = (uint8_t)code;
+#endif
                         if (P.rowmax_s) {
                             if (val > 0.0f && val >= rm_s) {
                                 rm_s = val;
@@ -1296,8 +1298,8 @@ static void launch_fill_t(const FillParams &p, bool store, bool swap, int n_ctas
 }
 // shape: 0 = bulk (one warp per problem), 1 = cooperative CTA, 2 = cooperative cluster of CLUSTER_CTAS CTAs
 void launch_fill(const FillParams &p, bool store, bool swap, int shape, int n_ctas, cudaStream_t st) {
-    if (shape == 2) launch_fill_t<COOP_WARPS, 1, CLUSTER_CTAS>(p, store, swap, n_ctas, st);
-    else if (shape == 1) launch_fill_t<COOP_WARPS, 1, 1>(p, store, swap, n_ctas, st);
+    if (shape == 2) launch_fill_t<CLUSTER_WARPS, 1, CLUSTER_CTAS>(p, store, swap, n_ctas, st);
+    else if (shape == 1) launch_fill_t<COOP_WARPS, COOP_MINB, 1>(p, store, swap, n_ctas, st);
     else launch_fill_t<1, FILL_MINB, 1>(p, store, swap, n_ctas, st);
 }
 
@@ -1338,8 +1340,8 @@ void launch_dfma_peak(double *sink, int iters, int n_ctas, cudaStream_t st) {
 int max_clusters() {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CLUSTER_CTAS * 64);
-    cfg.blockDim = dim3(COOP_WARPS * 32);
-    cfg.dynamicSmemBytes = fill_dyn_smem(COOP_WARPS);
+    cfg.blockDim = dim3(CLUSTER_WARPS * 32);
+    cfg.dynamicSmemBytes = fill_dyn_smem(CLUSTER_WARPS);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CLUSTER_CTAS;
@@ -1347,10 +1349,10 @@ int max_clusters() {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaFuncSetAttribute(fill_kernel<false, false, COOP_WARPS, 1, CLUSTER_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)fill_dyn_smem(COOP_WARPS));
+    cudaFuncSetAttribute(fill_kernel<false, false, CLUSTER_WARPS, 1, CLUSTER_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)fill_dyn_smem(CLUSTER_WARPS));
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, fill_kernel<false, false, COOP_WARPS, 1, CLUSTER_CTAS>, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&n, fill_kernel<false, false, CLUSTER_WARPS, 1, CLUSTER_CTAS>, &cfg) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }

@@ -111,7 +111,16 @@ void fill_powf_constants(double *pk);
 constexpr int FILL_MINB = SA_FILL_MINB;   // resident CTAs per SM the fill kernel is compiled for
 constexpr int CLUSTER_CTAS = 8;   // CTAs (SMs) per cluster of the cluster-cooperative variant used for huge problems
 constexpr int CLUSTER_MAIL_FLOATS = 16 + CLUSTER_CTAS * 16 + CLUSTER_CTAS * 8;  // per-cluster L2 mailbox
-constexpr int COOP_WARPS = 16;  // warps of the cooperative (one problem per CTA) variant used for large problems
+#ifndef SA_COOP_WARPS
+#define SA_COOP_WARPS (SA_PRUNE ? 8 : 16)
+#endif
+#ifndef SA_COOP_MINB
+#define SA_COOP_MINB (SA_PRUNE ? 3 : 1)
+#endif
+constexpr int COOP_WARPS = SA_COOP_WARPS;  // warps of the cooperative (one problem per CTA) variant used for large problems
+constexpr int COOP_MINB = SA_COOP_MINB;    // resident cooperative CTAs per SM (register budget 65536 / (MINB * 32 * warps))
+constexpr int CLUSTER_WARPS = 16;  // warps per CTA of the cluster shape: its step barrier is a cluster barrier (~2 us), so
+                                   // huge problems want the widest wavefront (8 SMs x 16 warps), one CTA per SM
 constexpr int FILL_WARPS = SA_FILL_WARPS;  // warps per CTA of the fill kernel (one problem per warp at a time)
 
 }  // namespace sa
