@@ -35,7 +35,7 @@ class Timing(C.Structure):
 # every symbol include/segaligner_b200.h declares (tests check the library exports exactly these)
 EXPORTS = [
     "sa_device_count", "sa_ctx_create", "sa_ctx_destroy", "sa_last_error", "sa_set_maps", "sa_score_batch",
-    "sa_plan_create", "sa_plan_destroy", "sa_plan_score", "sa_plan_results", "sa_plan_info", "sa_sync", "sa_align_batch", "sa_detect_batch", "sa_fill_one", "sa_powf12",
+    "sa_plan_create", "sa_plan_destroy", "sa_plan_score", "sa_plan_results", "sa_plan_info", "sa_sync", "sa_align_batch", "sa_align_batch_packed", "sa_detect_batch", "sa_fill_one", "sa_powf12",
     "sa_powf12_range", "sa_check_prune_bound", "sa_get_timing", "sa_get_prune_stats", "sa_measure_fp64_peak", "sa_event_record", "sa_event_elapsed_ms",
     "sa_host_non_collapse_probs", "sa_host_make_reverse", "sa_host_parse_cmap", "sa_host_score_thresholds",
     "sa_host_format_float", "sa_digest",

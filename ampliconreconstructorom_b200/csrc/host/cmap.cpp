@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <thread>
 
 namespace sah {
 
@@ -222,26 +223,47 @@ bool print_alignment(const std::string &outname, const std::vector<AlnEntry> &al
     return true;
 }
 
+// number of host threads for the embarrassingly parallel text / sort phases (not the reference's -nthreads, which
+// only determines the row order of *_all_scores.txt)
+static int host_threads(size_t work_items) {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    const size_t by_work = work_items / 65536 + 1;  // below ~64k items a thread is not worth starting
+    return (int)std::max<size_t>(1, std::min<size_t>(std::min<unsigned>(hw, 32u), by_work));
+}
+
 bool write_all_scores(const std::vector<ScoreRow> &rows, const std::string &prefix) {
     FILE *f = fopen((prefix + "_all_scores.txt").c_str(), "wb");
     if (!f) return false;
-    std::string out = "#seg\tcontig\tscore\n";
-    out.reserve(rows.size() * 24 + 32);
-    char num[64];
-    for (auto &r : rows) {
-        out += std::to_string(r.seg);
-        out += '\t';
-        out += std::to_string(r.contig);
-        out += '\t';
-        format_float(num, sizeof num, r.score);
-        out += num;
-        out += '\n';
-        if (out.size() > (1u << 22)) {
-            fwrite(out.data(), 1, out.size(), f);
-            out.clear();
+    fputs("#seg\tcontig\tscore\n", f);
+    // format blocks of rows in parallel, write them in order
+    const size_t block = 1u << 18;
+    const int nt = host_threads(rows.size());
+    for (size_t base = 0; base < rows.size(); base += block * (size_t)nt) {
+        std::vector<std::string> out((size_t)nt);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) {
+            const size_t lo = std::min(rows.size(), base + block * (size_t)t), hi = std::min(rows.size(), lo + block);
+            if (lo >= hi) break;
+            auto work = [&rows, &out, t, lo, hi]() {
+                std::string &o = out[(size_t)t];
+                o.reserve((hi - lo) * 24);
+                char num[64];
+                for (size_t k = lo; k < hi; k++) {
+                    const ScoreRow &r = rows[k];
+                    int n = snprintf(num, sizeof num, "%d\t%d\t", r.seg, r.contig);
+                    o.append(num, (size_t)n);
+                    n = format_float(num, sizeof num, r.score);
+                    o.append(num, (size_t)n);
+                    o += '\n';
+                }
+            };
+            if (nt == 1) work();
+            else th.emplace_back(work);
         }
+        for (auto &t : th) t.join();
+        for (auto &o : out) fwrite(o.data(), 1, o.size(), f);
     }
-    fwrite(out.data(), 1, out.size(), f);
     fclose(f);
     return true;
 }
@@ -261,62 +283,91 @@ bool write_score_thresholds(const std::vector<std::pair<int, float>> &thr, const
 
 std::vector<std::pair<int, float>> compute_score_thresholds(const std::vector<ScoreRow> &rows, const MapSet &segs,
                                                             const MapSet &contigs, double pvalue, int n_detect_scores) {
+    std::vector<std::vector<std::pair<int, float>>> out;
+    compute_score_thresholds_multi(rows, segs, contigs, std::vector<double>{pvalue}, n_detect_scores, out);
+    return out[0];
+}
+
+void compute_score_thresholds_multi(const std::vector<ScoreRow> &rows, const MapSet &segs, const MapSet &contigs,
+                                    const std::vector<double> &pvalues, int n_detect_scores,
+                                    std::vector<std::vector<std::pair<int, float>>> &out) {
     const int ns = segs.n_maps();
     std::vector<std::vector<float>> seg_scores((size_t)ns);
     {
+        // rows arrive in long runs of the same segment id: remember the last lookup
+        std::vector<int32_t> seg_of(rows.size());
         std::vector<size_t> cnt((size_t)ns, 0);
-        for (auto &r : rows) {
-            const int k = segs.index_of(r.seg);
-            if (k >= 0) cnt[(size_t)k]++;
+        int last_id = 0, last_k = -2;
+        for (size_t r = 0; r < rows.size(); r++) {
+            if (last_k == -2 || rows[r].seg != last_id) {
+                last_id = rows[r].seg;
+                last_k = segs.index_of(last_id);
+            }
+            seg_of[r] = last_k;
+            if (last_k >= 0) cnt[(size_t)last_k]++;
         }
         for (int k = 0; k < ns; k++) seg_scores[(size_t)k].reserve(cnt[(size_t)k]);
-        for (auto &r : rows) {
-            const int k = segs.index_of(r.seg);
-            if (k >= 0) seg_scores[(size_t)k].push_back(r.score);
-        }
+        for (size_t r = 0; r < rows.size(); r++)
+            if (seg_of[r] >= 0) seg_scores[(size_t)seg_of[r]].push_back(rows[r].score);
     }
     const int right_cutoff = 25;
     const int left_cut = (int)round(0.15 * fmin((double)contigs.n_maps(), (double)n_detect_scores));  // main.cpp:66
-    const double E_cutoff = -log(1 - pvalue);
     int m = 0;
     for (int c = 0; c < contigs.n_maps(); c++) m += contigs.labels(c);  // :69-72
-    std::vector<std::pair<int, float>> out;
-    out.reserve((size_t)ns);
-    for (int k = 0; k < ns; k++) {
+    out.assign(pvalues.size(), std::vector<std::pair<int, float>>((size_t)ns));
+    auto one_segment = [&](int k) {
         std::vector<float> &sc = seg_scores[(size_t)k];
-        std::sort(sc.begin(), sc.end());  // :59
-        const int n = segs.labels(k);     // :76
+        const int n = segs.labels(k);  // :76
         const int64_t sz = (int64_t)sc.size();
         const int64_t first = sz - (right_cutoff + left_cut);
         int64_t last = sz - 1 - right_cutoff;
         if (n < 12) last -= 25;  // :80-82
-        float thr;
-        if (first < 0 || last > sz || last < first) {
-            thr = -NAN;  // reference: iterators outside the vector (UB); observed output "-nan"
-        } else {
-            const int64_t cnt = last - first;
-            const double nn = (double)cnt;
-            double sx = 0.0, sy = 0.0;
-            for (int64_t t = 0; t < cnt; t++) sx += sc[(size_t)(first + t)];
-            for (int64_t t = 0; t < cnt; t++) sy += (int)log((double)(cnt - t));  // int-truncated ln(rank), :85-90
-            const double xbar = sx / nn, ybar = sy / nn;  // linreg, SegAligner.cpp:304-319
-            double cov = 0.0, var = 0.0;
-            for (int64_t t = 0; t < cnt; t++) {
-                const double xv = sc[(size_t)(first + t)];
-                const double yv = (int)log((double)(cnt - t));
-                cov += (xv - xbar) * (yv - ybar);
-                var += (xv - xbar) * (xv - xbar);
-            }
-            const double slope = cov / var;
-            const double intercept = ybar - slope * xbar;
-            const int mn = (int)((unsigned)m * (unsigned)n);  // int product of the reference (:97), wraps
-            const double K = exp(intercept - log((double)mn));
-            const double S_cutoff = -log(E_cutoff / (K * m * n)) / (-slope);  // :100
-            thr = (float)S_cutoff;
+        const bool bad = first < 0 || last > sz || last < first;
+        if (!bad) {
+            // the reference sorts the whole vector (:59) but only reads [first, last): order that tail only
+            std::nth_element(sc.begin(), sc.begin() + first, sc.end());
+            std::sort(sc.begin() + first, sc.end());
         }
-        out.emplace_back(segs.ids[(size_t)k], thr);
+        for (size_t pv = 0; pv < pvalues.size(); pv++) {
+            const double E_cutoff = -log(1 - pvalues[pv]);
+            float thr;
+            if (bad) {
+                thr = -NAN;  // reference: iterators outside the vector (UB); observed output "-nan"
+            } else {
+                const int64_t cnt = last - first;
+                const double nn = (double)cnt;
+                double sx = 0.0, sy = 0.0;
+                for (int64_t t = 0; t < cnt; t++) sx += sc[(size_t)(first + t)];
+                for (int64_t t = 0; t < cnt; t++) sy += (int)log((double)(cnt - t));  // int-truncated ln(rank), :85-90
+                const double xbar = sx / nn, ybar = sy / nn;  // linreg, SegAligner.cpp:304-319
+                double cov = 0.0, var = 0.0;
+                for (int64_t t = 0; t < cnt; t++) {
+                    const double xv = sc[(size_t)(first + t)];
+                    const double yv = (int)log((double)(cnt - t));
+                    cov += (xv - xbar) * (yv - ybar);
+                    var += (xv - xbar) * (xv - xbar);
+                }
+                const double slope = cov / var;
+                const double intercept = ybar - slope * xbar;
+                const int mn = (int)((unsigned)m * (unsigned)n);  // int product of the reference (:97), wraps
+                const double K = exp(intercept - log((double)mn));
+                const double S_cutoff = -log(E_cutoff / (K * m * n)) / (-slope);  // :100
+                thr = (float)S_cutoff;
+            }
+            out[pv][(size_t)k] = {segs.ids[(size_t)k], thr};
+        }
+    };
+    const int nt = host_threads(rows.size());
+    if (nt == 1) {
+        for (int k = 0; k < ns; k++) one_segment(k);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([&, t]() {
+                for (int k = t; k < ns; k += nt) one_segment(k);
+            });
+        for (auto &t : th) t.join();
     }
-    return out;
 }
 
 void partial_score_threshold(float full_threshold, const std::vector<AlnEntry> &aln, const float *contig, int contig_size,

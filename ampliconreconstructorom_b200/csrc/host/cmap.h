@@ -65,6 +65,11 @@ bool write_score_thresholds(const std::vector<std::pair<int, float>> &thr, const
 std::vector<std::pair<int, float>> compute_score_thresholds(const std::vector<ScoreRow> &rows, const MapSet &segs,
                                                             const MapSet &contigs, double pvalue, int n_detect_scores);
 
+// the same for several p-values at once (the grouping and ordering of the scores is shared): out[p][seg index]
+void compute_score_thresholds_multi(const std::vector<ScoreRow> &rows, const MapSet &segs, const MapSet &contigs,
+                                    const std::vector<double> &pvalues, int n_detect_scores,
+                                    std::vector<std::vector<std::pair<int, float>>> &out);
+
 // compute_partial_score_threshold (SegAligner.cpp:23-36)
 void partial_score_threshold(float full_threshold, const std::vector<AlnEntry> &aln, const float *contig, int contig_size,
                              float &by_label, float &by_length);

@@ -21,6 +21,7 @@
 #include <set>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 #include <unistd.h>
 #include "cmap.h"
@@ -158,7 +159,9 @@ struct Engine {
         for (int g = 0; g < (int)ctx.size(); g++) th.emplace_back([&, g]() { f(g); });
         for (auto &t : th) t.join();
     }
-    // shard[g] = indices of the problems GPU g handles: sorted by cells descending, dealt round-robin
+    // shard[g] = indices of the problems GPU g handles.  Problems are dealt round-robin WITHIN size classes
+    // (1/4-octave of cells), largest classes first, so every GPU gets the same mix of sizes in O(n) (the library
+    // orders each shard largest-first itself); a full sort of 10^7 problems would cost more than their scoring.
     std::vector<std::vector<int64_t>> shard(const std::vector<sa_problem> &pr) const {
         const int G = (int)ctx.size();
         std::vector<std::vector<int64_t>> sh((size_t)G);
@@ -167,11 +170,23 @@ struct Engine {
             for (size_t k = 0; k < pr.size(); k++) sh[0][k] = (int64_t)k;
             return sh;
         }
-        std::vector<std::pair<int64_t, int64_t>> key(pr.size());
-        for (size_t k = 0; k < pr.size(); k++)
-            key[k] = {-(int64_t)contigs->labels(pr[k].contig) * segs->labels(pr[k].seg), (int64_t)k};
-        std::sort(key.begin(), key.end());
-        for (size_t r = 0; r < key.size(); r++) sh[r % (size_t)G].push_back(key[r].second);
+        const int NB = 4 * 64;
+        std::vector<uint8_t> cls(pr.size());
+        std::vector<int64_t> cnt((size_t)NB + 1, 0);
+        for (size_t k = 0; k < pr.size(); k++) {
+            const double cells = (double)contigs->labels(pr[k].contig) * (double)segs->labels(pr[k].seg);
+            int b = cells > 1.0 ? (int)(std::log2(cells) * 4.0) : 0;
+            b = NB - 1 - std::min(b, NB - 1);  // descending size
+            cls[k] = (uint8_t)b;
+            cnt[(size_t)b + 1]++;
+        }
+        for (int b = 0; b < NB; b++) cnt[(size_t)b + 1] += cnt[(size_t)b];
+        std::vector<int64_t> rank(pr.size());  // position in the size-class order
+        for (size_t k = 0; k < pr.size(); k++) rank[k] = cnt[cls[k]]++;
+        for (auto &v : sh) v.reserve(pr.size() / (size_t)G + 1);
+        std::vector<int64_t> by_rank(pr.size());
+        for (size_t k = 0; k < pr.size(); k++) by_rank[(size_t)rank[k]] = (int64_t)k;
+        for (size_t r = 0; r < by_rank.size(); r++) sh[r % (size_t)G].push_back(by_rank[r]);
         return sh;
     }
 
@@ -216,51 +231,89 @@ struct Engine {
         });
     }
 
-    // alignment: paths[k] = traceback of problem k, end->start.  used[k] = bitmap of contig labels to skip.
-    void align(const sa_mode &mode, const std::vector<sa_problem> &pr_in, const std::vector<const std::vector<uint32_t> *> &used,
-               std::vector<sa_result> &res, std::vector<std::vector<AlnEntry>> &paths) {
-        res.assign(pr_in.size(), sa_result{0, -1, -1, 0});
-        paths.assign(pr_in.size(), {});
-        if (pr_in.empty()) return;
-        auto sh = shard(pr_in);
-        parallel([&](int g) {
-            const auto &idx = sh[(size_t)g];
-            if (idx.empty()) return;
-            const size_t m = idx.size();
-            std::vector<sa_problem> p(m);
-            int64_t words = 1;
-            for (size_t k = 0; k < m; k++) {
-                p[k] = pr_in[(size_t)idx[k]];
-                words = std::max<int64_t>(words, (contigs->labels(p[k].contig) + 31) / 32);
+    // alignment: out.get(k) = result and traceback (end->start) of problem k, read in place from the pinned buffers
+    // of the context that computed it (valid until the next align call).  used[k] = bitmap of contig labels to skip (or
+    // nullptr); identical pointers share one device slot, so the first round of the tip phase (every pair of a
+    // contig starts from the same bitmap) uploads one bitmap per contig.
+    struct AlignOut {
+        struct View {
+            const sa_result *res;
+            const int32_t *pj, *pq;
+            const float *ps;
+        };
+        std::vector<sa_packed_paths> pk;        // per GPU
+        std::vector<std::vector<int64_t>> idx;  // per GPU: the problems it handled (empty for a single GPU)
+        std::vector<int32_t> gpu_of;            // per problem (multi-GPU only)
+        std::vector<int64_t> local_of;
+        View get(size_t k) const {
+            const size_t g = gpu_of.empty() ? 0 : (size_t)gpu_of[k];
+            const size_t l = gpu_of.empty() ? k : (size_t)local_of[k];
+            const sa_packed_paths &p = pk[g];
+            return View{p.results + l, p.path_j + p.start[l], p.path_q + p.start[l], p.path_s + p.start[l]};
+        }
+    };
+    void align_one_gpu(int g, const sa_mode &mode, std::vector<sa_problem> &p, const std::vector<const std::vector<uint32_t> *> &used,
+                       const int64_t *idx /* or nullptr = identity */, sa_packed_paths *out) {
+        const size_t m = p.size();
+        int64_t words = 1;
+        bool any_used = false;
+        for (size_t k = 0; k < m; k++) {
+            const auto *u = used[(size_t)(idx ? idx[k] : (int64_t)k)];
+            if (u) {
+                any_used = true;
+                words = std::max<int64_t>(words, (int64_t)u->size());
             }
-            std::vector<uint32_t> pool;
-            bool any_used = false;
-            for (size_t k = 0; k < m; k++) any_used |= (used[(size_t)idx[k]] != nullptr);
-            if (any_used) pool.assign((size_t)words * m, 0u);
-            std::vector<int64_t> poff(m + 1, 0);
+        }
+        std::vector<uint32_t> pool;
+        int64_t n_slots = 0;
+        if (any_used) {
+            std::unordered_map<const std::vector<uint32_t> *, int32_t> slot_of;
             for (size_t k = 0; k < m; k++) {
+                const auto *u = used[(size_t)(idx ? idx[k] : (int64_t)k)];
                 p[k].used_slot = -1;
-                if (any_used && used[(size_t)idx[k]]) {
-                    const auto &u = *used[(size_t)idx[k]];
-                    std::copy(u.begin(), u.begin() + (long)std::min<size_t>(u.size(), (size_t)words), pool.begin() + (size_t)words * k);
-                    p[k].used_slot = (int32_t)k;
+                if (!u) continue;
+                auto it = slot_of.find(u);
+                if (it == slot_of.end()) {
+                    it = slot_of.emplace(u, (int32_t)n_slots).first;
+                    pool.resize((size_t)(words * (n_slots + 1)), 0u);
+                    std::copy(u->begin(), u->end(), pool.begin() + (size_t)(words * n_slots));
+                    n_slots++;
                 }
-                poff[k + 1] = poff[k] + std::min(contigs->labels(p[k].contig), segs->labels(p[k].seg));
+                p[k].used_slot = it->second;
             }
-            const size_t tot = (size_t)std::max<int64_t>(poff[m], 1);
-            std::vector<int32_t> pj(tot), pq(tot);
-            std::vector<float> ps(tot);
-            std::vector<sa_result> r(m);
-            int rc = sa_align_batch(ctx[(size_t)g], &mode, p.data(), (int64_t)m, any_used ? pool.data() : nullptr, words,
-                                    any_used ? (int64_t)m : 0, poff.data(), r.data(), pj.data(), pq.data(), ps.data());
-            if (rc) die(ctx[(size_t)g], "sa_align_batch", rc);
-            for (size_t k = 0; k < m; k++) {
-                res[(size_t)idx[k]] = r[k];
-                auto &pa = paths[(size_t)idx[k]];
-                pa.resize((size_t)r[k].path_len);
-                for (int t = 0; t < r[k].path_len; t++)
-                    pa[(size_t)t] = AlnEntry{pj[(size_t)poff[k] + t], pq[(size_t)poff[k] + t], ps[(size_t)poff[k] + t]};
+        } else {
+            for (size_t k = 0; k < m; k++) p[k].used_slot = -1;
+        }
+        int rc = sa_align_batch_packed(ctx[(size_t)g], &mode, p.data(), (int64_t)m, any_used ? pool.data() : nullptr, words,
+                                       n_slots, out);
+        if (rc) die(ctx[(size_t)g], "sa_align_batch_packed", rc);
+    }
+    void align(const sa_mode &mode, std::vector<sa_problem> &pr, const std::vector<const std::vector<uint32_t> *> &used,
+               AlignOut &out) {
+        const size_t n = pr.size();
+        const size_t G = ctx.size();
+        out.pk.assign(G, sa_packed_paths{});
+        out.idx.clear();
+        out.gpu_of.clear();
+        out.local_of.clear();
+        if (n == 0) return;
+        if (G == 1) {
+            align_one_gpu(0, mode, pr, used, nullptr, &out.pk[0]);
+            return;
+        }
+        out.idx = shard(pr);
+        out.gpu_of.resize(n);
+        out.local_of.resize(n);
+        parallel([&](int g) {
+            const auto &idx = out.idx[(size_t)g];
+            if (idx.empty()) return;
+            std::vector<sa_problem> p(idx.size());
+            for (size_t k = 0; k < idx.size(); k++) {
+                p[k] = pr[(size_t)idx[k]];
+                out.gpu_of[(size_t)idx[k]] = g;
+                out.local_of[(size_t)idx[k]] = (int64_t)k;
             }
+            align_one_gpu(g, mode, p, used, idx.data(), &out.pk[(size_t)g]);
         });
     }
 };
@@ -277,6 +330,7 @@ inline bool bm_any(const Bitmap &b) {
 // One pass of run_SA_aln (main.cpp:213-358) over a set of (segment, contig) pairs, as batched rounds.
 // used_seed: per contig the labels already taken (tip phase), else nullptr.  Returns per contig the labels
 // of the alignments that were WRITTEN (discovered_contig_used_labels).
+double wall_now();
 std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapSet &segs, const MapSet &contigs,
                                        const std::vector<std::pair<int, int>> &pairs /* (seg idx, contig idx) */,
                                        const std::vector<std::pair<int, float>> &thresholds /* by seg idx */,
@@ -290,12 +344,16 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
     int max_alns = o.max_seg_contig_alns;
     if (tip_aln && o.inst_gen == 2) max_alns = 6;
 
+    // Per-pair state.  The skip bitmap starts as a shared pointer (nullptr = empty, or the contig's seed bitmap in
+    // the tip phase) and becomes a private copy only when the pair accepts an alignment: 10^7 pairs stay cheap.
     struct PairState {
         int s, c;
         float thr, curr_best, exp_thresh;
         int count;
-        Bitmap used;
+        const Bitmap *seed;
+        Bitmap own;
         bool live;
+        const Bitmap *used() const { return own.empty() ? seed : &own; }
     };
     std::vector<PairState> st(pairs.size());
     for (size_t k = 0; k < pairs.size(); k++) {
@@ -306,8 +364,7 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
         p.curr_best = p.thr;
         p.exp_thresh = p.thr;
         p.count = 0;
-        if (used_seed) p.used = (*used_seed)[(size_t)p.c];
-        else p.used.assign(bm_words(contigs.labels(p.c)), 0u);
+        p.seed = (used_seed && bm_any((*used_seed)[(size_t)p.c])) ? &(*used_seed)[(size_t)p.c] : nullptr;
         p.live = true;
     }
     sa_mode mode;
@@ -317,47 +374,80 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
     mode.lookback = o.lookback;
     mode.swap_b_x = o.swap_b_x ? 1 : 0;
 
+    Engine::AlignOut out;  // reused across rounds
+    std::vector<size_t> live;
+    std::vector<sa_problem> pr;
+    std::vector<const Bitmap *> used;
+    std::vector<AlnEntry> aln;  // scratch: one alignment, end->start
     for (;;) {
-        std::vector<size_t> live;
+        live.clear();
         for (size_t k = 0; k < st.size(); k++) {
             PairState &p = st[k];
-            if (p.live && p.curr_best >= p.exp_thresh && p.count < max_alns) live.push_back(k);  // main.cpp:268
+            if (!p.live) continue;
+            if (p.curr_best >= p.exp_thresh && p.count < max_alns) live.push_back(k);  // main.cpp:268
             else p.live = false;
         }
         if (live.empty()) break;
-        std::vector<sa_problem> pr(live.size());
-        std::vector<const Bitmap *> used(live.size());
+        pr.resize(live.size());
+        used.resize(live.size());
         for (size_t n = 0; n < live.size(); n++) {
             const PairState &p = st[live[n]];
             pr[n] = sa_problem{p.c, p.s, -1, 0};
-            used[n] = bm_any(p.used) ? &p.used : nullptr;
+            used[n] = p.used();
         }
-        std::vector<sa_result> res;
-        std::vector<std::vector<AlnEntry>> paths;
-        eng.align(mode, pr, used, res, paths);
+        const double t_a0 = wall_now();
+        eng.align(mode, pr, used, out);
+        const double t_a1 = wall_now();
+        struct RoundLog {
+            double t0, t1;
+            size_t n;
+            ~RoundLog() {
+                if (getenv("SA_VERBOSE"))
+                    fprintf(stderr, "  alignment round: %zu pairs, align call %.3f s, host post-processing %.3f s\n", n, t1 - t0,
+                            wall_now() - t1);
+            }
+        } round_log{t_a0, t_a1, live.size()};
         for (size_t n = 0; n < live.size(); n++) {
             PairState &p = st[live[n]];
-            const std::vector<AlnEntry> &aln = paths[n];
-            if (aln.empty()) {  // no backtrack start (cannot happen with >= 1 label each); treat as exhausted
+            const Engine::AlignOut::View v = out.get(n);
+            const int len = v.res->path_len;
+            if (len <= 0) {  // no backtrack start (cannot happen with >= 1 label each); treat as exhausted
                 p.live = false;
                 continue;
             }
-            float by_lab, by_len;
-            partial_score_threshold(p.thr, aln, contigs.map(p.c), contigs.size(p.c), by_lab, by_len);
-            p.exp_thresh = fmaxf(by_lab, by_len);  // main.cpp:290
-            p.curr_best = res[n].score;
+            const int32_t *pj = v.pj;
+            {   // compute_partial_score_threshold (SegAligner.cpp:23-36) on the flat path: first = last entry
+                const float *contig = contigs.map(p.c);
+                const int contig_size = contigs.size(p.c);
+                const int first_lab = pj[len - 1], last_lab = pj[0];
+                const int aln_span_labs = last_lab - first_lab + 1;
+                const float tot_labs = (float)(contig_size - 1);
+                const float by_lab = p.thr * (aln_span_labs / tot_labs);
+                const float aln_span_bases = contig[last_lab] - contig[first_lab];
+                const float by_len = p.thr * (aln_span_bases / contig[contig_size - 1]);
+                p.exp_thresh = fmaxf(by_lab, by_len);  // main.cpp:290
+            }
+            p.curr_best = v.res->score;
             if (!(p.curr_best > p.exp_thresh)) {
                 // equality would spin forever in the reference (same DP, same result); we stop instead
                 if (p.curr_best == p.exp_thresh) p.live = false;
                 continue;
             }
             p.count += 1;
-            for (auto &e : aln) bm_set(p.used, e.j);  // main.cpp:298-300
-            if (tip_aln) {                             // must touch a contig end (main.cpp:303-308)
-                const size_t last_lab_gap = (size_t)(contigs.size(p.c) - 2) - (size_t)aln[0].j;
-                if (last_lab_gap > 3 && aln.back().j > 2) continue;
+            if (p.own.empty()) {
+                if (p.seed) p.own = *p.seed;
+                else p.own.assign(bm_words(contigs.labels(p.c)), 0u);
             }
-            if ((int)aln.size() < min_tip_aln_labels || (!tip_aln && (int)aln.size() < min_aln_labels)) continue;
+            for (int t = 0; t < len; t++) bm_set(p.own, pj[t]);  // main.cpp:298-300
+            if (tip_aln) {                                         // must touch a contig end (main.cpp:303-308)
+                const size_t last_lab_gap = (size_t)(contigs.size(p.c) - 2) - (size_t)pj[0];
+                if (last_lab_gap > 3 && pj[len - 1] > 2) continue;
+            }
+            if (len < min_tip_aln_labels || (!tip_aln && len < min_aln_labels)) continue;
+            const int32_t *pq = v.pq;
+            const float *ps = v.ps;
+            aln.resize((size_t)len);
+            for (int t = 0; t < len; t++) aln[(size_t)t] = AlnEntry{pj[t], pq[t], ps[t]};
             const float mean = aln[0].s / (float)(aln.size() - 1);
             const float median = aln_median(aln);
             if (aln.size() < 5) {
@@ -492,15 +582,18 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
         }
         sa_mode mode{SA_INIT_FITTING, SA_START_END, 1, o.lookback, o.swap_b_x ? 1 : 0};
         std::vector<const Bitmap *> used(pr.size(), nullptr);
-        std::vector<sa_result> res;
-        std::vector<std::vector<AlnEntry>> paths;
-        eng.align(mode, pr, used, res, paths);
+        Engine::AlignOut out;
+        eng.align(mode, pr, used, out);
+        std::vector<AlnEntry> aln;
         for (size_t k = 0; k < pr.size(); k++) {
             const int x = segs.ids[(size_t)pr[k].seg];
             const int contig_id = contigs.ids[(size_t)pr[k].contig];
             const std::string outname = o.sample_prefix + "_" + std::to_string(contig_id) + "_" +
                                         std::to_string(x < 0 ? -x : x) + "_fitting_aln.txt";
-            print_alignment(outname, paths[k], contig_id, x, segs.size(pr[k].seg), res[k].score);
+            const Engine::AlignOut::View v = out.get(k);
+            aln.resize((size_t)std::max(v.res->path_len, 0));
+            for (size_t t = 0; t < aln.size(); t++) aln[t] = AlnEntry{v.pj[t], v.pq[t], v.ps[t]};
+            print_alignment(outname, aln, contig_id, x, segs.size(pr[k].seg), v.res->score);
         }
         printf("elapsed seconds for run %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
         fflush(stdout);
@@ -557,8 +650,10 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
     pt.lap("write all_scores");
 
     // ---------------- phase 2: thresholds (main.cpp:555-557) ---------------------------------------------------
-    auto score_thresholds = compute_score_thresholds(rows, segs, contigs, (double)o.p_val, o.n_detect_scores);
-    auto tip_thresholds = compute_score_thresholds(rows, segs, contigs, (double)o.p_val_tip, o.n_detect_scores);
+    std::vector<std::vector<std::pair<int, float>>> thr2;
+    compute_score_thresholds_multi(rows, segs, contigs, {(double)o.p_val, (double)o.p_val_tip}, o.n_detect_scores, thr2);
+    const auto &score_thresholds = thr2[0];
+    const auto &tip_thresholds = thr2[1];
     printf("Writing scoring distribution.\n");
     write_score_thresholds(score_thresholds, o.sample_prefix + o.detection_label);
     printf("Completed generating scores.\n");

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -37,6 +38,33 @@ struct DevBuf {
     }
     void release() {
         if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+// grow-only pinned host buffer (results / packed paths travel D2H at full PCIe speed, no page faults per call)
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes, bool keep = false) {
+        if (bytes <= cap) return cudaSuccess;
+        void *np = nullptr;
+        const size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaMallocHost(&np, want);
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) memcpy(np, p, cap);
+        if (p) cudaFreeHost(p);
+        p = np;
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
     }
@@ -81,6 +109,7 @@ struct sa_ctx {
     MapSetHost sides[2];
     DevBuf d_problems, d_order, d_results, d_halo, d_counter, d_cell_off, d_S, d_code, d_used, d_path_off, d_path_j,
         d_path_q, d_path_s, d_tmp0, d_tmp1, d_tmp2, d_halo2, d_row_off, d_rowmax_s, d_rowmax_q, d_prev32, d_halo3, d_mail;
+    HostBuf h_res, h_start, h_pj, h_pq, h_ps;  // packed alignment output of the last sa_align_batch* call
     sa_timing timing = {0, 0, 0, 0};
     size_t store_budget_cells = 0;  // max cells of stored matrices per chunk
 };
@@ -357,6 +386,8 @@ void sa_ctx_destroy(sa_ctx *ctx) {
                       &ctx->d_path_s,   &ctx->d_tmp0,   &ctx->d_tmp1,     &ctx->d_tmp2,     &ctx->d_halo2,  &ctx->d_row_off, &ctx->d_rowmax_s,
                       &ctx->d_rowmax_q, &ctx->d_prev32, &ctx->d_halo3, &ctx->d_mail};
     for (auto b : bufs) b->release();
+    HostBuf *hbufs[] = {&ctx->h_res, &ctx->h_start, &ctx->h_pj, &ctx->h_pq, &ctx->h_ps};
+    for (auto b : hbufs) b->release();
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     for (auto &e : ctx->ev_user)
@@ -503,12 +534,10 @@ int sa_score_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
     return rc;
 }
 
-int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const uint32_t *used_bits,
-                   int64_t used_words_per_slot, int64_t n_used_slots, const int64_t *path_off, sa_result *results,
-                   int32_t *path_j, int32_t *path_q, float *path_s) {
-    if (!ctx) return SA_EINVAL;
-    if (n <= 0) return SA_OK;
-    if (!problems || !results || !path_off || !path_j || !path_q || !path_s) return fail(ctx, SA_EINVAL, "NULL buffer");
+// Fill + traceback of n problems; the paths are measured on the device first (count-only traceback + prefix sum) and
+// then written PACKED, so only sum(path_len) entries cross PCIe, into pinned host buffers owned by the context.
+static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const uint32_t *used_bits,
+                        int64_t used_words_per_slot, int64_t n_used_slots, int64_t *total_out) {
     CU(cudaSetDevice(ctx->device));
     int rc = check_problems(ctx, problems, n, used_bits ? n_used_slots : 0);
     if (rc) return rc;
@@ -525,6 +554,9 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
         P.used_words_per_slot = used_words_per_slot;
     }
     ctx->timing = {0, 0, 0, 0};
+    CU(ctx->h_res.reserve(sizeof(sa_result) * (size_t)n));
+    CU(ctx->h_start.reserve(sizeof(int64_t) * (size_t)(n + 1)));
+    int64_t total = 0;  // packed path entries so far
     // chunk so that the stored matrices fit the budget
     int64_t k0 = 0;
     std::vector<int64_t> cell_off;
@@ -539,12 +571,10 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
             k1++;
         }
         const int64_t m = k1 - k0;
+        const auto t_host0 = std::chrono::steady_clock::now();
         Plan plan;
         build_plan(ctx, problems + k0, m, n_fill_ctas(ctx) * FILL_WARPS, plan);
         const std::vector<int32_t> &order = plan.order;
-        std::vector<int64_t> poff((size_t)m + 1);
-        for (int64_t k = 0; k <= m; k++) poff[(size_t)k] = path_off[k0 + k] - path_off[k0];
-        const int64_t n_path = poff[(size_t)m];
         CU(ctx->d_problems.reserve(sizeof(sa_problem) * (size_t)m));
         CU(ctx->d_order.reserve(sizeof(int32_t) * (size_t)m));
         CU(ctx->d_results.reserve(sizeof(sa_result) * (size_t)m));
@@ -554,13 +584,9 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
         if (unbanded) CU(ctx->d_prev32.reserve(sizeof(int32_t) * (size_t)cells));
         else CU(ctx->d_code.reserve((size_t)cells));
         CU(ctx->d_path_off.reserve(sizeof(int64_t) * (size_t)(m + 1)));
-        CU(ctx->d_path_j.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(n_path, 1)));
-        CU(ctx->d_path_q.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(n_path, 1)));
-        CU(ctx->d_path_s.reserve(sizeof(float) * (size_t)std::max<int64_t>(n_path, 1)));
         CU(cudaMemcpyAsync(ctx->d_problems.p, problems + k0, sizeof(sa_problem) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_order.p, order.data(), sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_cell_off.p, cell_off.data(), sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_path_off.p, poff.data(), sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyHostToDevice, ctx->stream));
         P.problems = ctx->d_problems.as<sa_problem>();
         P.order = ctx->d_order.as<int32_t>();
         P.cell_off = ctx->d_cell_off.as<int64_t>();
@@ -591,31 +617,106 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
         T.n_problems = m;
         T.S = P.S;
         T.code = unbanded ? nullptr : P.code;
-        T.path_off = ctx->d_path_off.as<int64_t>();
         T.results = P.results;
+        // pass 1: measure the paths, prefix-sum the lengths into packed start offsets
+        int64_t *d_start = ctx->d_path_off.as<int64_t>();
+        T.count_only = 1;
+        T.len_out = d_start;
+        CU(cudaMemsetAsync(d_start + m, 0, sizeof(int64_t), ctx->stream));
+        launch_traceback(T, ctx->stream);
+        CU(cudaGetLastError());
+        size_t tmp_need = 0;
+        exclusive_scan_i64(d_start, m + 1, nullptr, 0, &tmp_need, ctx->stream);
+        CU(ctx->d_tmp2.reserve(tmp_need + 16));
+        if (exclusive_scan_i64(d_start, m + 1, ctx->d_tmp2.p, ctx->d_tmp2.cap, nullptr, ctx->stream))
+            return fail(ctx, SA_ECUDA, "prefix sum of the path lengths failed");
+        int64_t n_path = 0;
+        CU(cudaMemcpyAsync(&n_path, d_start + m, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        // pass 2: write the paths packed
+        CU(ctx->d_path_j.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(n_path, 1)));
+        CU(ctx->d_path_q.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(n_path, 1)));
+        CU(ctx->d_path_s.reserve(sizeof(float) * (size_t)std::max<int64_t>(n_path, 1)));
+        CU(ctx->h_pj.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(total + n_path, 1), true));
+        CU(ctx->h_pq.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(total + n_path, 1), true));
+        CU(ctx->h_ps.reserve(sizeof(float) * (size_t)std::max<int64_t>(total + n_path, 1), true));
+        T.count_only = 0;
+        T.len_out = nullptr;
+        T.path_off = d_start;
         T.path_j = ctx->d_path_j.as<int32_t>();
         T.path_q = ctx->d_path_q.as<int32_t>();
         T.path_s = ctx->d_path_s.as<float>();
         launch_traceback(T, ctx->stream);
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-        CU(cudaMemcpyAsync(results + k0, ctx->d_results.p, sizeof(sa_result) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->h_res.as<sa_result>() + k0, ctx->d_results.p, sizeof(sa_result) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->h_start.as<int64_t>() + k0, d_start, sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyDeviceToHost, ctx->stream));
         if (n_path > 0) {
-            CU(cudaMemcpyAsync(path_j + path_off[k0], ctx->d_path_j.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaMemcpyAsync(path_q + path_off[k0], ctx->d_path_q.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaMemcpyAsync(path_s + path_off[k0], ctx->d_path_s.p, sizeof(float) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->h_pj.as<int32_t>() + total, ctx->d_path_j.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->h_pq.as<int32_t>() + total, ctx->d_path_q.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->h_ps.as<float>() + total, ctx->d_path_s.p, sizeof(float) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
         }
         CU(cudaStreamSynchronize(ctx->stream));
+        if (total > 0) {  // chunk-local start offsets -> global
+            int64_t *hs = ctx->h_start.as<int64_t>() + k0;
+            for (int64_t k = 0; k <= m; k++) hs[k] += total;
+        }
+        total += n_path;
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
         ctx->timing.fill_ms += a;
         ctx->timing.post_ms += b;
-        ctx->timing.n_launches += 1;
+        ctx->timing.n_launches += 2;
         if (getenv("SA_VERBOSE"))
-            fprintf(stderr, "  sa_align_batch chunk: %lld problems, %.3e cells, fill %.2f ms (large %lld), traceback %.2f ms\n",
-                    (long long)m, (double)cells, a, (long long)(plan.n_large * 1000 + plan.n_huge), b);
+            fprintf(stderr, "  sa_align_batch chunk: %lld problems, %.3e cells, fill %.2f ms (large %lld), traceback %.2f ms, %lld path entries, chunk wall %.1f ms\n",
+                    (long long)m, (double)cells, a, (long long)(plan.n_large * 1000 + plan.n_huge), b, (long long)n_path,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
         k0 = k1;
+    }
+    *total_out = total;
+    return SA_OK;
+}
+
+int sa_align_batch_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const uint32_t *used_bits,
+                          int64_t used_words_per_slot, int64_t n_used_slots, sa_packed_paths *out) {
+    if (!ctx || !out) return SA_EINVAL;
+    memset(out, 0, sizeof(*out));
+    if (n <= 0) return SA_OK;
+    if (!problems || !mode) return fail(ctx, SA_EINVAL, "NULL buffer");
+    int64_t total = 0;
+    int rc = align_packed(ctx, mode, problems, n, used_bits, used_words_per_slot, n_used_slots, &total);
+    if (rc) return rc;
+    out->n = n;
+    out->total = total;
+    out->results = ctx->h_res.as<sa_result>();
+    out->start = ctx->h_start.as<int64_t>();
+    out->path_j = ctx->h_pj.as<int32_t>();
+    out->path_q = ctx->h_pq.as<int32_t>();
+    out->path_s = ctx->h_ps.as<float>();
+    return SA_OK;
+}
+
+int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const uint32_t *used_bits,
+                   int64_t used_words_per_slot, int64_t n_used_slots, const int64_t *path_off, sa_result *results,
+                   int32_t *path_j, int32_t *path_q, float *path_s) {
+    if (!ctx) return SA_EINVAL;
+    if (n <= 0) return SA_OK;
+    if (!problems || !results || !path_off || !path_j || !path_q || !path_s || !mode) return fail(ctx, SA_EINVAL, "NULL buffer");
+    sa_packed_paths pk;
+    int rc = sa_align_batch_packed(ctx, mode, problems, n, used_bits, used_words_per_slot, n_used_slots, &pk);
+    if (rc) return rc;
+    memcpy(results, pk.results, sizeof(sa_result) * (size_t)n);
+    for (int64_t k = 0; k < n; k++) {  // scatter the packed paths to the caller's capacity offsets
+        const int64_t cap = path_off[k + 1] - path_off[k];
+        int64_t len = pk.results[k].path_len;
+        if (len > cap) {  // the caller offered less room than the path needs: truncate like the device loop used to
+            len = cap;
+            results[k].path_len = (int32_t)cap;
+        }
+        memcpy(path_j + path_off[k], pk.path_j + pk.start[k], sizeof(int32_t) * (size_t)len);
+        memcpy(path_q + path_off[k], pk.path_q + pk.start[k], sizeof(int32_t) * (size_t)len);
+        memcpy(path_s + path_off[k], pk.path_s + pk.start[k], sizeof(float) * (size_t)len);
     }
     return SA_OK;
 }

@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <math_constants.h>
 #include <cooperative_groups.h>
+#include <cub/device/device_scan.cuh>
 namespace cg = cooperative_groups;
 #include "sa_kernels.cuh"
 #include "powf12.cuh"
@@ -1033,15 +1034,24 @@ __global__ void trace_kernel(const TraceParams P) {
     const uint8_t *C = P.code ? P.code + P.cell_off[k] : nullptr;
     sa_result res = P.results[k];
     int j = res.j, q = res.q;
-    const long long base = P.path_off[k];
-    const long long cap = P.path_off[k + 1] - base;
+    // count_only: no output arrays yet, the capacity is the longest possible path min(nb, nx)
+    const long long base = P.count_only ? 0 : P.path_off[k];
+    long long cap;
+    if (P.count_only) {
+        const int nb_ = (int)(P.contigs.pos_off[pr.contig + 1] - P.contigs.pos_off[pr.contig]) - 1;
+        cap = nb_ < nx ? nb_ : nx;
+    } else {
+        cap = P.path_off[k + 1] - base;
+    }
     int n = 0;
     if (j >= 0) res.score = S[(long long)j * nx + q];
     while (j >= 0 && n < cap) {
         const long long c = (long long)j * nx + q;
-        P.path_j[base + n] = j;
-        P.path_q[base + n] = q;
-        P.path_s[base + n] = S[c];
+        if (!P.count_only) {
+            P.path_j[base + n] = j;
+            P.path_q[base + n] = q;
+            P.path_s[base + n] = S[c];
+        }
         n++;
         if (P.prev32) {
             const int pv = P.prev32[P.cell_off[k] + c];
@@ -1058,6 +1068,7 @@ __global__ void trace_kernel(const TraceParams P) {
     }
     res.path_len = n;
     P.results[k] = res;
+    if (P.len_out) P.len_out[k] = n;
 }
 
 // multi_backtrack_scores (SegAligner.cpp:208-233) + zero_out_aln (:198-205) for one problem per CTA.
@@ -1311,6 +1322,14 @@ void fill_powf_constants(double *pk) {
     const double v[12] = {SA_POWF_A0, SA_POWF_A1, SA_POWF_A2, SA_POWF_A3, SA_POWF_A4, SA_Y12,
                           SA_EXP2F_C0, SA_EXP2F_C1, SA_EXP2F_C2, SA_EXP2F_SHIFT, -SA_EXP2F_SHIFT, 0.0};
     for (int i = 0; i < 12; i++) pk[i] = v[i];
+}
+
+int exclusive_scan_i64(int64_t *d_vals, int64_t n_plus_1, void *d_tmp, size_t tmp_bytes, size_t *tmp_needed, cudaStream_t st) {
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, d_vals, d_vals, (int)n_plus_1, st);
+    if (tmp_needed) *tmp_needed = need;
+    if (!d_tmp || tmp_bytes < need) return 1;
+    return cub::DeviceScan::ExclusiveSum(d_tmp, need, d_vals, d_vals, (int)n_plus_1, st) == cudaSuccess ? 0 : 2;
 }
 
 void launch_traceback(const TraceParams &p, cudaStream_t st) {

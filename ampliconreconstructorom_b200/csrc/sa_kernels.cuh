@@ -63,6 +63,8 @@ struct TraceParams {
     sa_result *results;
     int32_t *path_j, *path_q;
     float *path_s;
+    int32_t count_only;  // 1: only measure the paths (results[k].path_len, len_out[k]); nothing is written
+    int64_t *len_out;    // optional: path length per problem as int64 (input of the prefix sum)
 };
 
 struct DetectParams {
@@ -85,6 +87,8 @@ void launch_fill(const FillParams &p, bool store, bool swap, int shape, int n_ct
 int max_clusters();
 void launch_fill_unbanded(const FillParams &p, int32_t *prev32, bool swap, int n_ctas, cudaStream_t st);
 void launch_traceback(const TraceParams &p, cudaStream_t st);
+// in-place exclusive prefix sum of n+1 int64 values (the last input value is ignored: out[n] = total)
+int exclusive_scan_i64(int64_t *d_vals, int64_t n_plus_1, void *d_tmp, size_t tmp_bytes, size_t *tmp_needed, cudaStream_t st);
 void launch_powf12(const float *x, long long n, float *out, int fast, cudaStream_t st);
 void launch_powf12_range(uint32_t lo, uint32_t hi, float *out_fast, float *out_generic, cudaStream_t st);
 void launch_prune_bound(uint32_t lo, uint32_t hi, unsigned long long *n_viol, float *min_ratio, cudaStream_t st);

@@ -100,6 +100,20 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
                    const uint32_t *used_bits, int64_t used_words_per_slot, int64_t n_used_slots,
                    const int64_t *path_off, sa_result *results, int32_t *path_j, int32_t *path_q, float *path_s);
 
+/* The same, with the tracebacks PACKED: path k is path_j/q/s[start[k] .. start[k] + results[k].path_len), end -> start.
+ * All pointers refer to pinned host memory owned by the context and stay valid until the next sa_align_batch* call on it;
+ * only sum(path_len) entries cross PCIe (the capacity-offset form above moves min(nb,nx) per problem).  Used by the
+ * executable's run_SA_aln rounds (main.cpp:213-358), where tens of millions of pairs are aligned per round. */
+typedef struct sa_packed_paths {
+    int64_t n, total;          /* problems, packed path entries */
+    const sa_result *results;  /* n */
+    const int64_t *start;      /* n + 1 */
+    const int32_t *path_j, *path_q;
+    const float *path_s;
+} sa_packed_paths;
+int sa_align_batch_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const uint32_t *used_bits,
+                          int64_t used_words_per_slot, int64_t n_used_slots, sa_packed_paths *out);
+
 /* Detection-mode scoring (run_SA_score with detection=true, main.cpp:155-159): semiglobal init, dp_align,
  * then multi_backtrack_scores (SegAligner.cpp:208-233) harvesting n_want[k] path scores per problem in the
  * reference's order (including its skip of the single best cell).  scores_off[n+1] gives each problem's slot

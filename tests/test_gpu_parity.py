@@ -48,8 +48,8 @@ def upload(ctx, maps, probs, side):
 
 @pytest.fixture(params=["bulk", "coop", "cluster"], autouse=True)
 def kernel_class(request, monkeypatch):
-    """Run every parity case three times: through the one-warp-per-problem kernel, the cooperative 16-warp CTA
-    wavefront and the 8-CTA thread-block-cluster wavefront (forced by absurdly low size-class thresholds)."""
+    """Run every parity case three times: through the one-warp-per-problem kernel, the cooperative 8-warp CTA
+    wavefront and the 8-CTA x 16-warp thread-block-cluster wavefront (forced by absurdly low size-class thresholds)."""
     monkeypatch.setenv("SA_COOP_ALPHA", "0" if request.param == "bulk" else "1e-9")
     monkeypatch.setenv("SA_NO_CLUSTER", "0" if request.param == "cluster" else "1")
     monkeypatch.setenv("SA_HUGE_MIN_CELLS", "0")
@@ -178,6 +178,36 @@ def test_prune_bound_holds_for_every_float(ctx):
         worst = min(worst, r)
     assert total == 0, f"{total} floats where the pruning bound exceeds the exact powf"
     assert worst > 1.0  # strict slack everywhere (the margin PRUNE_C is 2^-14 in the log2 domain)
+
+
+def test_pruning_statistics_and_tie_rescans(ctx, oracle):
+    """The fill kernel replays powf bit-exactly once per cell and rescans a cell exactly when the winner is not
+    strictly ahead of every other candidate's upper bound.  Integer-valued maps make exact ties common: the rescan path
+    must run (n_rescans > 0), about one replay per cell must be executed, and results must still equal the oracle."""
+    rng = np.random.default_rng(77)
+    contigs, segs = {}, {}
+    for k in range(12):
+        b, x = helpers.related_maps(rng, int(rng.integers(60, 200)), int(rng.integers(20, 60)), integer=True)
+        contigs[k + 1], segs[k + 1] = b, x
+    cp, sp = oracle.probs(contigs, 2), oracle.probs(segs, 2)
+    cids = upload(ctx, contigs, cp, capi.SA_SIDE_CONTIG)
+    sids = upload(ctx, segs, sp, capi.SA_SIDE_SEG)
+    cc, ss = np.meshgrid(np.arange(len(cids)), np.arange(len(sids)), indexing="ij")
+    pr = ctx.problems(cc.ravel(), ss.ravel())
+    mode = ctx.mode(capi.SA_INIT_SEMIGLOBAL, capi.SA_START_SEMIGLOBAL, 0, 6, 0)
+    res = ctx.score_batch(mode, pr)
+    replays, rescans = ctx.prune_stats()
+    cells = sum((len(contigs[cids[int(c)]]) - 1) * (len(segs[sids[int(s)]]) - 1) for c, s in zip(pr["contig"], pr["seg"]))
+    # lanes of a partly filled 32-row strip replay too (clamped to the last row), hence the padded upper limit
+    padded = sum(-(-(len(contigs[cids[int(c)]]) - 1) // 32) * 32 * (len(segs[sids[int(s)]]) - 1)
+                 for c, s in zip(pr["contig"], pr["seg"]))
+    assert 0.5 * cells < replays <= padded, (replays, cells, padded)
+    assert 0 < rescans < 0.2 * cells, (rescans, cells)
+    for k in range(0, pr.size, 7):
+        c, s = int(pr["contig"][k]), int(pr["seg"][k])
+        So, _ = oracle.fill(contigs[cids[c]], segs[sids[s]], cp[cids[c]], sp[sids[s]], 0, 0, 6, None, 0)
+        st = oracle.start(So, 0)
+        assert (int(res["j"][k]), int(res["q"][k])) == st and bits(res["score"][k]) == bits(So[st])
 
 
 def test_unbanded_lookback_nl(ctx, oracle):
