@@ -232,9 +232,7 @@ struct Engine {
     }
 
     // alignment: out.get(k) = result and traceback (end->start) of problem k, read in place from the pinned buffers
-    // of the context that computed it (valid until the next align call).  used[k] = bitmap of contig labels to skip (or
-    // nullptr); identical pointers share one device slot, so the first round of the tip phase (every pair of a
-    // contig starts from the same bitmap) uploads one bitmap per contig.
+    // of the context that computed it (valid until the next align call).
     struct AlignOut {
         struct View {
             const sa_result *res;
@@ -252,44 +250,9 @@ struct Engine {
             return View{p.results + l, p.path_j + p.start[l], p.path_q + p.start[l], p.path_s + p.start[l]};
         }
     };
-    void align_one_gpu(int g, const sa_mode &mode, std::vector<sa_problem> &p, const std::vector<const std::vector<uint32_t> *> &used,
-                       const int64_t *idx /* or nullptr = identity */, sa_packed_paths *out) {
-        const size_t m = p.size();
-        int64_t words = 1;
-        bool any_used = false;
-        for (size_t k = 0; k < m; k++) {
-            const auto *u = used[(size_t)(idx ? idx[k] : (int64_t)k)];
-            if (u) {
-                any_used = true;
-                words = std::max<int64_t>(words, (int64_t)u->size());
-            }
-        }
-        std::vector<uint32_t> pool;
-        int64_t n_slots = 0;
-        if (any_used) {
-            std::unordered_map<const std::vector<uint32_t> *, int32_t> slot_of;
-            for (size_t k = 0; k < m; k++) {
-                const auto *u = used[(size_t)(idx ? idx[k] : (int64_t)k)];
-                p[k].used_slot = -1;
-                if (!u) continue;
-                auto it = slot_of.find(u);
-                if (it == slot_of.end()) {
-                    it = slot_of.emplace(u, (int32_t)n_slots).first;
-                    pool.resize((size_t)(words * (n_slots + 1)), 0u);
-                    std::copy(u->begin(), u->end(), pool.begin() + (size_t)(words * n_slots));
-                    n_slots++;
-                }
-                p[k].used_slot = it->second;
-            }
-        } else {
-            for (size_t k = 0; k < m; k++) p[k].used_slot = -1;
-        }
-        int rc = sa_align_batch_packed(ctx[(size_t)g], &mode, p.data(), (int64_t)m, any_used ? pool.data() : nullptr, words,
-                                       n_slots, out);
-        if (rc) die(ctx[(size_t)g], "sa_align_batch_packed", rc);
-    }
-    void align(const sa_mode &mode, std::vector<sa_problem> &pr, const std::vector<const std::vector<uint32_t> *> &used,
-               AlignOut &out) {
+    // pr[k].used_slot = WORD offset of the problem's skip bitmap inside `arena` (or -1): the C ABI is used with one
+    // word per slot, so bitmaps of different lengths sit packed and the arena is uploaded as it is.
+    void align(const sa_mode &mode, std::vector<sa_problem> &pr, const std::vector<uint32_t> &arena, AlignOut &out) {
         const size_t n = pr.size();
         const size_t G = ctx.size();
         out.pk.assign(G, sa_packed_paths{});
@@ -297,8 +260,11 @@ struct Engine {
         out.gpu_of.clear();
         out.local_of.clear();
         if (n == 0) return;
+        const uint32_t *bits = arena.empty() ? nullptr : arena.data();
+        const int64_t n_words = (int64_t)arena.size();
         if (G == 1) {
-            align_one_gpu(0, mode, pr, used, nullptr, &out.pk[0]);
+            int rc = sa_align_batch_packed(ctx[0], &mode, pr.data(), (int64_t)n, bits, 1, n_words, &out.pk[0]);
+            if (rc) die(ctx[0], "sa_align_batch_packed", rc);
             return;
         }
         out.idx = shard(pr);
@@ -313,7 +279,8 @@ struct Engine {
                 out.gpu_of[(size_t)idx[k]] = g;
                 out.local_of[(size_t)idx[k]] = (int64_t)k;
             }
-            align_one_gpu(g, mode, p, used, idx.data(), &out.pk[(size_t)g]);
+            int rc = sa_align_batch_packed(ctx[(size_t)g], &mode, p.data(), (int64_t)p.size(), bits, 1, n_words, &out.pk[(size_t)g]);
+            if (rc) die(ctx[(size_t)g], "sa_align_batch_packed", rc);
         });
     }
 };
@@ -344,16 +311,23 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
     int max_alns = o.max_seg_contig_alns;
     if (tip_aln && o.inst_gen == 2) max_alns = 6;
 
-    // Per-pair state.  The skip bitmap starts as a shared pointer (nullptr = empty, or the contig's seed bitmap in
-    // the tip phase) and becomes a private copy only when the pair accepts an alignment: 10^7 pairs stay cheap.
+    // Skip bitmaps live packed in one arena of 32-bit words that is uploaded as it is: first the seed bitmap of every
+    // contig that has one (tip phase; shared by all pairs of the contig until they accept an alignment), then one
+    // private copy per pair, appended when the pair accepts its first alignment.  10^7 pairs stay cheap.
+    std::vector<uint32_t> arena;
+    std::vector<int64_t> seed_off((size_t)contigs.n_maps(), -1);
+    if (used_seed)
+        for (int c = 0; c < contigs.n_maps(); c++)
+            if (bm_any((*used_seed)[(size_t)c])) {
+                seed_off[(size_t)c] = (int64_t)arena.size();
+                arena.insert(arena.end(), (*used_seed)[(size_t)c].begin(), (*used_seed)[(size_t)c].end());
+            }
     struct PairState {
         int s, c;
         float thr, curr_best, exp_thresh;
         int count;
-        const Bitmap *seed;
-        Bitmap own;
-        bool live;
-        const Bitmap *used() const { return own.empty() ? seed : &own; }
+        int64_t used_off;  // word offset of the skip bitmap in the arena, -1 = none
+        bool own, live;
     };
     std::vector<PairState> st(pairs.size());
     for (size_t k = 0; k < pairs.size(); k++) {
@@ -364,7 +338,8 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
         p.curr_best = p.thr;
         p.exp_thresh = p.thr;
         p.count = 0;
-        p.seed = (used_seed && bm_any((*used_seed)[(size_t)p.c])) ? &(*used_seed)[(size_t)p.c] : nullptr;
+        p.used_off = seed_off[(size_t)p.c];
+        p.own = false;
         p.live = true;
     }
     sa_mode mode;
@@ -377,7 +352,6 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
     Engine::AlignOut out;  // reused across rounds
     std::vector<size_t> live;
     std::vector<sa_problem> pr;
-    std::vector<const Bitmap *> used;
     std::vector<AlnEntry> aln;  // scratch: one alignment, end->start
     for (;;) {
         live.clear();
@@ -388,15 +362,17 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
             else p.live = false;
         }
         if (live.empty()) break;
+        if (arena.size() >= (1ull << 31)) {
+            fprintf(stderr, "SegAligner(b200): skip bitmaps of this run exceed 2^31 words\n");
+            throw JobExit{2, true};
+        }
         pr.resize(live.size());
-        used.resize(live.size());
         for (size_t n = 0; n < live.size(); n++) {
             const PairState &p = st[live[n]];
-            pr[n] = sa_problem{p.c, p.s, -1, 0};
-            used[n] = p.used();
+            pr[n] = sa_problem{p.c, p.s, (int32_t)p.used_off, 0};
         }
         const double t_a0 = wall_now();
-        eng.align(mode, pr, used, out);
+        eng.align(mode, pr, arena, out);
         const double t_a1 = wall_now();
         struct RoundLog {
             double t0, t1;
@@ -434,11 +410,15 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
                 continue;
             }
             p.count += 1;
-            if (p.own.empty()) {
-                if (p.seed) p.own = *p.seed;
-                else p.own.assign(bm_words(contigs.labels(p.c)), 0u);
+            if (!p.own) {  // first accepted alignment of the pair: private copy of the seed (or an empty bitmap)
+                const size_t w = bm_words(contigs.labels(p.c));
+                const int64_t at = (int64_t)arena.size();
+                arena.resize(arena.size() + w, 0u);  // (may reallocate: copy by fresh iterators afterwards)
+                if (p.used_off >= 0) std::copy(arena.begin() + p.used_off, arena.begin() + p.used_off + (long)w, arena.begin() + at);
+                p.used_off = at;
+                p.own = true;
             }
-            for (int t = 0; t < len; t++) bm_set(p.own, pj[t]);  // main.cpp:298-300
+            for (int t = 0; t < len; t++) arena[(size_t)p.used_off + ((size_t)pj[t] >> 5)] |= 1u << (pj[t] & 31);  // main.cpp:298-300
             if (tip_aln) {                                         // must touch a contig end (main.cpp:303-308)
                 const size_t last_lab_gap = (size_t)(contigs.size(p.c) - 2) - (size_t)pj[0];
                 if (last_lab_gap > 3 && pj[len - 1] > 2) continue;
@@ -581,9 +561,8 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
             }
         }
         sa_mode mode{SA_INIT_FITTING, SA_START_END, 1, o.lookback, o.swap_b_x ? 1 : 0};
-        std::vector<const Bitmap *> used(pr.size(), nullptr);
         Engine::AlignOut out;
-        eng.align(mode, pr, used, out);
+        eng.align(mode, pr, std::vector<uint32_t>(), out);
         std::vector<AlnEntry> aln;
         for (size_t k = 0; k < pr.size(); k++) {
             const int x = segs.ids[(size_t)pr[k].seg];

@@ -54,7 +54,7 @@ struct HostBuf {
     cudaError_t reserve(size_t bytes, bool keep = false) {
         if (bytes <= cap) return cudaSuccess;
         void *np = nullptr;
-        const size_t want = bytes + bytes / 4 + 4096;
+        const size_t want = keep ? std::max(bytes + bytes / 4 + 4096, 2 * cap) : bytes + bytes / 4 + 4096;  // appended-to buffers double
         cudaError_t e = cudaMallocHost(&np, want);
         if (e != cudaSuccess) return e;
         if (keep && p && cap) memcpy(np, p, cap);
