@@ -35,6 +35,17 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+# The driver reads ONE JSON line from stdout.  Libraries loaded later (NCCL prints its version banner to stdout on some
+# boxes) must not be able to add lines: keep a private duplicate of the original stdout for the JSON line and point
+# file descriptor 1 at stderr for everything else.
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_json(obj) -> None:
+    os.write(_JSON_FD, (json.dumps(obj) + "\n").encode())
+
+
 METRIC = "dp_gcups"
 UNIT = "GCUPS"
 REF_BIN = ROOT / "oracle" / "_ref" / "SegAligner_ref"
@@ -141,7 +152,7 @@ def run_reference_arm(args, rank, world):
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
             "data": "synthetic"}
     if not REF_BIN.exists():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/SegAligner_ref was not built"}))
+        emit_json({"impl": "reference", "unavailable": "oracle/_ref/SegAligner_ref was not built"})
         return
     n_threads = os.cpu_count() or 1
     w = build_workload(0, args.scale)
@@ -164,7 +175,7 @@ def run_reference_arm(args, rank, world):
                  "cpu_baseline": {"value": gcups, "unit": UNIT, "cores": n_threads, "kind": "reference", "sample": sample},
                  "e2e": {"value": gcups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "gpu_launches": 0})
-    print(json.dumps(base))
+    emit_json(base)
 
 
 def main():
@@ -342,7 +353,7 @@ def main():
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                                    "sample": "skipped (--no-cpu-baseline)" if args.no_cpu_baseline
                                    else "oracle/_ref/SegAligner_ref not present"}
-        print(json.dumps(out))
+        emit_json(out)
     plan.destroy()
     ctx.close()
     if world > 1:
