@@ -38,17 +38,14 @@ __constant__ double c_pk[12] = {SA_POWF_A0, SA_POWF_A1, SA_POWF_A2, SA_POWF_A3, 
 
 // ---- shared-memory tables of the powf replay -----------------------------------------------------------------
 // Variant knob (compile time, both measured on B200 -- see DESIGN.md 4.1):
-//   SA_TAB2D 3 (default): LANE-REPLICATED, bank-conflict-free tables.  The log table {invc_i, logc_i + (double)k}
+//   SA_TAB2D 3 (dense kernel, SA_PRUNE=0): LANE-REPLICATED, bank-conflict-free tables.  The log table {invc_i, logc_i + (double)k}
 //                 holds 32 binades x 16 entries, each entry stored 8 times (16 B x 8 = one 128-byte bank row), and lane
 //                 l reads copy l & 7: the 8 lanes of an LDS.128 quarter-warp phase always hit 8 different 16-byte bank
 //                 groups => exactly 4 shared-memory wavefronts per LDS.128 whatever the indices.  The exp2 table holds
 //                 its 32 u64 entries 16 times (8 B x 16 = one bank row), lane l reads copy l & 15 => exactly 2
 //                 wavefronts per LDS.64.  64 KB + 4 KB per CTA, so the kernels run one CTA per SM.
-//   SA_TAB2D 1:   one copy: 52 x 16 entries of 16 B + 32 x u64 (13.4 wavefronts per evaluation instead of 7: random
+//   SA_TAB2D 1 (pruning kernel, the default): one copy: 52 x 16 entries of 16 B + 32 x u64 (13.4 wavefronts per evaluation instead of 7: random
 //                 indices conflict 2-3 ways per phase); 16 KB, 3 CTAs per SM.
-#ifndef SA_BREADTH
-#define SA_BREADTH 1  // breadth-first scheduling of the 6 powf chains of a look-back row
-#endif
 
 // fast-path domain of the delta term: discrep in [0.7 * 2^-KLO, 0.7 * 2^(KBIN-KLO)); anything else (exact 0, tiny,
 // huge, inf, NaN) is flagged and the cell is redone through the generic path
@@ -74,19 +71,11 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-#ifndef SA_VOL_LDS
-#define SA_VOL_LDS 0  // 1: table loads are volatile asm => they keep their source order (pins the software pipeline)
-#endif
-#if SA_VOL_LDS
-#define SA_ASM_TAB asm volatile
-#else
-#define SA_ASM_TAB asm
-#endif
 __device__ __forceinline__ void lds_f64x2(uint32_t addr, double &a, double &b) {
-    SA_ASM_TAB("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
 }
 __device__ __forceinline__ void lds_u32x2(uint32_t addr, uint32_t &lo, uint32_t &hi) {
-    SA_ASM_TAB("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
 }
 
 #if SA_TAB2D == 3
@@ -243,16 +232,8 @@ __device__ __forceinline__ void row_prefetch(PowRow &n, float db_row, const floa
         const uint32_t ix = __float_as_uint(fabsf(__fsub_rn(db_row, dx[c])));
         u[c] = ix - IX_LO;
         const uint32_t iz = ix - (u[c] & 0xff800000u) + ((uint32_t)KLO << 23);
-#ifdef SA_KO_T2D
-        n.invc[c] = __hiloint2double(0x3ff00000, (int)u[c]), n.y0[c] = __hiloint2double(0x3ff00000, (int)ix);
-#else
         lds_f64x2(ta.t2d | ((u[c] >> T2D_SHIFT) & T2D_MASK), n.invc[c], n.y0[c]);
-#endif
-#ifdef SA_KO_F2F_IN
-        n.z[c] = __hiloint2double((int)iz, (int)ix);
-#else
         n.z[c] = f2d_normal(iz);
-#endif
     }
     umax = __vimax3_u32(umax, __vimax3_u32(u[0], u[1], u[2]), __vimax3_u32(u[3], u[4], u[5]));
 }
@@ -299,11 +280,7 @@ __device__ __forceinline__ void row_powf(const PowRow &w, const TabAddr ta, cons
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         ki[c] = (uint32_t)__double2loint(kd[c]);
-#ifdef SA_KO_EXP
-        tlo[c] = ki[c], thi[c] = 0x3ff00000u;
-#else
         lds_u32x2(ta.exp | ((ki[c] << EXP_SHIFT) & EXP_MASK), tlo[c], thi[c]);
-#endif
     }
 #pragma unroll
     for (int c = 0; c < NC; c++) kd[c] = __dadd_rn(kd[c], PK(10));
@@ -320,11 +297,7 @@ __device__ __forceinline__ void row_powf(const PowRow &w, const TabAddr ta, cons
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         const double sc = __hiloint2double((int)(thi[c] + (ki[c] << 15)), (int)tlo[c]);
-#ifdef SA_KO_F2F_OUT
-        out[c] = __int_as_float(__double2hiint(__dmul_rn(yy[c], sc)));
-#else
         out[c] = d2f_normal(__dmul_rn(yy[c], sc));
-#endif
     }
 }
 
@@ -660,11 +633,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                         float delta[LB], sc[LB], ns[LB];
 #pragma unroll
                         for (int c = 0; c < LB; c++) {
-#ifdef SA_KO_PRED
-                            sc[c] = __uint_as_float(PC(c) - djh * 4);
-#else
                             sc[c] = lds_f32(PC(c) - djh * 4);
-#endif
                         }
                         if (h == 0) {
                             row_powf(rowA, a_tab, P.pk, delta);
@@ -742,10 +711,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
             if (active) {
                 if (row_ok) {
                     if (STORE) {
-#ifndef SA_KO_STORE
                         Sout[(long long)j * nx + q] = val;
                         Cout[(long long)j * nx + q] = (uint8_t)code;
-#endif
                         if (P.rowmax_s) {
                             if (val > 0.0f && val >= rm_s) {
                                 rm_s = val;

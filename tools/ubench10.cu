@@ -1,6 +1,6 @@
 // The fill kernel's inner evaluation pipeline (row_prefetch + row_powf + fp32 tail, rolled row-pair loop) in isolation:
 // no DP ring, no problem queue, no step bookkeeping.  Measures sub-partition cycles per predecessor evaluation for
-// 1..4 warps per sub-partition.  Build variants with -DSA_KO_* / -DSA_INT_CVT=.. to see what each piece costs.
+// 1..4 warps per sub-partition.  The -DSA_KO_* knock-out switches it was run with lived in sa_kernels.cu up to commit 322adb9 (removed afterwards).
 // Developer tool (round 1 cost model); includes the product kernels' source to reuse their device functions.
 #include "../ampliconreconstructorom_b200/csrc/sa_kernels.cu"  // NOTE: written against the dense pipeline (SA_PRUNE=0 era); row_prefetch/row_powf still exist
 using namespace sa;

@@ -1,5 +1,5 @@
 // fp64 pipe capacity for the EXACT powf replay dataflow (17 fp64 per chain, 6 chains breadth-first), operands in
-// registers, no table loads, no conversions (build with -DSA_KO_EXP -DSA_KO_F2F_OUT).  Developer tool.
+// registers, no table loads, no conversions (was built with -DSA_KO_EXP -DSA_KO_F2F_OUT, switches that lived in sa_kernels.cu up to commit 322adb9).  Developer tool.
 #include "../ampliconreconstructorom_b200/csrc/sa_kernels.cu"
 using namespace sa;
 __global__ void __launch_bounds__(512) k11(float *out, int iters, FillParams P) {
