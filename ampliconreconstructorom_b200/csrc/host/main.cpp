@@ -352,7 +352,6 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
     Engine::AlignOut out;  // reused across rounds
     std::vector<size_t> live;
     std::vector<sa_problem> pr;
-    std::vector<AlnEntry> aln;  // scratch: one alignment, end->start
     for (;;) {
         live.clear();
         for (size_t k = 0; k < st.size(); k++) {
@@ -383,67 +382,103 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
                             wall_now() - t1);
             }
         } round_log{t_a0, t_a1, live.size()};
-        for (size_t n = 0; n < live.size(); n++) {
-            PairState &p = st[live[n]];
-            const Engine::AlignOut::View v = out.get(n);
-            const int len = v.res->path_len;
-            if (len <= 0) {  // no backtrack start (cannot happen with >= 1 label each); treat as exhausted
-                p.live = false;
-                continue;
+        // Post-processing of the round, in parallel over contiguous ranges of pairs.  Pairs are independent except for
+        // (a) new private bitmaps, which each worker appends to its own arena piece (spliced into the arena afterwards)
+        // and (b) the labels of WRITTEN alignments, which each worker records and the main thread ORs in afterwards.
+        const size_t n_live = live.size();
+        const int n_workers = (int)std::max<size_t>(1, std::min<size_t>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u),
+                                                                        n_live / 50000 + 1));
+        struct Worker {
+            std::vector<uint32_t> piece;           // private bitmaps created this round
+            std::vector<size_t> fresh;             // pairs (index into st) whose used_off is relative to `piece`
+            std::vector<std::pair<int, int>> disc;  // (contig, label) of written alignments
+            std::vector<AlnEntry> aln;
+        };
+        std::vector<Worker> workers((size_t)n_workers);
+        auto work = [&](int wi) {
+            Worker &W = workers[(size_t)wi];
+            const size_t lo = n_live * (size_t)wi / (size_t)n_workers, hi = n_live * ((size_t)wi + 1) / (size_t)n_workers;
+            std::vector<AlnEntry> &aln = W.aln;
+            for (size_t n = lo; n < hi; n++) {
+                PairState &p = st[live[n]];
+                const Engine::AlignOut::View v = out.get(n);
+                const int len = v.res->path_len;
+                if (len <= 0) {  // no backtrack start (cannot happen with >= 1 label each); treat as exhausted
+                    p.live = false;
+                    continue;
+                }
+                const int32_t *pj = v.pj;
+                {   // compute_partial_score_threshold (SegAligner.cpp:23-36) on the flat path: first = last entry
+                    const float *contig = contigs.map(p.c);
+                    const int contig_size = contigs.size(p.c);
+                    const int first_lab = pj[len - 1], last_lab = pj[0];
+                    const int aln_span_labs = last_lab - first_lab + 1;
+                    const float tot_labs = (float)(contig_size - 1);
+                    const float by_lab = p.thr * (aln_span_labs / tot_labs);
+                    const float aln_span_bases = contig[last_lab] - contig[first_lab];
+                    const float by_len = p.thr * (aln_span_bases / contig[contig_size - 1]);
+                    p.exp_thresh = fmaxf(by_lab, by_len);  // main.cpp:290
+                }
+                p.curr_best = v.res->score;
+                if (!(p.curr_best > p.exp_thresh)) {
+                    // equality would spin forever in the reference (same DP, same result); we stop instead
+                    if (p.curr_best == p.exp_thresh) p.live = false;
+                    continue;
+                }
+                p.count += 1;
+                uint32_t *bits;
+                if (!p.own) {  // first accepted alignment of the pair: private copy of the seed (or an empty bitmap)
+                    const size_t w = bm_words(contigs.labels(p.c));
+                    const size_t at = W.piece.size();
+                    W.piece.resize(at + w, 0u);
+                    if (p.used_off >= 0) std::copy(arena.begin() + p.used_off, arena.begin() + p.used_off + (long)w, W.piece.begin() + (long)at);
+                    p.used_off = (int64_t)at;  // relative to the piece until the splice below
+                    p.own = true;
+                    W.fresh.push_back(live[n]);
+                    bits = W.piece.data() + at;
+                } else {
+                    bits = arena.data() + p.used_off;  // the arena itself is not resized while the workers run
+                }
+                for (int t = 0; t < len; t++) bits[(size_t)pj[t] >> 5] |= 1u << (pj[t] & 31);  // main.cpp:298-300
+                if (tip_aln) {                                                              // must touch a contig end (:303-308)
+                    const size_t last_lab_gap = (size_t)(contigs.size(p.c) - 2) - (size_t)pj[0];
+                    if (last_lab_gap > 3 && pj[len - 1] > 2) continue;
+                }
+                if (len < min_tip_aln_labels || (!tip_aln && len < min_aln_labels)) continue;
+                const int32_t *pq = v.pq;
+                const float *ps = v.ps;
+                aln.resize((size_t)len);
+                for (int t = 0; t < len; t++) aln[(size_t)t] = AlnEntry{pj[t], pq[t], ps[t]};
+                const float mean = aln[0].s / (float)(aln.size() - 1);
+                const float median = aln_median(aln);
+                if (aln.size() < 5) {
+                    const float min_score = aln_min(aln);
+                    if (mean < 9400 || median < 9400 || min_score < 9200) continue;
+                } else if (mean < mean_thresh || median < med_thresh) {
+                    continue;
+                }
+                const int x = segs.ids[(size_t)p.s];
+                const int contig_id = contigs.ids[(size_t)p.c];
+                std::string seg_id = std::to_string(x < 0 ? -x : x);
+                if (x < 0) seg_id += "_r";
+                const std::string outname = o.sample_prefix + "_" + std::to_string(contig_id) + "_" + seg_id + "_" +
+                                            std::to_string(p.count) + (tip_aln ? "_tip" : "") + "_aln.txt";
+                print_alignment(outname, aln, contig_id, x, segs.size(p.s), p.curr_best);
+                for (auto &e : aln) W.disc.emplace_back(p.c, e.j);  // SAHelper.cpp:115
             }
-            const int32_t *pj = v.pj;
-            {   // compute_partial_score_threshold (SegAligner.cpp:23-36) on the flat path: first = last entry
-                const float *contig = contigs.map(p.c);
-                const int contig_size = contigs.size(p.c);
-                const int first_lab = pj[len - 1], last_lab = pj[0];
-                const int aln_span_labs = last_lab - first_lab + 1;
-                const float tot_labs = (float)(contig_size - 1);
-                const float by_lab = p.thr * (aln_span_labs / tot_labs);
-                const float aln_span_bases = contig[last_lab] - contig[first_lab];
-                const float by_len = p.thr * (aln_span_bases / contig[contig_size - 1]);
-                p.exp_thresh = fmaxf(by_lab, by_len);  // main.cpp:290
-            }
-            p.curr_best = v.res->score;
-            if (!(p.curr_best > p.exp_thresh)) {
-                // equality would spin forever in the reference (same DP, same result); we stop instead
-                if (p.curr_best == p.exp_thresh) p.live = false;
-                continue;
-            }
-            p.count += 1;
-            if (!p.own) {  // first accepted alignment of the pair: private copy of the seed (or an empty bitmap)
-                const size_t w = bm_words(contigs.labels(p.c));
-                const int64_t at = (int64_t)arena.size();
-                arena.resize(arena.size() + w, 0u);  // (may reallocate: copy by fresh iterators afterwards)
-                if (p.used_off >= 0) std::copy(arena.begin() + p.used_off, arena.begin() + p.used_off + (long)w, arena.begin() + at);
-                p.used_off = at;
-                p.own = true;
-            }
-            for (int t = 0; t < len; t++) arena[(size_t)p.used_off + ((size_t)pj[t] >> 5)] |= 1u << (pj[t] & 31);  // main.cpp:298-300
-            if (tip_aln) {                                         // must touch a contig end (main.cpp:303-308)
-                const size_t last_lab_gap = (size_t)(contigs.size(p.c) - 2) - (size_t)pj[0];
-                if (last_lab_gap > 3 && pj[len - 1] > 2) continue;
-            }
-            if (len < min_tip_aln_labels || (!tip_aln && len < min_aln_labels)) continue;
-            const int32_t *pq = v.pq;
-            const float *ps = v.ps;
-            aln.resize((size_t)len);
-            for (int t = 0; t < len; t++) aln[(size_t)t] = AlnEntry{pj[t], pq[t], ps[t]};
-            const float mean = aln[0].s / (float)(aln.size() - 1);
-            const float median = aln_median(aln);
-            if (aln.size() < 5) {
-                const float min_score = aln_min(aln);
-                if (mean < 9400 || median < 9400 || min_score < 9200) continue;
-            } else if (mean < mean_thresh || median < med_thresh) {
-                continue;
-            }
-            const int x = segs.ids[(size_t)p.s];
-            const int contig_id = contigs.ids[(size_t)p.c];
-            std::string seg_id = std::to_string(x < 0 ? -x : x);
-            if (x < 0) seg_id += "_r";
-            const std::string outname = o.sample_prefix + "_" + std::to_string(contig_id) + "_" + seg_id + "_" +
-                                        std::to_string(p.count) + (tip_aln ? "_tip" : "") + "_aln.txt";
-            print_alignment(outname, aln, contig_id, x, segs.size(p.s), p.curr_best);
-            for (auto &e : aln) bm_set(discovered[(size_t)p.c], e.j);  // SAHelper.cpp:115
+        };
+        if (n_workers == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int wi = 0; wi < n_workers; wi++) th.emplace_back(work, wi);
+            for (auto &t : th) t.join();
+        }
+        for (Worker &W : workers) {  // splice the new private bitmaps into the arena, record the written labels
+            const int64_t base = (int64_t)arena.size();
+            arena.insert(arena.end(), W.piece.begin(), W.piece.end());
+            for (size_t k : W.fresh) st[k].used_off += base;
+            for (auto &e : W.disc) bm_set(discovered[(size_t)e.first], e.second);
         }
     }
     return discovered;

@@ -557,6 +557,12 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
     CU(ctx->h_res.reserve(sizeof(sa_result) * (size_t)n));
     CU(ctx->h_start.reserve(sizeof(int64_t) * (size_t)(n + 1)));
     int64_t total = 0;  // packed path entries so far
+    if (n > 100000) {  // big batches: one pinned allocation up front (paths average a handful of entries) instead of regrowing
+        const size_t guess = (size_t)n * 8;
+        CU(ctx->h_pj.reserve(sizeof(int32_t) * guess));
+        CU(ctx->h_pq.reserve(sizeof(int32_t) * guess));
+        CU(ctx->h_ps.reserve(sizeof(float) * guess));
+    }
     // chunk so that the stored matrices fit the budget
     int64_t k0 = 0;
     std::vector<int64_t> cell_off;
