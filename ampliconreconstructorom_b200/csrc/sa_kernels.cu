@@ -385,6 +385,7 @@ __device__ __noinline__ CellRes cell_slow(bool swap, uint32_t a_row, float dx0, 
 }
 
 constexpr int RING_W = 40;  // 6 halo rows + 32 lanes + 2 pad
+constexpr int STAGE_BYTES_PER_WARP = 32 * 9 * 4 + 32 * 12;  // STORE staging tiles: scores [32][9] floats + codes [32][12] bytes
 #define NEG_INF (-CUDART_INF_F)
 
 // NW = warps that cooperate on one problem.
@@ -410,6 +411,9 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
     float(*s_ring)[2 * LB][RING_W] = reinterpret_cast<float(*)[2 * LB][RING_W]>(s_dyn + TAB_SMEM_BYTES);
     float(*s_rowop)[2 * LB][32] =
         reinterpret_cast<float(*)[2 * LB][32]>(s_dyn + TAB_SMEM_BYTES + WPC * 2 * LB * RING_W * sizeof(float));
+    // STORE only: per-warp staging tiles of 32 rows x 8 columns (scores: row pitch 9 floats, codes: row pitch 12 bytes) so
+    // that the stored matrices are written 8 consecutive columns (32 B / 8 B) per row instead of one element per row
+    unsigned char *s_stage = s_dyn + TAB_SMEM_BYTES + WPC * (2 * LB * RING_W + 2 * LB * 32) * sizeof(float);
     __shared__ float s_xbuf[WPC][2][8];
     __shared__ unsigned long long s_next;
     __shared__ float s_red_s[WPC];
@@ -425,6 +429,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
     const uint32_t a_my = (uint32_t)__cvta_generic_to_shared(&s_ring[warp][0][6 + lane]);
     const uint32_t a_halo = (uint32_t)__cvta_generic_to_shared(&s_ring[warp][0][lane]);  // lanes 0..5 only
     const uint32_t a_row = (uint32_t)__cvta_generic_to_shared(&s_rowop[warp][0][lane]);
+    const uint32_t a_tile_s = (uint32_t)__cvta_generic_to_shared(s_stage + warp * STAGE_BYTES_PER_WARP);  // [32][9] floats
+    const uint32_t a_tile_c = a_tile_s + 32 * 9 * 4;                                                    // [32][12] bytes
 
     const long long gunit = (NW == 1) ? ((long long)blockIdx.x * FILL_WARPS + warp) : (long long)(blockIdx.x / CS);
     float *halo = P.halo + gunit * P.halo_stride;
@@ -709,10 +715,32 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
             else if (CS == 1) __syncthreads();
             else cg::this_cluster().sync();
             if (active) {
+                if (STORE) {
+                    // stage this column; every 8 columns (and at the end of the row) flush the 32 x 8 tile: 8 lanes
+                    // write the 8 consecutive columns of one row, 4 rows per instruction
+                    const int cq = q & 7;
+                    sts_f32(a_tile_s + lane * 36 + cq * 4, val);
+                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_tile_c + lane * 12 + cq), "r"(code) : "memory");
+                    if (cq == 7 || q == nx - 1) {
+                        __syncwarp();
+                        const int q0 = q - cq, col = lane & 7;
+#pragma unroll
+                        for (int it = 0; it < 8; it++) {
+                            const int r = it * 4 + (lane >> 3);
+                            const int jr = (strip << 5) + r;
+                            if (col <= cq && jr < nb) {
+                                const long long o = (long long)jr * nx + q0 + col;
+                                uint32_t cv;
+                                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cv) : "r"(a_tile_c + r * 12 + col));
+                                Sout[o] = lds_f32(a_tile_s + r * 36 + col * 4);
+                                Cout[o] = (uint8_t)cv;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
                 if (row_ok) {
                     if (STORE) {
-                        Sout[(long long)j * nx + q] = val;
-                        Cout[(long long)j * nx + q] = (uint8_t)code;
                         if (P.rowmax_s) {
                             if (val > 0.0f && val >= rm_s) {
                                 rm_s = val;
@@ -1242,12 +1270,13 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *sink, int iters)
 }
 
 // dynamic shared memory of a fill CTA with `wpc` warps: table region + mirrored ring + row operands
-static size_t fill_dyn_smem(int wpc) {
-    return TAB_SMEM_BYTES + (size_t)wpc * (2 * LB * RING_W + 2 * LB * 32) * sizeof(float);
+static size_t fill_dyn_smem(int wpc, bool store = true) {
+    return TAB_SMEM_BYTES + (size_t)wpc * (2 * LB * RING_W + 2 * LB * 32) * sizeof(float) +
+           (store ? (size_t)wpc * STAGE_BYTES_PER_WARP : 0);
 }
 template <int NW, int MINB, int CS>
 static void launch_fill_t(const FillParams &p, bool store, bool swap, int n_ctas, cudaStream_t st) {
-    const size_t sm = fill_dyn_smem(NW == 1 ? FILL_WARPS : NW);
+    const size_t sm = fill_dyn_smem(NW == 1 ? FILL_WARPS : NW, store);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_ctas);
     cfg.blockDim = dim3((NW == 1 ? FILL_WARPS : NW) * 32);
