@@ -537,7 +537,7 @@ int sa_score_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
 // Fill + traceback of n problems; the paths are measured on the device first (count-only traceback + prefix sum) and
 // then written PACKED, so only sum(path_len) entries cross PCIe, into pinned host buffers owned by the context.
 static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const uint32_t *used_bits,
-                        int64_t used_words_per_slot, int64_t n_used_slots, int64_t *total_out) {
+                        int64_t used_words_per_slot, int64_t n_used_slots, int64_t *total_out, bool want_S = false) {
     CU(cudaSetDevice(ctx->device));
     int rc = check_problems(ctx, problems, n, used_bits ? n_used_slots : 0);
     if (rc) return rc;
@@ -556,6 +556,11 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
     ctx->timing = {0, 0, 0, 0};
     CU(ctx->h_res.reserve(sizeof(sa_result) * (size_t)n));
     CU(ctx->h_start.reserve(sizeof(int64_t) * (size_t)(n + 1)));
+    // The banded fill stores only the 1-byte predecessor codes (the traceback recomputes the scores along the path
+    // exactly); -nl keeps its stored scores and 4-byte predecessors.  `want_S` (the sa_fill_one test hook) keeps S too.
+    const bool unbanded_mode = mode->lookback != LB;
+    const bool keep_S = unbanded_mode || want_S;
+    const size_t budget_cells = keep_S ? ctx->store_budget_cells : ctx->store_budget_cells * 5;
     int64_t total = 0;  // packed path entries so far
     if (n > 100000) {  // big batches: one pinned allocation up front (paths average a handful of entries) instead of regrowing
         const size_t guess = (size_t)n * 8;
@@ -571,7 +576,7 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
         int64_t cells = 0, k1 = k0;
         while (k1 < n) {
             const int64_t c = (int64_t)ctx->sides[0].labels(problems[k1].contig) * ctx->sides[1].labels(problems[k1].seg);
-            if (k1 > k0 && (size_t)(cells + c) > ctx->store_budget_cells) break;
+            if (k1 > k0 && (size_t)(cells + c) > budget_cells) break;
             cell_off.push_back(cells);
             cells += c;
             k1++;
@@ -586,7 +591,7 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
         CU(ctx->d_results.reserve(sizeof(sa_result) * (size_t)m));
         CU(ctx->d_cell_off.reserve(sizeof(int64_t) * (size_t)m));
         const bool unbanded = mode->lookback != LB;
-        CU(ctx->d_S.reserve(sizeof(float) * (size_t)cells));
+        if (keep_S) CU(ctx->d_S.reserve(sizeof(float) * (size_t)cells));
         if (unbanded) CU(ctx->d_prev32.reserve(sizeof(int32_t) * (size_t)cells));
         else CU(ctx->d_code.reserve((size_t)cells));
         CU(ctx->d_path_off.reserve(sizeof(int64_t) * (size_t)(m + 1)));
@@ -598,7 +603,7 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
         P.cell_off = ctx->d_cell_off.as<int64_t>();
         P.n_problems = m;
         P.results = ctx->d_results.as<sa_result>();
-        P.S = ctx->d_S.as<float>();
+        P.S = keep_S ? ctx->d_S.as<float>() : nullptr;
         P.code = ctx->d_code.as<uint8_t>();
         CU(cudaEventRecord(ctx->ev[0], ctx->stream));
         if (unbanded) {
@@ -624,6 +629,8 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
         T.S = P.S;
         T.code = unbanded ? nullptr : P.code;
         T.results = P.results;
+        T.init_mode = mode->init_mode;
+        T.swap = mode->swap_b_x != 0;
         // pass 1: measure the paths, prefix-sum the lengths into packed start offsets
         int64_t *d_start = ctx->d_path_off.as<int64_t>();
         T.count_only = 1;
@@ -736,14 +743,11 @@ int sa_fill_one(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problem, con
     int rc = check_problems(ctx, &pr, 1, used_bits ? 1 : 0);
     if (rc) return rc;
     const int nb = ctx->sides[0].labels(pr.contig), nx = ctx->sides[1].labels(pr.seg);
-    const int64_t cap = std::min(nb, nx);
-    std::vector<int64_t> poff = {0, cap};
-    std::vector<int32_t> pj((size_t)cap), pq((size_t)cap);
-    std::vector<float> ps((size_t)cap);
     if (used_bits) pr.used_slot = 0;
-    rc = sa_align_batch(ctx, mode, &pr, 1, used_bits, used_words, used_bits ? 1 : 0, poff.data(), result, pj.data(),
-                        pq.data(), ps.data());
+    int64_t total = 0;
+    rc = align_packed(ctx, mode, &pr, 1, used_bits, used_words, used_bits ? 1 : 0, &total, /*want_S=*/true);
     if (rc) return rc;
+    *result = ctx->h_res.as<sa_result>()[0];
     const size_t cells = (size_t)nb * nx;
     if (S) CU(cudaMemcpy(S, ctx->d_S.p, sizeof(float) * cells, cudaMemcpyDeviceToHost));
     if (prev && mode->lookback != LB) {

@@ -472,7 +472,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         float *Sout = nullptr;
         uint8_t *Cout = nullptr;
         if (STORE) {
-            Sout = P.S + P.cell_off[pidx];
+            Sout = P.S ? P.S + P.cell_off[pidx] : nullptr;
             Cout = P.code + P.cell_off[pidx];
         }
 
@@ -719,7 +719,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     // stage this column; every 8 columns (and at the end of the row) flush the 32 x 8 tile: 8 lanes
                     // write the 8 consecutive columns of one row, 4 rows per instruction
                     const int cq = q & 7;
-                    sts_f32(a_tile_s + lane * 36 + cq * 4, val);
+                    if (Sout) sts_f32(a_tile_s + lane * 36 + cq * 4, val);  // Sout == nullptr: only the codes are stored
                     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_tile_c + lane * 12 + cq), "r"(code) : "memory");
                     if (cq == 7 || q == nx - 1) {
                         __syncwarp();
@@ -732,7 +732,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                                 const long long o = (long long)jr * nx + q0 + col;
                                 uint32_t cv;
                                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cv) : "r"(a_tile_c + r * 12 + col));
-                                Sout[o] = lds_f32(a_tile_s + r * 36 + col * 4);
+                                if (Sout) Sout[o] = lds_f32(a_tile_s + r * 36 + col * 4);
                                 Cout[o] = (uint8_t)cv;
                             }
                         }
@@ -1025,7 +1025,8 @@ __global__ void trace_kernel(const TraceParams P) {
     const sa_problem pr = P.problems[k];
     const int64_t xoff = P.segs.pos_off[pr.seg];
     const int nx = (int)(P.segs.pos_off[pr.seg + 1] - xoff) - 1;
-    const float *S = P.S + P.cell_off[k];
+    // S == nullptr: only the predecessor codes were stored; the scores along the path are recomputed below
+    const float *S = P.S ? P.S + P.cell_off[k] : nullptr;
     const uint8_t *C = P.code ? P.code + P.cell_off[k] : nullptr;
     sa_result res = P.results[k];
     int j = res.j, q = res.q;
@@ -1039,13 +1040,13 @@ __global__ void trace_kernel(const TraceParams P) {
         cap = P.path_off[k + 1] - base;
     }
     int n = 0;
-    if (j >= 0) res.score = S[(long long)j * nx + q];
+    if (j >= 0 && S) res.score = S[(long long)j * nx + q];
     while (j >= 0 && n < cap) {
         const long long c = (long long)j * nx + q;
         if (!P.count_only) {
             P.path_j[base + n] = j;
             P.path_q[base + n] = q;
-            P.path_s[base + n] = S[c];
+            if (S) P.path_s[base + n] = S[c];
         }
         n++;
         if (P.prev32) {
@@ -1060,6 +1061,35 @@ __global__ void trace_kernel(const TraceParams P) {
             j -= dj;
             q -= dq;
         }
+    }
+    if (!S && !P.count_only && n > 0) {
+        // Scores along the path, recomputed exactly as dp_align produced them (SegAligner.cpp:119-127): the path's first
+        // cell kept its initial value (code 0), every later cell is S[pred] + score_f(pred -> cell) in the reference's
+        // fp32 operation order with the bit-exact powf.  Saves storing 4 of the 5 bytes per DP cell.
+        const int64_t boff = P.contigs.pos_off[pr.contig];
+        const LabelOps *bops = P.contigs.ops + (boff - pr.contig);
+        const LabelOps *xops = P.segs.ops + (xoff - pr.seg);
+        const int j0 = P.path_j[base + n - 1], q0 = P.path_q[base + n - 1];
+        float sv;
+        if (P.init_mode == SA_INIT_SEMIGLOBAL) sv = (j0 == 0 || q0 < 2) ? 0.0f : NEG_INF;
+        else if (P.init_mode == SA_INIT_LOCAL) sv = 0.0f;
+        else sv = (j0 == 0 || q0 == 0) ? 0.0f : NEG_INF;
+        P.path_s[base + n - 1] = sv;
+        int jp = j0, qp = q0;
+        for (int t = n - 2; t >= 0; t--) {
+            const int jc = P.path_j[base + t], qc = P.path_q[base + t];
+            const int dj = jc - jp, dq = qc - qp;
+            const float discrep = fabsf(__fsub_rn(bops[jc].d[dj - 1], xops[qc].d[dq - 1]));
+            const float delta = powf12_slow(discrep);
+            float fnfp;
+            if (!P.swap) fnfp = (dj == 1) ? xops[qc].f[dq - 1] : __fadd_rn(5000.0f * (float)(dj - 1), xops[qc].f[dq - 1]);
+            else fnfp = (dq == 1) ? bops[jc].f[dj - 1] : __fadd_rn(5000.0f * (float)(dq - 1), bops[jc].f[dj - 1]);
+            sv = __fadd_rn(sv, __fsub_rn(10000.0f, __fadd_rn(fnfp, delta)));
+            P.path_s[base + t] = sv;
+            jp = jc;
+            qp = qc;
+        }
+        res.score = sv;
     }
     res.path_len = n;
     P.results[k] = res;

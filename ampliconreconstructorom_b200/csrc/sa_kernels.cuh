@@ -56,13 +56,14 @@ struct TraceParams {
     const sa_problem *problems;
     const int64_t *cell_off;
     long long n_problems;
-    const float *S;
+    const float *S;          // stored scores, or nullptr: banded fill stored only the codes, scores are recomputed
     const uint8_t *code;     // banded: predecessor codes
     const int32_t *prev32;   // unbanded (-nl): packed predecessors i<<16|p, -1 = none
     const int64_t *path_off;
     sa_result *results;
     int32_t *path_j, *path_q;
     float *path_s;
+    int32_t init_mode, swap;  // needed when S == nullptr (scores along the path are recomputed)
     int32_t count_only;  // 1: only measure the paths (results[k].path_len, len_out[k]); nothing is written
     int64_t *len_out;    // optional: path length per problem as int64 (input of the prefix sum)
 };

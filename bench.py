@@ -333,6 +333,11 @@ def main():
                                       "replays_per_cell": n_replays / cells,
                                       "fp64_instr_per_s_T": 17.0 * n_replays / (fill_ms[-1] * 1e-3) / 1e12,
                                       "frac_of_fp64_peak": 17.0 * n_replays / (fill_ms[-1] * 1e-3) / peak,
+                                      # XU pipe: 2 MUFU per predecessor evaluation (bound pass) + 2 F2F per replay, against the
+                                      # nominal 16 lanes/clk/SM x 148 SMs x the SM clock sampled during the run
+                                      "xu_instr_per_s_T": (2.0 * evals + 2.0 * n_replays) / (fill_ms[-1] * 1e-3) / 1e12,
+                                      "xu_frac_of_nominal": (2.0 * evals + 2.0 * n_replays) / (fill_ms[-1] * 1e-3)
+                                      / (16.0 * 148 * 1e6 * max(float(summarise_clocks(samples).get("sm_mhz") or 1965.0), 1.0)),
                                       "note": "executed work is bound by the XU pipe (2 MUFU per candidate, 16 lanes/clk/SM) "
                                               "and by issue slots, not by fp64 issue; see DESIGN.md 4.1"},
                          "kernel_ms_per_launch": sum(fill_ms) / K, "traffic": None,

@@ -3,7 +3,7 @@
 problem index (-ngpus=N).  Runs it on 1 GPU and on N GPUs, checks the two output directories are byte-identical and
 prints the phase timings.  The reference is far too slow for this size (~20 CPU core-hours); its parity is covered at
 CLI level by tests/test_cli_parity.py and tests/test_gpu_fullsize.py.
-usage: python tests/perf/c5_cohort.py [n_gpus] [scale]"""
+usage: python tests/perf/c5_cohort.py [n_gpus] [scale] [c5|c2]"""
 import os, shutil, subprocess, sys, tempfile, time
 from pathlib import Path
 import numpy as np
@@ -15,13 +15,17 @@ import cli_cases as cc
 n_gpus = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 tmp = Path(tempfile.mkdtemp(prefix="c5_"))
-segs, contigs = synth.make_workload(5, int(2000 * scale), int(3000 * scale), seg_median=40, contig_median=150,
-                                    contig_sigma=0.5, contig_clip=(40, 1200))
+config = sys.argv[3] if len(sys.argv) > 3 else "c5"
+if config == "c2":  # the bench.py workload (2,000 segments x 500 long DLE1 contigs) through the whole executable
+    segs, contigs = synth.make_workload(2000, int(2000 * scale), int(500 * scale))
+else:
+    segs, contigs = synth.make_workload(5, int(2000 * scale), int(3000 * scale), seg_median=40, contig_median=150,
+                                        contig_sigma=0.5, contig_clip=(40, 1200))
 synth.write_cmap(tmp / "segs.cmap", segs)
 synth.write_cmap(tmp / "contigs.cmap", contigs)
 nx = sum(len(m) - 1 for m in segs.values()); nb = sum(len(m) - 1 for m in contigs.values())
 cells = 2.0 * nx * nb
-print(f"C5: {len(segs)} segments ({nx} labels) x 2 orientations vs {len(contigs)} contigs ({nb} labels): {cells:.3e} scoring cells")
+print(f"{config.upper()}: {len(segs)} segments ({nx} labels) x 2 orientations vs {len(contigs)} contigs ({nb} labels): {cells:.3e} scoring cells")
 env = dict(os.environ, SA_VERBOSE="1")
 times = {}
 for g in sorted({1, n_gpus}):
