@@ -469,14 +469,10 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         const LabelOps *xops = P.segs.ops + (xoff - pr.seg);
         const uint32_t *used =
             (P.used_bits && pr.used_slot >= 0) ? P.used_bits + (long long)pr.used_slot * P.used_words_per_slot : nullptr;
-        float *Sout = nullptr;
-        uint8_t *Cout = nullptr;
-        if (STORE) {
-            Sout = P.S ? P.S + P.cell_off[pidx] : nullptr;
-            Cout = P.code + P.cell_off[pidx];
-        }
+        // (STORE: the output pointers are rebuilt from P.S / P.code + cell_off[pidx] at every flush instead of living in
+        // four registers through the bound pass -- the kernel is compiled for 80 registers)
 
-        unsigned n_replay = 0, n_rescan = 0;  // pruning statistics of this lane: fp64 replays, whole-cell rescans
+        unsigned n_replay = 0;  // pruning statistics of this lane: fp64 replays (rescans are rare: counted by an atomic)
         // backtrack-start tracking (per lane, reduced at the end)
         float st_s = NEG_INF;
         int st_j = -1, st_q = -1;
@@ -618,7 +614,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                                                          pbase, a_tab.t2d, a_tab.exp, best, code);
                             best = cr.best;
                             code = cr.code;
-                            n_rescan++;
+                            if (P.stats) atomicAdd(P.stats + 1, 1ull);
                         }
                     }
                 }
@@ -719,10 +715,13 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     // stage this column; every 8 columns (and at the end of the row) flush the 32 x 8 tile: 8 lanes
                     // write the 8 consecutive columns of one row, 4 rows per instruction
                     const int cq = q & 7;
-                    if (Sout) sts_f32(a_tile_s + lane * 36 + cq * 4, val);  // Sout == nullptr: only the codes are stored
+                    if (P.S) sts_f32(a_tile_s + lane * 36 + cq * 4, val);  // P.S == nullptr: only the codes are stored
                     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_tile_c + lane * 12 + cq), "r"(code) : "memory");
                     if (cq == 7 || q == nx - 1) {
                         __syncwarp();
+                        const long long coff = P.cell_off[pidx];
+                        float *Sout = P.S ? P.S + coff : nullptr;
+                        uint8_t *Cout = P.code + coff;
                         const int q0 = q - cq, col = lane & 7;
 #pragma unroll
                         for (int it = 0; it < 8; it++) {
@@ -848,11 +847,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
             }
         }
         if (P.stats) {
-            const unsigned a = __reduce_add_sync(0xffffffffu, n_replay), b = __reduce_add_sync(0xffffffffu, n_rescan);
-            if (lane == 0) {
-                atomicAdd(P.stats, (unsigned long long)a);
-                if (b) atomicAdd(P.stats + 1, (unsigned long long)b);
-            }
+            const unsigned a = __reduce_add_sync(0xffffffffu, n_replay);
+            if (lane == 0) atomicAdd(P.stats, (unsigned long long)a);
         }
         if ((NW == 1 && lane == 0) || (NW > 1 && threadIdx.x == 0 && crank == 0)) {
             sa_result res;
