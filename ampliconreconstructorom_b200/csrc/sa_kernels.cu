@@ -3,23 +3,28 @@
 //   fill_kernel    dp_align (/root/reference/SegAligner/SegAligner.cpp:95-133) with score_f (:83-92) inlined,
 //                  the three initialisers (:254-287) folded in as the cell's initial value, and the
 //                  backtrack-start scans (:142-154, :172-195) fused into the sweep.
-//   trace_kernel   get_aln_list (SAHelper.cpp:83-95).
+//   trace_kernel   get_aln_list (SAHelper.cpp:83-95); recomputes the scores along the path when only the
+//                  predecessor codes were stored.
+//   detect_kernel  multi_backtrack_scores + zero_out_aln (SegAligner.cpp:198-233).
 //
 // Mapping.  One warp owns one (contig x segment) problem at a time (persistent warps pull problems, largest
-// first, from a global queue).  Lanes lie along the contig (rows j) in strips of 32 rows; the warp sweeps the
-// segment columns q = 0..nx-1 of a strip, then moves to the next strip.  Cell (j,q) depends only on rows
-// j-6..j-1 and columns q-6..q-1 (SegAligner.cpp:100,108-110), so all 32 cells of a step are independent.
-//   * the last 6 columns of the strip live in a per-warp shared-memory ring [6][6+32]; entries 0..5 of each
-//     slot are the 6 rows above the strip (bottom rows of the previous strip, spilled to a small L2-resident
-//     scratch), so a predecessor read is one LDS with no boundary special-casing: out-of-matrix predecessors
-//     simply read -inf;
+// first, from a global queue; large problems are swept by a whole CTA or a thread-block cluster as a wavefront).
+// Lanes lie along the contig (rows j) in strips of 32 rows; the warp sweeps the segment columns q = 0..nx-1 of a
+// strip, then moves to the next strip.  Cell (j,q) depends only on rows j-6..j-1 and columns q-6..q-1
+// (SegAligner.cpp:100,108-110), so all 32 cells of a step are independent.
+//   * the last 6 columns of the strip live in a per-warp shared-memory ring, mirrored ([12][6+32]) so that the six
+//     previous columns sit at static offsets; entries 0..5 of each slot are the 6 rows above the strip (bottom rows
+//     of the previous strip, spilled to a small L2-resident scratch), so a predecessor read is one LDS with no
+//     boundary special-casing: out-of-matrix predecessors simply read -inf;
 //   * per-label operand tables (LabelOps) make `b[j]-b[i]`, `x[q]-x[p]` and the fp_t term single loads; the
 //     row-side values sit in registers for the whole strip, the column-side values are warp-uniform loads;
-//   * powf(discrep,1.2f) is replayed bit-exactly in fp64 (powf12.cuh) with its two tables in shared memory.
-// All fp32 arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction), in the reference's order.
-// Tie-breaking: the reference scans predecessors with i ascending then p ascending and replaces on strict '>'
-// (:109-127), i.e. the winner is the max score with the smallest (i,p).  We scan in exactly the reverse order
-// (dj = j-i ascending, dq = q-p ascending) and replace on '>=', which selects the same predecessor.
+//   * EXACT PRUNING (default): every candidate gets an fp32 upper bound of its score (two MUFU), only the winner's
+//     powf(discrep,1.2f) is replayed bit-exactly in fp64 (powf12.cuh, tables in shared memory), and a cell whose
+//     winner is not strictly ahead of the runner-up's bound is rescanned exactly (see "exact pruning" below).
+// All fp32 arithmetic of the exact path uses explicit round-to-nearest intrinsics (no FMA contraction), in the
+// reference's order.  Tie-breaking: the reference scans predecessors with i ascending then p ascending and replaces on
+// strict '>' (:109-127), i.e. the winner is the max score with the smallest (i,p) = the largest (dj,dq); the exact
+// rescan (cell_slow) scans dj, dq ascending and keeps the last maximum, which selects the same predecessor.
 #include <cstdio>
 #include <math_constants.h>
 #include <cooperative_groups.h>
@@ -315,12 +320,12 @@ __device__ __noinline__ float powf12_any(float ax, uint32_t t2d, uint32_t exp) {
 // Every fp32 operation of `S[i][p] + (10000 - ((fn + fp) + delta))` is monotone in delta, so a LOWER bound of
 // delta gives an UPPER bound `hi` of the candidate's exact score with no error analysis.  Per cell:
 //   1. all 36 candidates get `hi` from delta_lo(d) = ex2.approx(1.2 * lg2.approx(d) - PRUNE_C) (two MUFU, fp32 only;
-//      delta_lo <= the bit-exact powf replay for EVERY float, certified exhaustively on the GPU by sa_check_prune);
-//      the two largest `hi` are tracked, the candidate index rides in the low 3 mantissa bits of the key;
+//      delta_lo <= the bit-exact powf replay for EVERY float, certified exhaustively on the GPU by
+//      sa_check_prune_bound); the largest `hi` (with its candidate number) and the second largest are tracked;
 //   2. the candidate with the largest `hi` is evaluated exactly (the one fp64 replay of the cell);
-//   3. if its exact score is larger than the second largest `hi` (+ the key perturbation) it is the strict maximum and
-//      the cell is done; otherwise (ties and near-ties: rare) the whole cell is redone exactly by cell_slow().
-// Measured on the C2 workload: the second step settles > 99.9 % of the cells.
+//   3. if its exact score is larger than the second largest `hi` it is the strict maximum and the cell is done;
+//      otherwise (ties and near-ties: rare) the whole cell is redone exactly by cell_slow().
+// Measured on the C2 workload: step 3 settles 99.98 % of the cells.
 #ifndef SA_PRUNE_C
 #define SA_PRUNE_C 0x1p-16f  // >= 1.316e-5 needed for every float (measured, tools/chk_prune.py); 2^-16 = 1.526e-5
 #endif
