@@ -390,7 +390,9 @@ __device__ __noinline__ CellRes cell_slow(bool swap, uint32_t a_row, float dx0, 
 }
 
 constexpr int RING_W = 40;  // 6 halo rows + 32 lanes + 2 pad
-constexpr int STAGE_BYTES_PER_WARP = 32 * 9 * 4 + 32 * 12;  // STORE staging tiles: scores [32][9] floats + codes [32][12] bytes
+// STORE staging per warp: scores [32][9] floats + codes [32][12] bytes + the problem's cell offset (8 B, read back at every
+// flush from shared memory instead of living in registers or being re-fetched from global memory)
+constexpr int STAGE_BYTES_PER_WARP = 32 * 9 * 4 + 32 * 12 + 16;
 #define NEG_INF (-CUDART_INF_F)
 
 // NW = warps that cooperate on one problem.
@@ -474,8 +476,15 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         const LabelOps *xops = P.segs.ops + (xoff - pr.seg);
         const uint32_t *used =
             (P.used_bits && pr.used_slot >= 0) ? P.used_bits + (long long)pr.used_slot * P.used_words_per_slot : nullptr;
-        // (STORE: the output pointers are rebuilt from P.S / P.code + cell_off[pidx] at every flush instead of living in
-        // four registers through the bound pass -- the kernel is compiled for 80 registers)
+        // (STORE: the output pointers are rebuilt at every flush from P.S / P.code + the cell offset parked in shared memory,
+        // instead of living in four registers through the bound pass -- the kernel is compiled for 80 registers)
+        if (STORE) {
+            if (lane == 0) {
+                const long long coff = P.cell_off[pidx];
+                asm volatile("st.shared.s64 [%0], %1;" ::"r"(a_tile_c + 32 * 12), "l"(coff) : "memory");
+            }
+            __syncwarp();
+        }
 
         unsigned n_replay = 0;  // pruning statistics of this lane: fp64 replays (rescans are rare: counted by an atomic)
         // backtrack-start tracking (per lane, reduced at the end)
@@ -724,7 +733,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_tile_c + lane * 12 + cq), "r"(code) : "memory");
                     if (cq == 7 || q == nx - 1) {
                         __syncwarp();
-                        const long long coff = P.cell_off[pidx];
+                        long long coff;
+                        asm volatile("ld.shared.s64 %0, [%1];" : "=l"(coff) : "r"(a_tile_c + 32 * 12));
                         float *Sout = P.S ? P.S + coff : nullptr;
                         uint8_t *Cout = P.code + coff;
                         const int q0 = q - cq, col = lane & 7;
