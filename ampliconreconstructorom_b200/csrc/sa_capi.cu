@@ -274,7 +274,7 @@ int prepare_fill(sa_ctx *ctx, FillParams &P, const sa_mode *mode) {
 
 // Launch the fill over an uploaded problem list whose device order array holds n_bulk bulk problems followed
 // by n_large large ones.  The two kernels run concurrently (stream / stream2) and join on `stream`.
-int launch_fill_classes(sa_ctx *ctx, FillParams P, const int32_t *d_order, const Plan &plan, bool store, bool swap) {
+int launch_fill_classes(sa_ctx *ctx, FillParams P, const int32_t *d_order, const Plan &plan, int store, bool swap) {
     const int64_t n_bulk = plan.n_bulk, n_large = plan.n_large, n_huge = plan.n_huge;
     unsigned long long *counters = ctx->d_counter.as<unsigned long long>();
     CU(cudaMemsetAsync(counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -493,7 +493,7 @@ int sa_plan_score(sa_ctx *ctx, sa_plan *pl, const sa_mode *mode) {
     P.results = pl->d_results.as<sa_result>();
     ctx->timing = {-1.0f, 0, 0, 0};  // fill_ms resolved lazily by sa_get_timing
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    rc = launch_fill_classes(ctx, P, pl->d_order.as<int32_t>(), pl->plan, false, mode->swap_b_x != 0);
+    rc = launch_fill_classes(ctx, P, pl->d_order.as<int32_t>(), pl->plan, 0, mode->swap_b_x != 0);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     return SA_OK;
@@ -614,7 +614,7 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
             CU(cudaGetLastError());
             ctx->timing.n_launches += 1;
         } else {
-            rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan, true, mode->swap_b_x != 0);
+            rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan, keep_S ? 2 : 1, mode->swap_b_x != 0);
             if (rc) return rc;
         }
         CU(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -852,7 +852,7 @@ int sa_detect_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
             CU(cudaGetLastError());
             ctx->timing.n_launches += 1;
         } else {
-            rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan, true, mode->swap_b_x != 0);
+            rc = launch_fill_classes(ctx, P, ctx->d_order.as<int32_t>(), plan, 2, mode->swap_b_x != 0);
             if (rc) return rc;
         }
         CU(cudaEventRecord(ctx->ev[1], ctx->stream));

@@ -405,8 +405,12 @@ constexpr int STAGE_BYTES_PER_WARP = 32 * 9 * 4 + 32 * 12 + 16;
 //   CS  > 1 : a thread-block CLUSTER of CS such CTAs (CS*NW warps on CS SMs) sweeps one huge problem: same wavefront,
 //             the step barrier becomes a cluster barrier, bottom rows cross CTA boundaries through a small
 //             L2-resident mailbox.  Used for chromosome-sized problems whose single-SM time would be the tail.
-template <bool STORE, bool SWAP, int NW, int MINB, int CS>
+// STORE_MODE: 0 = nothing per cell (scoring), 1 = predecessor codes only (alignment), 2 = codes + scores + per-row maxima
+// (detection, -nl-free test hook).  Separate instantiations keep the alignment kernel free of the registers mode 2 needs.
+template <int STORE_MODE, bool SWAP, int NW, int MINB, int CS>
 __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_kernel(const FillParams P) {
+    constexpr bool STORE = STORE_MODE != 0;
+    constexpr bool STORE_S = STORE_MODE == 2;
     constexpr int WPC = (NW == 1) ? FILL_WARPS : NW;  // warps per CTA
     constexpr int NWT = NW * CS;                        // warps in the wavefront
     static_assert(CS == 1 || NW > 1, "clusters only for the cooperative shape");
@@ -729,13 +733,13 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     // stage this column; every 8 columns (and at the end of the row) flush the 32 x 8 tile: 8 lanes
                     // write the 8 consecutive columns of one row, 4 rows per instruction
                     const int cq = q & 7;
-                    if (P.S) sts_f32(a_tile_s + lane * 36 + cq * 4, val);  // P.S == nullptr: only the codes are stored
+                    if (STORE_S) sts_f32(a_tile_s + lane * 36 + cq * 4, val);
                     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_tile_c + lane * 12 + cq), "r"(code) : "memory");
                     if (cq == 7 || q == nx - 1) {
                         __syncwarp();
                         long long coff;
                         asm volatile("ld.shared.s64 %0, [%1];" : "=l"(coff) : "r"(a_tile_c + 32 * 12));
-                        float *Sout = P.S ? P.S + coff : nullptr;
+                        float *Sout = STORE_S ? P.S + coff : nullptr;
                         uint8_t *Cout = P.code + coff;
                         const int q0 = q - cq, col = lane & 7;
 #pragma unroll
@@ -746,7 +750,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                                 const long long o = (long long)jr * nx + q0 + col;
                                 uint32_t cv;
                                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cv) : "r"(a_tile_c + r * 12 + col));
-                                if (Sout) Sout[o] = lds_f32(a_tile_s + r * 36 + col * 4);
+                                if (STORE_S) Sout[o] = lds_f32(a_tile_s + r * 36 + col * 4);
                                 Cout[o] = (uint8_t)cv;
                             }
                         }
@@ -754,7 +758,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     }
                 }
                 if (row_ok) {
-                    if (STORE) {
+                    if (STORE_S) {
                         if (P.rowmax_s) {
                             if (val > 0.0f && val >= rm_s) {
                                 rm_s = val;
@@ -1316,8 +1320,8 @@ static size_t fill_dyn_smem(int wpc, bool store = true) {
            (store ? (size_t)wpc * STAGE_BYTES_PER_WARP : 0);
 }
 template <int NW, int MINB, int CS>
-static void launch_fill_t(const FillParams &p, bool store, bool swap, int n_ctas, cudaStream_t st) {
-    const size_t sm = fill_dyn_smem(NW == 1 ? FILL_WARPS : NW, store);
+static void launch_fill_t(const FillParams &p, int store, bool swap, int n_ctas, cudaStream_t st) {
+    const size_t sm = fill_dyn_smem(NW == 1 ? FILL_WARPS : NW, store != 0);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_ctas);
     cfg.blockDim = dim3((NW == 1 ? FILL_WARPS : NW) * 32);
@@ -1335,17 +1339,20 @@ static void launch_fill_t(const FillParams &p, bool store, bool swap, int n_ctas
         cudaFuncSetAttribute(fill_kernel<S_, W_, NW, MINB, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
         cudaLaunchKernelEx(&cfg, fill_kernel<S_, W_, NW, MINB, CS>, p);                                                \
     } while (0)
-    if (store) {
-        if (swap) SA_LAUNCH_FILL(true, true);
-        else SA_LAUNCH_FILL(true, false);
+    if (store == 2) {
+        if (swap) SA_LAUNCH_FILL(2, true);
+        else SA_LAUNCH_FILL(2, false);
+    } else if (store == 1) {
+        if (swap) SA_LAUNCH_FILL(1, true);
+        else SA_LAUNCH_FILL(1, false);
     } else {
-        if (swap) SA_LAUNCH_FILL(false, true);
-        else SA_LAUNCH_FILL(false, false);
+        if (swap) SA_LAUNCH_FILL(0, true);
+        else SA_LAUNCH_FILL(0, false);
     }
 #undef SA_LAUNCH_FILL
 }
 // shape: 0 = bulk (one warp per problem), 1 = cooperative CTA, 2 = cooperative cluster of CLUSTER_CTAS CTAs
-void launch_fill(const FillParams &p, bool store, bool swap, int shape, int n_ctas, cudaStream_t st) {
+void launch_fill(const FillParams &p, int store, bool swap, int shape, int n_ctas, cudaStream_t st) {
     if (shape == 2) launch_fill_t<CLUSTER_WARPS, 1, CLUSTER_CTAS>(p, store, swap, n_ctas, st);
     else if (shape == 1) launch_fill_t<COOP_WARPS, COOP_MINB, 1>(p, store, swap, n_ctas, st);
     else launch_fill_t<1, FILL_MINB, 1>(p, store, swap, n_ctas, st);
@@ -1405,10 +1412,10 @@ int max_clusters() {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaFuncSetAttribute(fill_kernel<false, false, CLUSTER_WARPS, 1, CLUSTER_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(fill_kernel<0, false, CLUSTER_WARPS, 1, CLUSTER_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)fill_dyn_smem(CLUSTER_WARPS));
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, fill_kernel<false, false, CLUSTER_WARPS, 1, CLUSTER_CTAS>, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&n, fill_kernel<0, false, CLUSTER_WARPS, 1, CLUSTER_CTAS>, &cfg) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -1416,9 +1423,9 @@ int max_clusters() {
 }
 int fill_ctas_per_sm() {
     int n = 0;
-    cudaFuncSetAttribute(fill_kernel<false, false, 1, FILL_MINB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(fill_kernel<0, false, 1, FILL_MINB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)fill_dyn_smem(FILL_WARPS));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<false, false, 1, FILL_MINB, 1>, FILL_WARPS * 32,
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<0, false, 1, FILL_MINB, 1>, FILL_WARPS * 32,
                                                   fill_dyn_smem(FILL_WARPS));
     return n > 0 ? n : 1;
 }

@@ -84,7 +84,8 @@ struct DetectParams {
 };
 
 void launch_detect(const DetectParams &p, cudaStream_t st);
-void launch_fill(const FillParams &p, bool store, bool swap, int shape, int n_ctas, cudaStream_t st);
+// store: 0 = scoring (nothing per cell), 1 = predecessor codes, 2 = codes + scores (+ per-row maxima when requested)
+void launch_fill(const FillParams &p, int store, bool swap, int shape, int n_ctas, cudaStream_t st);
 int max_clusters();
 void launch_fill_unbanded(const FillParams &p, int32_t *prev32, bool swap, int n_ctas, cudaStream_t st);
 void launch_traceback(const TraceParams &p, cudaStream_t st);
