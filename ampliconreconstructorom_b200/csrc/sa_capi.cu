@@ -235,6 +235,8 @@ int check_problems(sa_ctx *ctx, const sa_problem *pr, int64_t n, int64_t n_used_
         if (pr[k].used_slot >= n_used_slots) return fail(ctx, SA_EINVAL, "problem: used_slot out of range");
         if (ctx->sides[0].labels(pr[k].contig) < 1 || ctx->sides[1].labels(pr[k].seg) < 1)
             return fail(ctx, SA_EINVAL, "problem " + std::to_string(k) + ": map without labels");
+        if ((double)ctx->sides[0].labels(pr[k].contig) * (double)std::max(ctx->sides[1].labels(pr[k].seg), 128) > 34359738368.0)
+            return fail(ctx, SA_EINVAL, "problem " + std::to_string(k) + ": more than 2^35 DP cells (32-bit step counter)");
     }
     return SA_OK;
 }

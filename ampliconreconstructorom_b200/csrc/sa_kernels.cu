@@ -494,12 +494,18 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         // backtrack-start tracking (per lane, reduced at the end)
         float st_s = NEG_INF;
         int st_j = -1, st_q = -1;
-        long long st_ord = 0x7fffffffffffffffll;
+        // position of a cell in sg_aln_backtrack_start's scan (last row by q, then rows by j over the last 2 columns);
+        // derived from (j, q) when needed instead of being carried in two registers through the sweep
+        auto sg_ord = [&](int jj, int qq) -> long long {
+            if (jj < 0) return 0x7fffffffffffffffll;
+            return (jj == nb - 1) ? (long long)qq : (long long)nx + 2ll * jj + (qq - (nx - 2));
+        };
+        long long st_ord = 0x7fffffffffffffffll;  // filled in after the sweep
 
         const int nstrips = (nb + 31) >> 5;
         const int R = (NW == 1) ? nx : (nx > NWT ? nx : NWT);  // steps per round
         const int rounds = (nstrips + NWT - 1) / NWT;
-        const long long T = (long long)rounds * R + (NWT - 1);
+        const int T = rounds * R + (NWT - 1);  // < 2^31: check_problems() rejects problems with more than 2^35 cells
 
         // per-warp sweep state
         int strip = w;
@@ -519,7 +525,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         float rm_s = 0.0f;  // detection: best positive score of this lane's row, ties -> larger q
         int rm_q = -1;
 
-        for (long long t = 0; t < T; t++) {
+        for (int t = 0; t < T; t++) {
             const bool active = (NW == 1) ? true : ((t >= w) && (strip < nstrips) && (q < nx));  // NW==1: T = nstrips*nx
             float val = 0.0f, rv = 0.0f, hv = NEG_INF;
             int code = 0;
@@ -781,12 +787,10 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                         const bool last_row = (j == nb - 1);
                         const bool last_cols = (q >= nx - 2);
                         if (last_row || last_cols) {
-                            const long long ord = last_row ? (long long)q : (long long)nx + 2ll * j + (q - (nx - 2));
-                            if (val > st_s || (val == st_s && ord < st_ord)) {
+                            if (val > st_s || (val == st_s && sg_ord(j, q) < sg_ord(st_j, st_q))) {
                                 st_s = val;
                                 st_j = j;
                                 st_q = q;
-                                st_ord = ord;
                             }
                         }
                     }
@@ -805,6 +809,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
 
         // reduce the start over lanes (and warps): max score, ties -> smallest scan order
         if (P.start_mode == SA_START_LOCAL) st_ord = (st_j < 0) ? 0x7fffffffffffffffll : (long long)st_j * nx + st_q;
+        else if (P.start_mode == SA_START_SEMIGLOBAL) st_ord = sg_ord(st_j, st_q);
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) {
             const float os = __shfl_xor_sync(0xffffffffu, st_s, m);
