@@ -549,6 +549,8 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
     rc = prepare_fill(ctx, P, mode);
     if (rc) return rc;
     if (used_bits && n_used_slots > 0) {
+        if ((double)used_words_per_slot * (double)n_used_slots >= 2147483648.0)
+            return fail(ctx, SA_EINVAL, "used-label bitmaps exceed 2^31 words");
         const size_t bytes = sizeof(uint32_t) * (size_t)(used_words_per_slot * n_used_slots);
         CU(ctx->d_used.reserve(bytes));
         CU(cudaMemcpyAsync(ctx->d_used.p, used_bits, bytes, cudaMemcpyHostToDevice, ctx->stream));

@@ -474,12 +474,13 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         const sa_problem pr = P.problems[pidx];
         const int64_t boff = P.contigs.pos_off[pr.contig];
         const int nb = (int)(P.contigs.pos_off[pr.contig + 1] - boff) - 1;
-        const LabelOps *bops = P.contigs.ops + (boff - pr.contig);
+        // label / bitmap bases as 32-bit element offsets from the kernel-parameter pointers (one register each instead
+        // of a 64-bit pointer; the map sets hold fewer than 2^31 labels, sa_set_maps checks)
+        const int bo = (int)(boff - pr.contig);  // bops = P.contigs.ops + bo: only needed at strip set-up
         const int64_t xoff = P.segs.pos_off[pr.seg];
         const int nx = (int)(P.segs.pos_off[pr.seg + 1] - xoff) - 1;
         const LabelOps *xops = P.segs.ops + (xoff - pr.seg);
-        const uint32_t *used =
-            (P.used_bits && pr.used_slot >= 0) ? P.used_bits + (long long)pr.used_slot * P.used_words_per_slot : nullptr;
+        const int used_off = (P.used_bits && pr.used_slot >= 0) ? pr.used_slot * (int)P.used_words_per_slot : -1;  // host-checked < 2^31
         // (STORE: the output pointers are rebuilt at every flush from P.S / P.code + the cell offset parked in shared memory,
         // instead of living in four registers through the bound pass -- the kernel is compiled for 80 registers)
         if (STORE) {
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     j = (strip << 5) + lane;
                     row_ok = j < nb;
                     jc = row_ok ? j : nb - 1;
-                    const float4 *src = reinterpret_cast<const float4 *>(bops + jc);
+                    const float4 *src = reinterpret_cast<const float4 *>(P.contigs.ops + bo + jc);
                     const float4 a = __ldg(src), b4 = __ldg(src + 1), c4 = __ldg(src + 2);
 #if SA_PRUNE
                     db[0] = a.x, db[1] = a.y, db[2] = a.z, db[3] = a.w, db[4] = b4.x, db[5] = b4.y;
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                         sts_f32(a_row + 6 * 128, b4.z), sts_f32(a_row + 7 * 128, b4.w), sts_f32(a_row + 8 * 128, c4.x);
                         sts_f32(a_row + 9 * 128, c4.y), sts_f32(a_row + 10 * 128, c4.z), sts_f32(a_row + 11 * 128, c4.w);
                     }
-                    row_used = used ? ((used[jc >> 5] >> (jc & 31)) & 1u) : false;
+                    row_used = used_off >= 0 ? ((P.used_bits[used_off + (jc >> 5)] >> (jc & 31)) & 1u) : false;
                     __syncwarp();
 #pragma unroll
                     for (int s = 0; s < 2 * LB; s++) {
