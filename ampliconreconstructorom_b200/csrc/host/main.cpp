@@ -521,6 +521,24 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
     if (o.inst_gen == 2) o.max_seg_contig_alns *= 2;  // main.cpp:479-481
 
     PhaseTimer pt;
+    // A run that was told to use one GPU hides the others from the CUDA driver before its first CUDA call: driver
+    // initialisation enumerates every visible device, which costs seconds on an 8-GPU box (measured: 5-6 s to open
+    // one context there vs 0.4-2 s on a single-GPU box).  Only when nothing is open yet (not in the resident server).
+    {
+        int want = o.n_gpus;
+        if (want <= 0)
+            if (const char *e = getenv("SA_NGPUS")) want = atoi(e);
+        if (want == 1 && eng.ctx.empty() && !keep_open) {
+            const char *vis = getenv("CUDA_VISIBLE_DEVICES");
+            std::string first = "0";
+            if (vis && *vis) {
+                first = vis;
+                const size_t comma = first.find(',');
+                if (comma != std::string::npos) first.resize(comma);
+            }
+            setenv("CUDA_VISIBLE_DEVICES", first.c_str(), 1);
+        }
+    }
     // CUDA start-up (driver init + context, ~0.3 s) overlaps with CMAP parsing: open device 0 right away
     JobExit open_err{0, false};
     std::thread gpu_open([&eng, &open_err]() {
