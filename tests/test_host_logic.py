@@ -87,6 +87,27 @@ def test_score_thresholds(oracle, n_contigs, n_detect, per_pair):
             assert capi.host_format_float(ours[1]) == "-nan"
 
 
+def test_score_thresholds_threaded_partial_sort(oracle):
+    """Cohort-sized score vectors (> 65 536 rows) take the multi-threaded path of compute_score_thresholds, which orders
+    only the tail of each segment's scores that the regression reads; it must still equal the oracle, which sorts
+    everything like the reference (main.cpp:59)."""
+    rng = np.random.default_rng(99)
+    segs = {k: helpers.random_map(rng, int(rng.integers(8, 40))) for k in list(range(-30, 0)) + list(range(1, 31))}
+    n_contigs = 1500
+    contigs = {k + 1: helpers.random_map(rng, int(rng.integers(20, 60))) for k in range(n_contigs)}
+    s_ids, c_ids = np.array(sorted(segs)), np.array(sorted(contigs))
+    rs = np.repeat(s_ids, n_contigs)
+    rc = np.tile(c_ids, s_ids.size)
+    sc = rng.normal(20000, 15000, size=rs.size).astype(np.float32)
+    assert rs.size > 65536
+    m = sum(len(v) - 1 for v in contigs.values())
+    for pv in (float(np.float32(1e-4)), float(np.float32(1e-6))):
+        ours = capi.host_score_thresholds(rs, rc, sc, segs, contigs, pv, 500)
+        for s in segs:
+            exp = oracle.threshold(sc[rs == s], n_contigs, 500, m, len(segs[s]) - 1, pv)
+            assert (np.isnan(exp) and np.isnan(ours[s])) or bits(exp) == bits(ours[s])
+
+
 @pytest.mark.parametrize("n_contigs,seg_lo", [(80, 12), (200, 6)])
 def test_score_thresholds_match_reference(ref, n_contigs, seg_lo):
     """Segments with < 12 labels shift the regression window down by 25 (main.cpp:80-82); with fewer than 170
