@@ -28,6 +28,11 @@ class Mode(C.Structure):
                 ("lookback", C.c_int32), ("swap_b_x", C.c_int32)]
 
 
+class PackedPaths(C.Structure):
+    _fields_ = [("n", C.c_int64), ("total", C.c_int64), ("results", C.c_void_p), ("start", C.c_void_p),
+                ("path_j", C.c_void_p), ("path_q", C.c_void_p), ("path_s", C.c_void_p)]
+
+
 class Timing(C.Structure):
     _fields_ = [("fill_ms", C.c_float), ("post_ms", C.c_float), ("n_launches", C.c_int32), ("reserved", C.c_int32)]
 
@@ -70,6 +75,7 @@ def load_library() -> C.CDLL:
     lib.sa_plan_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_double)]
     lib.sa_sync.argtypes = [vp]
     lib.sa_align_batch.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, i64, i64, vp, vp, vp, vp, vp]
+    lib.sa_align_batch_packed.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, i64, i64, C.POINTER(PackedPaths)]
     lib.sa_detect_batch.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, vp, vp, vp]
     lib.sa_fill_one.argtypes = [vp, C.POINTER(Mode), vp, vp, i64, vp, vp, vp]
     lib.sa_powf12.argtypes = [vp, vp, i64, vp, C.c_int]
@@ -296,6 +302,29 @@ class Context:
                                             used_words_per_slot, n_slots, _ptr(path_off), _ptr(res), _ptr(pj),
                                             _ptr(pq), _ptr(ps)), "sa_align_batch")
         return res, path_off, pj, pq, ps
+
+    def align_batch_packed(self, mode: Mode, problems: np.ndarray, used_bits: np.ndarray | None = None,
+                           used_words_per_slot: int = 0):
+        """sa_align_batch_packed: returns copies (results, start, path_j, path_q, path_s) of the context-owned buffers;
+        path k is path_*[start[k] : start[k] + results['path_len'][k]], end->start."""
+        problems = np.ascontiguousarray(problems, dtype=problem_dtype)
+        n = problems.size
+        n_slots = 0
+        if used_bits is not None:
+            used_bits = np.ascontiguousarray(used_bits, dtype=np.uint32)
+            n_slots = used_bits.size // max(used_words_per_slot, 1)
+        pk = PackedPaths()
+        self._check(self.lib.sa_align_batch_packed(self.h, C.byref(mode), _ptr(problems), n, _ptr(used_bits),
+                                                   used_words_per_slot, n_slots, C.byref(pk)), "sa_align_batch_packed")
+
+        def view(addr, count, dtype):
+            if count == 0 or not addr:
+                return np.zeros(0, dtype=dtype)
+            buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(addr)
+            return np.frombuffer(buf, dtype=dtype).copy()
+
+        return (view(pk.results, n, result_dtype), view(pk.start, n + 1, np.int64), view(pk.path_j, pk.total, np.int32),
+                view(pk.path_q, pk.total, np.int32), view(pk.path_s, pk.total, np.float32))
 
     def detect_batch(self, mode: Mode, problems: np.ndarray, n_want: np.ndarray):
         problems = np.ascontiguousarray(problems, dtype=problem_dtype)

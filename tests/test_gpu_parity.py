@@ -141,6 +141,34 @@ def test_used_label_masks_in_batch(ctx, oracle):
         assert not set(pj[sl][:-1].tolist()) & set(used_sets[k])
 
 
+def test_packed_alignment_output_equals_capacity_form(ctx, oracle):
+    """sa_align_batch_packed (what the executable uses: tracebacks packed by a device prefix sum, pinned buffers owned by
+    the context) against sa_align_batch with caller-provided capacity offsets, with and without used-label bitmaps."""
+    rng = np.random.default_rng(23)
+    contigs, segs, cp, sp = build_sets(rng, oracle, 16, 2, max_nb=260, max_nx=90)
+    cids = upload(ctx, contigs, cp, capi.SA_SIDE_CONTIG)
+    sids = upload(ctx, segs, sp, capi.SA_SIDE_SEG)
+    cc, ss = np.meshgrid(np.arange(len(cids)), np.arange(len(sids)), indexing="ij")
+    pr = ctx.problems(cc.ravel(), ss.ravel())
+    words = (max(len(contigs[c]) for c in cids) + 31) // 32
+    used = rng.integers(0, 2 ** 32, size=(pr.size, words), dtype=np.uint64).astype(np.uint32) & \
+        rng.integers(0, 2 ** 32, size=(pr.size, words), dtype=np.uint64).astype(np.uint32)
+    for init, fit, swap, start in MODES[:4]:
+        mode = ctx.mode(init, start, fit, 6, swap)
+        for ub, wps, slots in ((None, 0, False), (used.ravel(), words, True)):
+            p = pr.copy()
+            p["used_slot"] = np.arange(pr.size) if slots else -1
+            res, poff, pj, pq, ps = ctx.align_batch(mode, p, ub, wps)
+            r2, st, j2, q2, s2 = ctx.align_batch_packed(mode, p, ub, wps)
+            assert res.tobytes() == r2.tobytes()
+            assert int(st[-1]) == int(res["path_len"].sum()) == j2.size
+            for k in range(pr.size):
+                L = int(res["path_len"][k])
+                a, b = int(poff[k]), int(st[k])
+                assert np.array_equal(pj[a:a + L], j2[b:b + L]) and np.array_equal(pq[a:a + L], q2[b:b + L])
+                assert np.array_equal(bits(ps[a:a + L]), bits(s2[b:b + L]))
+
+
 def test_powf12_device_matches_host_libm(ctx, oracle):
     """Both device paths of powf(x,1.2f) against the host libm the reference links, on 2^22 random bit patterns
     plus every boundary of the fast-path domain and the special values."""
