@@ -375,8 +375,8 @@ class Context:
 
     def powf12_range(self, lo_bits: int, hi_bits: int):
         n = hi_bits - lo_bits
-        a = np.zeros(n, dtype=np.float32)
-        b = np.zeros(n, dtype=np.float32)
+        a = np.empty(n, dtype=np.float32)
+        b = np.empty(n, dtype=np.float32)
         self._check(self.lib.sa_powf12_range(self.h, lo_bits, hi_bits, _ptr(a), _ptr(b)), "sa_powf12_range")
         return a, b
 

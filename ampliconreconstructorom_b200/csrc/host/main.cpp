@@ -106,6 +106,21 @@ struct Engine {
         fprintf(stderr, "SegAligner(b200): %s failed (%d): %s\n", what, rc, c ? sa_last_error(c) : "");
         throw JobExit{2, true};
     }
+    // SA_GPU_OVERSUBSCRIBE=1 (testing aid): -ngpus=N may exceed the visible devices; context g then lives on device
+    // g % visible, so the sharded multi-GPU path (shard / score / align below) can be exercised on a one-GPU box.
+    static bool oversubscribe() {
+        const char *e = getenv("SA_GPU_OVERSUBSCRIBE");
+        return e && atoi(e) != 0;
+    }
+    void open_range(int have, int n, int avail) {
+        ctx.resize((size_t)n, nullptr);
+        std::vector<std::thread> th;
+        std::vector<int> rcs((size_t)n, 0);
+        for (int g = have; g < n; g++) th.emplace_back([&, g]() { rcs[(size_t)g] = sa_ctx_create(g % avail, &ctx[(size_t)g]); });
+        for (auto &t : th) t.join();
+        for (int g = have; g < n; g++)
+            if (rcs[(size_t)g]) die(nullptr, "sa_ctx_create (need an sm_100 GPU)", rcs[(size_t)g]);
+    }
     void open(int n) {
         if (!ctx.empty()) return;  // resident server: contexts stay open between jobs
         const int avail = sa_device_count();
@@ -113,27 +128,15 @@ struct Engine {
             fprintf(stderr, "SegAligner(b200): no CUDA device visible; this build has no CPU fallback\n");
             throw JobExit{2, true};
         }
-        n = std::max(1, std::min(n, avail));
-        ctx.assign((size_t)n, nullptr);
-        std::vector<std::thread> th;
-        std::vector<int> rcs((size_t)n, 0);
-        for (int g = 0; g < n; g++) th.emplace_back([&, g]() { rcs[(size_t)g] = sa_ctx_create(g, &ctx[(size_t)g]); });
-        for (auto &t : th) t.join();
-        for (int g = 0; g < n; g++)
-            if (rcs[(size_t)g]) die(nullptr, "sa_ctx_create (need an sm_100 GPU)", rcs[(size_t)g]);
+        n = std::max(1, oversubscribe() ? std::min(n, 64) : std::min(n, avail));
+        open_range(0, n, avail);
     }
     void open_more(int n) {  // device 0 is already open; add devices 1..n-1
         const int avail = sa_device_count();
-        n = std::max(1, std::min(n, avail));
+        n = std::max(1, oversubscribe() ? std::min(n, 64) : std::min(n, avail));
         const int have = (int)ctx.size();
         if (n <= have) return;
-        ctx.resize((size_t)n, nullptr);
-        std::vector<std::thread> th;
-        std::vector<int> rcs((size_t)n, 0);
-        for (int g = have; g < n; g++) th.emplace_back([&, g]() { rcs[(size_t)g] = sa_ctx_create(g, &ctx[(size_t)g]); });
-        for (auto &t : th) t.join();
-        for (int g = have; g < n; g++)
-            if (rcs[(size_t)g]) die(nullptr, "sa_ctx_create (need an sm_100 GPU)", rcs[(size_t)g]);
+        open_range(have, n, avail);
     }
     void close() {
         for (auto c : ctx) sa_ctx_destroy(c);
@@ -149,6 +152,9 @@ struct Engine {
             if (rc) die(ctx[(size_t)g], "sa_set_maps(segments)", rc);
         });
     }
+    // f(g) on one host thread per GPU.  die() throws JobExit; an exception must not escape a std::thread (that would be
+    // std::terminate instead of the documented exit code 2), so each worker parks its JobExit and the first one is
+    // rethrown on the calling thread after the join.
     template <class F>
     void parallel(F f) {
         if (ctx.size() == 1) {
@@ -156,8 +162,18 @@ struct Engine {
             return;
         }
         std::vector<std::thread> th;
-        for (int g = 0; g < (int)ctx.size(); g++) th.emplace_back([&, g]() { f(g); });
+        std::vector<JobExit> errs(ctx.size(), JobExit{0, false});
+        for (int g = 0; g < (int)ctx.size(); g++)
+            th.emplace_back([&, g]() {
+                try {
+                    f(g);
+                } catch (const JobExit &e) {
+                    errs[(size_t)g] = e.code ? e : JobExit{2, true};
+                }
+            });
         for (auto &t : th) t.join();
+        for (const JobExit &e : errs)
+            if (e.code) throw e;
     }
     // shard[g] = indices of the problems GPU g handles.  Problems are dealt round-robin WITHIN size classes
     // (1/4-octave of cells), largest classes first, so every GPU gets the same mix of sizes in O(n) (the library
@@ -574,10 +590,18 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
     fflush(stdout);
     if (segs.n_maps() == 0 || contigs.n_maps() == 0) {
         // nothing to align; the reference still writes the (empty) score files unless -fitting
-        if (!o.fitting_aln) {
+        if (!o.fitting_aln) {  // same progress lines as the reference's (empty) phases (main.cpp:528-649)
+            printf("Computing scoring thresholds.\n");
             write_all_scores({}, o.sample_prefix);
+            printf("Writing scoring distribution.\n");
             write_score_thresholds({}, o.sample_prefix + o.detection_label);
+            printf("Completed generating scores.\n");
+            printf("elapsed seconds for scoring %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
+            printf("Performing alignments\nFinished standard alignment. \n");
+            if (o.do_tip) printf("Doing tip alignment.\nPerforming alignments\nFinished tip alignments.\n\n");
         }
+        printf("elapsed seconds for run %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
+        fflush(stdout);
         gpu_open.join();
         if (open_err.code) throw open_err;
         if (!keep_open) eng.close();
@@ -733,14 +757,20 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
     return 0;
 }
 
-// ---- resident server (opt-in, SA_SERVER=1) ----------------------------------------------------------------------
+// ---- resident server ----------------------------------------------------------------------------------------------
 // OMPathFinder.py:407-428 execs one `SegAligner -fitting` process per candidate path (a 50-cell problem, 0.2 ms in
-// the reference); creating a CUDA context costs 0.3-1.7 s per process.  With SA_SERVER=1 the first invocation leaves
-// a background server holding the GPU context on a Unix socket; later invocations forward argv + cwd to it and
-// print the stdout it returns.  Same executable, same files, same exit codes; no CPU fallback anywhere.
+// the reference); creating a CUDA context costs 0.3-6 s per process.  The first such invocation therefore leaves a
+// background server holding the GPU context on a Unix socket; later invocations forward argv + cwd to it and print the
+// stdout it returns.  Same executable, same files, same exit codes; no CPU fallback anywhere.
+//   -fitting runs           use the server by default (idle timeout 30 s); SA_SERVER=0 turns that off
+//   SA_SERVER=1             every run goes through the server (idle timeout 300 s); SA_SERVER_IDLE=<s> overrides both
+// The socket lives in a directory only this user can enter ($XDG_RUNTIME_DIR/segaligner_b200, else
+// /tmp/segaligner_b200_<uid>, mode 0700, owner and mode verified with lstat), is bound under umask 077, and both ends
+// check SO_PEERCRED: a peer with another uid is never trusted -- the client then runs the job in-process instead.
 #include <fcntl.h>
 #include <poll.h>
 #include <signal.h>
+#include <sys/mman.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
 #include <sys/un.h>
@@ -748,9 +778,33 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
 
 namespace {
 
+// a directory that exists (created 0700 if missing), is a real directory (no symlink), is ours and is closed to others
+bool private_dir_ok(const std::string &dir) {
+    if (mkdir(dir.c_str(), 0700) != 0 && errno != EEXIST) return false;
+    struct stat sb;
+    if (lstat(dir.c_str(), &sb) != 0) return false;
+    return S_ISDIR(sb.st_mode) && sb.st_uid == getuid() && (sb.st_mode & 077) == 0;
+}
+
+// "" = no trustworthy place for the socket (the caller runs in-process)
 std::string server_socket_path() {
-    if (const char *e = getenv("SA_SERVER_SOCKET")) return e;
-    return "/tmp/segaligner_b200_" + std::to_string((long)getuid()) + ".sock";
+    if (const char *e = getenv("SA_SERVER_SOCKET")) return e;  // explicit path: the caller vouches for the directory
+    std::string dir;
+    if (const char *x = getenv("XDG_RUNTIME_DIR")) {
+        struct stat sb;
+        if (*x && lstat(x, &sb) == 0 && S_ISDIR(sb.st_mode) && sb.st_uid == getuid() && (sb.st_mode & 077) == 0)
+            dir = std::string(x) + "/segaligner_b200";
+    }
+    if (dir.empty()) dir = "/tmp/segaligner_b200_" + std::to_string((long)getuid());
+    if (!private_dir_ok(dir)) return "";
+    return dir + "/server.sock";
+}
+
+bool peer_is_me(int fd) {
+    struct ucred cr;
+    socklen_t len = sizeof cr;
+    if (getsockopt(fd, SOL_SOCKET, SO_PEERCRED, &cr, &len) != 0 || len != sizeof cr) return false;
+    return cr.uid == getuid();
 }
 
 bool write_all(int fd, const void *buf, size_t n) {
@@ -773,10 +827,6 @@ bool read_all(int fd, void *buf, size_t n) {
     }
     return true;
 }
-bool send_str(int fd, const std::string &s) {
-    const uint32_t n = (uint32_t)s.size();
-    return write_all(fd, &n, 4) && write_all(fd, s.data(), n);
-}
 bool recv_str(int fd, std::string &s) {
     uint32_t n = 0;
     if (!read_all(fd, &n, 4) || n > (64u << 20)) return false;
@@ -794,18 +844,36 @@ int connect_server(const std::string &path) {
         close(fd);
         return -1;
     }
+    if (!peer_is_me(fd)) {  // somebody else's process answers on this path: never hand it our argv or trust its reply
+        close(fd);
+        return -2;
+    }
     return fd;
 }
 
-[[noreturn]] void serve(const std::string &path) {
+[[noreturn]] void serve(const std::string &path, int idle_s) {
     const int ls = socket(AF_UNIX, SOCK_STREAM, 0);
     sockaddr_un a{};
     a.sun_family = AF_UNIX;
     snprintf(a.sun_path, sizeof a.sun_path, "%s", path.c_str());
+    umask(077);  // the socket is created 0600: no window between bind() and a later chmod()
     if (ls < 0 || bind(ls, (sockaddr *)&a, sizeof a) != 0 || listen(ls, 64) != 0) _exit(0);  // somebody else serves
-    chmod(path.c_str(), 0600);
-    int idle_s = 300;
     if (const char *e = getenv("SA_SERVER_IDLE")) idle_s = std::max(1, atoi(e));
+    // The server drives one GPU unless its environment asks for more (SA_NGPUS > 1): hiding the other devices before
+    // the first CUDA call saves seconds of driver initialisation on a multi-GPU box (see run_job).
+    {
+        const char *ng = getenv("SA_NGPUS");
+        if (!ng || atoi(ng) <= 1) {
+            const char *vis = getenv("CUDA_VISIBLE_DEVICES");
+            std::string first = "0";
+            if (vis && *vis) {
+                first = vis;
+                const size_t comma = first.find(',');
+                if (comma != std::string::npos) first.resize(comma);
+            }
+            setenv("CUDA_VISIBLE_DEVICES", first.c_str(), 1);
+        }
+    }
     Engine eng;
     bool fatal = false;
     while (!fatal) {
@@ -813,6 +881,10 @@ int connect_server(const std::string &path) {
         if (poll(&pf, 1, idle_s * 1000) <= 0) break;  // idle: give the GPU back
         const int c = accept(ls, nullptr, nullptr);
         if (c < 0) continue;
+        if (!peer_is_me(c)) {
+            close(c);
+            continue;
+        }
         uint32_t n_args = 0;
         std::vector<std::string> args;
         std::string cwd;
@@ -835,10 +907,12 @@ int connect_server(const std::string &path) {
             close(c);
             break;
         }
-        // run the job with stdout captured into an unlinked temp file
-        char tmpl[] = "/tmp/sa_b200_out_XXXXXX";
-        const int tf = mkstemp(tmpl);
-        unlink(tmpl);
+        // run the job with stdout captured into an anonymous memory file (no file-system round trip)
+        const int tf = memfd_create("sa_b200_stdout", MFD_CLOEXEC);
+        if (tf < 0) {
+            close(c);
+            continue;
+        }
         fflush(stdout);
         const int saved = dup(1);
         dup2(tf, 1);
@@ -873,10 +947,13 @@ int connect_server(const std::string &path) {
     _exit(0);
 }
 
-// returns -1 when the server route is unavailable (caller then runs the job in-process)
-int run_via_server(int argc, char *argv[]) {
+// returns -1 when the server route is unavailable or not trustworthy (caller then runs the job in-process)
+int run_via_server(int argc, char *argv[], int idle_s) {
     const std::string path = server_socket_path();
+    if (path.empty() || path.size() >= sizeof(sockaddr_un{}.sun_path)) return -1;
     int fd = connect_server(path);
+    if (fd == -2) return -1;
+    if (fd < 0 && argc == 2 && strcmp(argv[1], "--server-stop") == 0) return 0;  // nothing to stop
     if (fd < 0) {
         // no server yet (or a stale socket): start one.  fork happens before any CUDA call in this process.
         unlink(path.c_str());
@@ -892,21 +969,32 @@ int run_via_server(int argc, char *argv[]) {
                 if (!getenv("SA_VERBOSE")) dup2(dn, 2);
             }
             for (int f = 3; f < 256; f++) close(f);
-            serve(path);
+            serve(path, idle_s);
         }
         if (pid < 0) return -1;
-        for (int tries = 0; tries < 600 && fd < 0; tries++) {  // the socket appears before CUDA is initialised
-            usleep(5000);
+        for (int tries = 0; tries < 3000 && fd < 0; tries++) {  // the socket appears before CUDA is initialised
+            usleep(1000);
             fd = connect_server(path);
+            if (fd == -2) return -1;
         }
         if (fd < 0) return -1;
     }
     char cwd[4096];
     if (!getcwd(cwd, sizeof cwd)) cwd[0] = 0;
+    // one write: argc, argv strings and cwd, each length-prefixed
+    std::string msg;
+    auto put = [&msg](const void *p, size_t n) { msg.append((const char *)p, n); };
     const uint32_t n_args = (uint32_t)argc;
-    bool ok = write_all(fd, &n_args, 4);
-    for (int k = 0; ok && k < argc; k++) ok = send_str(fd, argv[k]);
-    ok = ok && send_str(fd, cwd);
+    put(&n_args, 4);
+    for (int k = 0; k < argc; k++) {
+        const uint32_t n = (uint32_t)strlen(argv[k]);
+        put(&n, 4);
+        put(argv[k], n);
+    }
+    const uint32_t nc = (uint32_t)strlen(cwd);
+    put(&nc, 4);
+    put(cwd, nc);
+    bool ok = write_all(fd, msg.data(), msg.size());
     uint32_t code = 0;
     uint64_t olen = 0;
     ok = ok && read_all(fd, &code, 4) && read_all(fd, &olen, 8) && olen < (1ull << 32);
@@ -920,6 +1008,9 @@ int run_via_server(int argc, char *argv[]) {
     close(fd);
     fwrite(out.data(), 1, out.size(), stdout);
     fflush(stdout);
+    if (code == 2)
+        fprintf(stderr, "SegAligner(b200): the job failed inside the resident server (exit code 2); rerun with SA_SERVER=0 "
+                        "to see its diagnostics\n");
     return (int)code;
 }
 
@@ -927,9 +1018,14 @@ int run_via_server(int argc, char *argv[]) {
 
 int main(int argc, char *argv[]) {
     signal(SIGPIPE, SIG_IGN);
+    // the resident server: always with SA_SERVER=1, never with SA_SERVER=0, by default for -fitting runs (the
+    // OMPathFinder pattern: thousands of tiny one-shot processes) with a short idle timeout
     const char *sv = getenv("SA_SERVER");
-    if (sv && atoi(sv) != 0) {
-        const int rc = run_via_server(argc, argv);
+    const bool forced = sv && atoi(sv) != 0, forbidden = sv && atoi(sv) == 0;
+    bool fitting = false;
+    for (int i = 3; i < argc; i++) fitting = fitting || strcmp(argv[i], "-fitting") == 0;
+    if (forced || (fitting && !forbidden) || (argc == 2 && strcmp(argv[1], "--server-stop") == 0)) {
+        const int rc = run_via_server(argc, argv, forced ? 300 : 30);
         if (rc >= 0) return rc;
     }
     Engine eng;

@@ -30,8 +30,10 @@ struct DevBuf {
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
+            (void)cudaGetLastError();  // clear the sticky allocation error, or the next launch check would report it
             e = cudaMalloc(&p, bytes);
             want = bytes;
+            if (e != cudaSuccess) (void)cudaGetLastError();
         }
         if (e == cudaSuccess) cap = want;
         return e;
@@ -229,6 +231,7 @@ namespace {
 
 int check_problems(sa_ctx *ctx, const sa_problem *pr, int64_t n, int64_t n_used_slots) {
     const int nc = ctx->sides[0].n_maps, ns = ctx->sides[1].n_maps;
+    if (n >= 2147483648ll) return fail(ctx, SA_EINVAL, "more than 2^31-1 problems in one batch (32-bit order arrays)");
     for (int64_t k = 0; k < n; k++) {
         if (pr[k].contig < 0 || pr[k].contig >= nc || pr[k].seg < 0 || pr[k].seg >= ns)
             return fail(ctx, SA_EINVAL, "problem " + std::to_string(k) + ": map index out of range");
@@ -423,6 +426,7 @@ int sa_set_maps(sa_ctx *ctx, int side, int32_t n_maps, const int64_t *off, const
     S.max_labels = 0;
     const int64_t n_pos = off[n_maps];
     const int64_t n_lab = n_pos - n_maps;
+    if (n_pos >= 2147483648ll) return fail(ctx, SA_EINVAL, "map set holds 2^31 or more entries (the kernels index labels with 32 bits)");
     for (int m = 0; m < n_maps; m++) {
         if (off[m + 1] - off[m] < 1) return fail(ctx, SA_EINVAL, "map with no entries");
         S.max_labels = std::max(S.max_labels, S.labels(m));
@@ -448,7 +452,7 @@ int sa_plan_create(sa_ctx *ctx, const sa_problem *problems, int64_t n, sa_plan *
     *out = nullptr;
     if (n <= 0 || !problems) return fail(ctx, SA_EINVAL, "empty problem list");
     CU(cudaSetDevice(ctx->device));
-    int rc = check_problems(ctx, problems, n, 0);
+    int rc = check_problems(ctx, problems, n, 0);  // also rejects n >= 2^31
     if (rc) return rc;
     sa_plan *pl = new sa_plan();
     pl->n = n;

@@ -475,7 +475,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         const int64_t boff = P.contigs.pos_off[pr.contig];
         const int nb = (int)(P.contigs.pos_off[pr.contig + 1] - boff) - 1;
         // label / bitmap bases as 32-bit element offsets from the kernel-parameter pointers (one register each instead
-        // of a 64-bit pointer; the map sets hold fewer than 2^31 labels, sa_set_maps checks)
+        // of a 64-bit pointer; sa_set_maps rejects map sets with 2^31 or more entries)
         const int bo = (int)(boff - pr.contig);  // bops = P.contigs.ops + bo: only needed at strip set-up
         const int64_t xoff = P.segs.pos_off[pr.seg];
         const int nx = (int)(P.segs.pos_off[pr.seg + 1] - xoff) - 1;

@@ -6,8 +6,9 @@ import numpy as np
 
 
 def shard_problems(cells: np.ndarray, world: int, rank: int) -> np.ndarray:
-    """Indices of the problems `rank` handles: problems sorted by size (largest first) and dealt round-robin, the
-    same rule the executable's multi-GPU engine uses (csrc/host/main.cpp Engine::shard)."""
+    """Indices of the problems `rank` handles: problems sorted by size (largest first, stable) and dealt round-robin, so
+    every rank gets the same mix of sizes.  (The executable's multi-GPU engine, csrc/host/main.cpp Engine::shard, deals
+    round-robin within 1/4-octave size classes instead of a full sort -- same balance, O(n).)"""
     order = np.argsort(-cells.astype(np.int64), kind="stable")
     return order[rank::world]
 

@@ -9,6 +9,30 @@
 
 float sao_powf12(float x) { return powf(x, 1.2f); }
 
+/* Exhaustive check helper: for every float bit pattern in [lo, hi) compare the host libm powf(x, 1.2f) the reference
+ * links (SegAligner.cpp:88) with two device result arrays (got_a/got_b, hi-lo entries each), bit for bit (NaN matches
+ * NaN).  Returns the number of mismatching patterns; *first_bad receives the first one (or 0xffffffff). */
+long long sao_powf12_cmp_range(unsigned lo, unsigned hi, const float *got_a, const float *got_b, unsigned *first_bad) {
+    long long bad = 0;
+    if (first_bad) *first_bad = 0xffffffffu;
+    for (unsigned long long i = 0; i < (unsigned long long)hi - lo; i++) {
+        unsigned bits = lo + (unsigned)i, e, a, b;
+        float x, r;
+        memcpy(&x, &bits, 4);
+        r = powf(x, 1.2f);
+        memcpy(&e, &r, 4);
+        memcpy(&a, &got_a[i], 4);
+        memcpy(&b, &got_b[i], 4);
+        if (r != r) { /* NaN: any NaN on the device side matches */
+            if (got_a[i] == got_a[i] || got_b[i] == got_b[i]) { if (!bad && first_bad) *first_bad = bits; bad++; }
+        } else if (a != e || b != e) {
+            if (!bad && first_bad) *first_bad = bits;
+            bad++;
+        }
+    }
+    return bad;
+}
+
 /* SegAligner.cpp:40-68.  left_0 = 1; nc_k = f(pos[k]-pos[k-1]); out[k-1] = left_{k-1}*nc_k; the last label
  * gets left_{last}*nc_last (:65) where nc_last is whatever `non_collapse` holds -- for a 1-label map that is
  * the value carried over from the previous map (:43). */

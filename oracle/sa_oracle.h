@@ -48,6 +48,8 @@ void sao_score_batch(int64_t n, const int *pair_contig, const int *pair_seg, con
 /* main.cpp:43-105 for one segment: scores (unsorted, n of them), returns threshold (NaN if window invalid). */
 float sao_score_threshold(const float *scores, int64_t n, int n_contigs, int n_detect_scores, int m_total_labels,
                           int seg_labels, double pvalue);
+/* host libm powf(x, 1.2f) vs two device result arrays over the float bit patterns [lo, hi); returns #mismatches */
+long long sao_powf12_cmp_range(unsigned lo, unsigned hi, const float *got_a, const float *got_b, unsigned *first_bad);
 #ifdef __cplusplus
 }
 #endif

@@ -51,10 +51,10 @@ def write_case(tmp: Path, segs, contigs):
     return tmp / "segs.cmap", tmp / "contigs.cmap"
 
 
-def run_bin(binary: Path, workdir: Path, seg_file, contig_file, flags, timeout=1800):
+def run_bin(binary: Path, workdir: Path, seg_file, contig_file, flags, timeout=1800, env=None):
     workdir.mkdir(parents=True, exist_ok=True)
     cmd = [str(binary), str(seg_file), str(contig_file), f"-prefix={workdir}/SA"] + list(flags)
-    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout, env=env)
     return p
 
 
@@ -109,3 +109,47 @@ def make_edge_case(seed: int):
 
 
 EDGE_FLAGS = ["-nthreads=2", "-min_labs=2", "-gen=2"]
+
+
+# ---- named BASELINE configs pinned against the reference binary --------------------------------------
+DATA = ROOT / "oracle" / "_ref" / "data"
+C1_FLAGS = ["-min_labs=10", "-gen=1"]  # README.md:162-191 (the GBM39 test run: BspQI / Irys = -gen=1)
+C5_FLAGS = ["-min_labs=12", "-gen=2"]
+
+
+def make_c1(n_contigs=2500, seed=39):
+    """C1: the shipped GBM39 segment CMAP (real data, argv[1]) against a seeded Irys-like BspQI assembly: `n_contigs`
+    contigs with ~LogNormal(median 110, sigma 0.5) labels clipped to [15, 600] cut from an in-silico BspQI genome, plus 6
+    contigs that are noisy windows of the real hg19 chr7 map over 54.5-56.5 Mb (where the GBM39 EGFR amplicon segments
+    come from), so that real alignments exist.  Returns (path of the segment CMAP, {id: contig map})."""
+    import gzip
+    rng = np.random.default_rng(seed)
+    nb = synth.lognormal_sizes(rng, n_contigs, 110, 0.5, 15, 600)
+    g = synth.genome_positions(rng, 400_000, "BspQI")
+    contigs = {}
+    for k in range(n_contigs):
+        s = int(rng.integers(1, g.size - nb[k] - 2))
+        contigs[k + 1] = synth.noisy_contig(rng, g, s, int(nb[k]))
+    chr7 = []
+    with gzip.open(DATA / "hg19_BspQI.cmap.gz", "rt") as f:
+        for line in f:
+            if line.startswith("#"):
+                continue
+            t = line.split("\t")
+            if t[0] == "7" and t[4] != "0":
+                chr7.append(float(t[5]))
+    chr7 = np.array(chr7)
+    lo = int(np.searchsorted(chr7, 54.5e6))
+    hi = int(np.searchsorted(chr7, 56.5e6))
+    for k in range(6):
+        n = int(rng.integers(60, 140))
+        s = int(rng.integers(lo, max(hi - n, lo + 1)))
+        contigs[n_contigs + k + 1] = synth.noisy_contig(rng, chr7, s, n)
+    return DATA / "GBM39_amplicon1_graph_BSPQI.cmap", contigs
+
+
+def make_c5_shaped(n_segs=300, n_contigs=320, seed=5):
+    """A C5-shaped subsample (cohort sweep: many short graph segments x many short genome-wide DLE1 contigs) of the
+    generator tests/perf/c5_cohort.py uses at full size, small enough for the reference to finish in about a minute."""
+    return synth.make_workload(seed, n_segs, n_contigs, seg_median=16, seg_sigma=0.6, seg_clip=(12, 80), contig_median=80,
+                               contig_sigma=0.5, contig_clip=(40, 400), genome_labels=50_000)

@@ -47,10 +47,11 @@ def test_cli_contig_list(tmp_path):
     _run_both(tmp_path, segs, contigs, ["-nthreads=3", "-gen=2", f"-contig_list={lst}"])
 
 
-def test_cli_fitting(tmp_path):
+def test_cli_fitting(tmp_path, monkeypatch):
     """OMPathFinder-style call (OMPathFinder.py:407-428): one compound segment map vs one sub-contig map, plus
     the KA-2 known answer of SURVEY.md section 8(c)."""
     _need_bins()
+    monkeypatch.setenv("SA_SERVER", "0")  # in-process here; the default (resident server) has its own test below
     seg = np.array([0, 5200, 9100, 20500, 31000, 33900, 47000, 47001], dtype=np.float64)
     contig = np.array([0, 5150, 9300, 15000, 20400, 31200, 34000, 46800, 46801], dtype=np.float64)
     _run_both(tmp_path / "ka2", {1: seg}, {1: contig}, ["-fitting", "-min_labs=0", "-gen=2"])
@@ -77,6 +78,133 @@ def test_cli_degenerate_shapes(tmp_path):
     _run_both(tmp_path / "loc", segs, contigs, cc.EDGE_FLAGS + ["-local", "-no_tip_aln"])
 
 
+def test_c1_gbm39_segments_vs_bspqi_assembly(tmp_path):
+    """BASELINE.json configs[0] (/root/reference/README.md:162-191): the shipped GBM39 amplicon segment
+    CMAP against a BspQI contig assembly -- 2,500 seeded synthetic contigs (seed 39) plus 6 noisy windows of the real
+    hg19 chr7 map around EGFR -- standard mode, every output file byte-identical to the unmodified reference binary."""
+    import os
+    _need_bins()
+    if not (cc.DATA / "hg19_BspQI.cmap.gz").exists():
+        pytest.skip("oracle/_ref/data not present")
+    seg_f, contigs = cc.make_c1()
+    (tmp_path / "in").mkdir()
+    synth.write_cmap(tmp_path / "in" / "contigs.cmap", contigs)
+    flags = cc.C1_FLAGS + [f"-nthreads={min(os.cpu_count() or 1, 16)}"]
+    r = cc.run_bin(cc.REF_BIN, tmp_path / "ref", seg_f, tmp_path / "in" / "contigs.cmap", flags)
+    n = cc.run_bin(cc.NEW_BIN, tmp_path / "new", seg_f, tmp_path / "in" / "contigs.cmap", flags)
+    assert r.returncode == 0 and n.returncode == 0, n.stderr[-2000:]
+    only_ref, only_new, diff, n_files = cc.compare_dirs(tmp_path / "ref", tmp_path / "new")
+    assert not only_ref and not only_new and not diff, (only_ref[:5], only_new[:5], diff[:5])
+    assert n_files >= 8, "C1 must produce real alignments of the GBM39 segments on the chr7 contigs"
+
+
+def test_c5_shaped_cohort_vs_reference(tmp_path, monkeypatch):
+    """A C5-shaped subsample (BASELINE.json configs[4]: cohort sweep of many short segments x many short contigs) at a
+    size where the cohort-scale host path takes its big-batch branches: > 100,000 pairs per tip-alignment round (pinned
+    pre-sizing, several post-processing workers splicing private bitmaps into the arena), stored matrices split into
+    many chunks (SA_STORE_BUDGET_CELLS), packed tracebacks -- byte-identical to the unmodified reference binary."""
+    import os
+    _need_bins()
+    segs, contigs = cc.make_c5_shaped()
+    seg_f, con_f = cc.write_case(tmp_path / "in", segs, contigs)
+    flags = cc.C5_FLAGS + [f"-nthreads={min(os.cpu_count() or 1, 16)}"]
+    r = cc.run_bin(cc.REF_BIN, tmp_path / "ref", seg_f, con_f, flags)
+    assert r.returncode == 0, r.stderr[-2000:]
+    monkeypatch.setenv("SA_STORE_BUDGET_CELLS", "4000000")
+    monkeypatch.setenv("SA_VERBOSE", "1")
+    n = cc.run_bin(cc.NEW_BIN, tmp_path / "new", seg_f, con_f, flags + ["-ngpus=1"])
+    assert n.returncode == 0, n.stderr[-2000:]
+    only_ref, only_new, diff, n_files = cc.compare_dirs(tmp_path / "ref", tmp_path / "new")
+    assert not only_ref and not only_new and not diff, (only_ref[:5], only_new[:5], diff[:5])
+    assert n_files > 300
+    rounds = [int(l.split()[2]) for l in n.stderr.splitlines() if l.strip().startswith("alignment round:")]
+    chunks = [l for l in n.stderr.splitlines() if "sa_align_batch chunk" in l]
+    assert max(rounds) > 100000, f"largest alignment round has {max(rounds)} pairs: the big-batch branches were not taken"
+    assert len(chunks) > 2 * len(rounds), "stored matrices were not chunked"
+
+
+@pytest.mark.parametrize("n_ctx", [2, 3])
+def test_sharded_engine_matches_reference(tmp_path, monkeypatch, n_ctx):
+    """The multi-GPU product path (Engine::shard / score / detect / align, host/main.cpp; reference fan-out
+    SegAligner/main.cpp:531-551, 575-602): problems sharded by index over `n_ctx` contexts.  Runs on whatever the box has:
+    with fewer than n_ctx GPUs the contexts share devices (SA_GPU_OVERSUBSCRIBE=1), which exercises exactly the same
+    host code.  Standard and detection runs, byte-identical to the unmodified reference binary."""
+    _need_bins()
+    monkeypatch.setenv("SA_GPU_OVERSUBSCRIBE", "1")
+    for name in ("standard_gen2", "detection"):
+        kwargs, flags = cc.CASES[name]
+        segs, contigs = cc.make_case(**kwargs)
+        seg_f, con_f = cc.write_case(tmp_path / name / "in", segs, contigs)
+        r = cc.run_bin(cc.REF_BIN, tmp_path / name / "ref", seg_f, con_f, flags)
+        n = cc.run_bin(cc.NEW_BIN, tmp_path / name / "new", seg_f, con_f, flags + [f"-ngpus={n_ctx}"])
+        assert r.returncode == 0 and n.returncode == 0, n.stderr[-2000:]
+        only_ref, only_new, diff, n_files = cc.compare_dirs(tmp_path / name / "ref", tmp_path / name / "new")
+        assert not only_ref and not only_new and not diff and n_files > 2, (only_ref[:5], only_new[:5], diff[:5])
+
+
+def test_fitting_calls_are_fast_by_default(tmp_path, monkeypatch):
+    """OMPathFinder.py:407-428 execs one `SegAligner -fitting` process per candidate path.  With NO environment set the
+    first such call leaves the resident server behind (private socket directory, peer credentials checked) and the
+    following calls are forwarded to it: 200 sequential calls must take < 1 s in total and write the same bytes as the
+    unmodified reference binary."""
+    import os
+    import subprocess
+    import time
+    _need_bins()
+    for k in ("SA_SERVER", "SA_SERVER_SOCKET", "SA_SERVER_IDLE"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("XDG_RUNTIME_DIR", str(tmp_path))  # keeps this test's server apart from any other
+    os.chmod(tmp_path, 0o700)
+    rng = np.random.default_rng(17)
+    g = synth.genome_positions(rng, 2000)
+    seg_f, con_f = cc.write_case(tmp_path / "in", {1: synth.window_map(g, 10, 9)}, {1: synth.noisy_contig(rng, g, 8, 14)})
+    flags = ["-fitting", "-min_labs=0", "-gen=2"]
+    ref = cc.run_bin(cc.REF_BIN, tmp_path / "ref", seg_f, con_f, flags)
+    assert ref.returncode == 0
+    try:
+        warm = cc.run_bin(cc.NEW_BIN, tmp_path / "warm", seg_f, con_f, flags)  # starts the server (CUDA start-up)
+        assert warm.returncode == 0, warm.stderr
+        assert (tmp_path / "segaligner_b200" / "server.sock").exists()
+        assert oct((tmp_path / "segaligner_b200").stat().st_mode & 0o777) == "0o700"
+        outs = [tmp_path / f"o{k}" for k in range(200)]
+        for o in outs:
+            o.mkdir()
+        t0 = time.perf_counter()
+        for o in outs:
+            rc = subprocess.call([str(cc.NEW_BIN), str(seg_f), str(con_f), f"-prefix={o}/SA"] + flags,
+                                 stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            assert rc == 0
+        dt = time.perf_counter() - t0
+        want = cc.dir_digest(tmp_path / "ref")
+        for o in outs:
+            assert cc.dir_digest(o) == want
+        assert dt < 1.0, f"200 fitting calls took {dt:.2f} s"
+        print(f"200 sequential -fitting calls: {dt:.3f} s ({dt / 200 * 1e3:.2f} ms per call)")
+    finally:
+        subprocess.run([str(cc.NEW_BIN), "--server-stop"], capture_output=True, timeout=60)
+
+
+def test_server_socket_is_not_trusted_blindly(tmp_path, monkeypatch):
+    """A socket directory that is not a private directory of this user (here: group/world accessible) must not be used:
+    the run then happens in-process and still succeeds with identical output."""
+    import os
+    _need_bins()
+    for k in ("SA_SERVER_SOCKET", "SA_SERVER_IDLE"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("SA_SERVER", "1")
+    monkeypatch.setenv("XDG_RUNTIME_DIR", str(tmp_path))
+    os.chmod(tmp_path, 0o700)
+    (tmp_path / "segaligner_b200").mkdir()
+    os.chmod(tmp_path / "segaligner_b200", 0o777)  # somebody else could have planted a socket here
+    seg = np.array([0, 5200, 9100, 20500, 31000, 33900, 47000, 47001], dtype=np.float64)
+    contig = np.array([0, 5150, 9300, 15000, 20400, 31200, 34000, 46800, 46801], dtype=np.float64)
+    seg_f, con_f = cc.write_case(tmp_path / "in", {1: seg}, {1: contig})
+    p = cc.run_bin(cc.NEW_BIN, tmp_path / "new", seg_f, con_f, ["-fitting", "-min_labs=0", "-gen=2"])
+    assert p.returncode == 0, p.stderr
+    assert not (tmp_path / "segaligner_b200" / "server.sock").exists(), "a server was started in an untrusted directory"
+    assert (tmp_path / "new" / "SA_1_1_fitting_aln.txt").read_text().splitlines()[1] == "#1+\t51069\tFalse"
+
+
 def test_cli_resident_server(tmp_path):
     """SA_SERVER=1: the first call leaves a server holding the CUDA context on a Unix socket; later calls are
     forwarded to it.  Outputs (files and stdout) must equal the in-process run; repeated fitting calls -- the
@@ -91,7 +219,7 @@ def test_cli_resident_server(tmp_path):
     contig = np.array([0, 5150, 9300, 15000, 20400, 31200, 34000, 46800, 46801], dtype=np.float64)
     seg_f, con_f = cc.write_case(tmp_path / "in", {1: seg}, {1: contig})
     flags = ["-fitting", "-min_labs=0", "-gen=2"]
-    direct = cc.run_bin(cc.NEW_BIN, tmp_path / "direct", seg_f, con_f, flags)
+    direct = cc.run_bin(cc.NEW_BIN, tmp_path / "direct", seg_f, con_f, flags, env=dict(os.environ, SA_SERVER="0"))
     assert direct.returncode == 0
     try:
         times = []

@@ -46,10 +46,11 @@ def upload(ctx, maps, probs, side):
     return ids
 
 
-@pytest.fixture(params=["bulk", "coop", "cluster"], autouse=True)
+@pytest.fixture(params=["bulk", "coop", "cluster"])
 def kernel_class(request, monkeypatch):
-    """Run every parity case three times: through the one-warp-per-problem kernel, the cooperative 8-warp CTA
-    wavefront and the 8-CTA x 16-warp thread-block-cluster wavefront (forced by absurdly low size-class thresholds)."""
+    """Run a parity case three times: through the one-warp-per-problem kernel, the cooperative 8-warp CTA wavefront and
+    the 8-CTA x 16-warp thread-block-cluster wavefront (forced by absurdly low size-class thresholds).  Requested only
+    by the tests whose result depends on the kernel shape (the powf / pruning-bound sweeps do not)."""
     monkeypatch.setenv("SA_COOP_ALPHA", "0" if request.param == "bulk" else "1e-9")
     monkeypatch.setenv("SA_NO_CLUSTER", "0" if request.param == "cluster" else "1")
     monkeypatch.setenv("SA_HUGE_MIN_CELLS", "0")
@@ -61,7 +62,7 @@ def bits(a):
 
 
 @pytest.mark.parametrize("gen", [1, 2])
-def test_fill_one_bit_exact(ctx, oracle, gen):
+def test_fill_one_bit_exact(ctx, oracle, gen, kernel_class):
     rng = np.random.default_rng(100 + gen)
     contigs, segs, cp, sp = build_sets(rng, oracle, 24, gen)
     cids = upload(ctx, contigs, cp, capi.SA_SIDE_CONTIG)
@@ -82,7 +83,7 @@ def test_fill_one_bit_exact(ctx, oracle, gen):
                 assert bits(res["score"]) == bits(So[st])
 
 
-def test_score_and_align_batch(ctx, oracle):
+def test_score_and_align_batch(ctx, oracle, kernel_class):
     rng = np.random.default_rng(7)
     gen = 2
     contigs, segs, cp, sp = build_sets(rng, oracle, 40, gen, max_nb=300, max_nx=120)
@@ -112,7 +113,7 @@ def test_score_and_align_batch(ctx, oracle):
             assert bits(ares["score"][n]) == bits(So[st])
 
 
-def test_used_label_masks_in_batch(ctx, oracle):
+def test_used_label_masks_in_batch(ctx, oracle, kernel_class):
     rng = np.random.default_rng(11)
     contigs, segs, cp, sp = build_sets(rng, oracle, 12, 1, max_nb=120, max_nx=60)
     cids = upload(ctx, contigs, cp, capi.SA_SIDE_CONTIG)
@@ -141,7 +142,7 @@ def test_used_label_masks_in_batch(ctx, oracle):
         assert not set(pj[sl][:-1].tolist()) & set(used_sets[k])
 
 
-def test_packed_alignment_output_equals_capacity_form(ctx, oracle):
+def test_packed_alignment_output_equals_capacity_form(ctx, oracle, kernel_class):
     """sa_align_batch_packed (what the executable uses: tracebacks packed by a device prefix sum, pinned buffers owned by
     the context) against sa_align_batch with caller-provided capacity offsets, with and without used-label bitmaps."""
     rng = np.random.default_rng(23)
@@ -192,6 +193,39 @@ def test_powf12_device_matches_host_libm(ctx, oracle):
     assert np.array_equal(bits(fast[samp]), bits(ref))
 
 
+def test_powf12_device_exhaustive(ctx, oracle):
+    """EVERY non-negative float bit pattern (zero, subnormals, all normals, +inf, the first NaNs) through both device
+    paths of powf(x, 1.2f) -- the table replay with its out-of-domain patch, and the generic path -- against the host libm
+    powf the reference links (SegAligner.cpp:88), bit for bit: 2^31 device evaluations per path, compared on the host by
+    oracle/sa_oracle.c:sao_powf12_cmp_range on all cores."""
+    import ctypes as C
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    cmp_ = oracle.lib.sao_powf12_cmp_range
+    cmp_.restype = C.c_longlong
+    cmp_.argtypes = [C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+    n_thr = max(1, min(os.cpu_count() or 1, 32))
+    step = 1 << 27
+    end = 0x7f800010
+    bad_total, first = 0, None
+    with ThreadPoolExecutor(n_thr) as pool:
+        for lo in range(0, end, step):
+            hi = min(lo + step, end)
+            fast, gen = ctx.powf12_range(lo, hi)
+            cuts = np.linspace(lo, hi, n_thr + 1).astype(np.int64)
+
+            def part(t):
+                a, b = int(cuts[t]), int(cuts[t + 1])
+                fb = C.c_uint(0)
+                n = cmp_(a, b, fast[a - lo:].ctypes.data, gen[a - lo:].ctypes.data, C.byref(fb))
+                return n, fb.value
+            for n, fb in pool.map(part, range(n_thr)):
+                if n and first is None:
+                    first = fb
+                bad_total += n
+    assert bad_total == 0, f"{bad_total} bit patterns differ from host powf; first 0x{first:08x}"
+
+
 def test_prune_bound_holds_for_every_float(ctx):
     """The fill kernel prunes candidates with an fp32 lower bound of powf(d, 1.2f) (two MUFU approximations); the
     pruning is exact only if that bound never exceeds the bit-exact replay.  Checked for EVERY non-negative float
@@ -208,7 +242,7 @@ def test_prune_bound_holds_for_every_float(ctx):
     assert worst > 1.0  # strict slack everywhere (the margin PRUNE_C is 2^-14 in the log2 domain)
 
 
-def test_pruning_statistics_and_tie_rescans(ctx, oracle):
+def test_pruning_statistics_and_tie_rescans(ctx, oracle, kernel_class):
     """The fill kernel replays powf bit-exactly once per cell and rescans a cell exactly when the winner is not
     strictly ahead of every other candidate's upper bound.  Integer-valued maps make exact ties common: the rescan path
     must run (n_rescans > 0), about one replay per cell must be executed, and results must still equal the oracle."""
