@@ -148,7 +148,7 @@ def make_c1(n_contigs=2500, seed=39):
     return DATA / "GBM39_amplicon1_graph_BSPQI.cmap", contigs
 
 
-def make_c5_shaped(n_segs=300, n_contigs=320, seed=5):
+def make_c5_shaped(n_segs=300, n_contigs=560, seed=5):
     """A C5-shaped subsample (cohort sweep: many short graph segments x many short genome-wide DLE1 contigs) of the
     generator tests/perf/c5_cohort.py uses at full size, small enough for the reference to finish in about a minute."""
     return synth.make_workload(seed, n_segs, n_contigs, seg_median=16, seg_sigma=0.6, seg_clip=(12, 80), contig_median=80,

@@ -107,7 +107,7 @@ def test_c5_shaped_cohort_vs_reference(tmp_path, monkeypatch):
     _need_bins()
     segs, contigs = cc.make_c5_shaped()
     seg_f, con_f = cc.write_case(tmp_path / "in", segs, contigs)
-    flags = cc.C5_FLAGS + [f"-nthreads={min(os.cpu_count() or 1, 16)}"]
+    flags = cc.C5_FLAGS + [f"-nthreads={min(os.cpu_count() or 1, 32)}"]
     r = cc.run_bin(cc.REF_BIN, tmp_path / "ref", seg_f, con_f, flags)
     assert r.returncode == 0, r.stderr[-2000:]
     monkeypatch.setenv("SA_STORE_BUDGET_CELLS", "4000000")
