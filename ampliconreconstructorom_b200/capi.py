@@ -41,7 +41,7 @@ class Timing(C.Structure):
 EXPORTS = [
     "sa_device_count", "sa_ctx_create", "sa_ctx_destroy", "sa_last_error", "sa_set_maps", "sa_score_batch",
     "sa_plan_create", "sa_plan_destroy", "sa_plan_score", "sa_plan_results", "sa_plan_info", "sa_sync", "sa_align_batch", "sa_align_batch_packed", "sa_detect_batch", "sa_fill_one", "sa_powf12",
-    "sa_powf12_range", "sa_check_prune_bound", "sa_get_timing", "sa_get_prune_stats", "sa_measure_fp64_peak", "sa_event_record", "sa_event_elapsed_ms",
+    "sa_powf12_range", "sa_check_prune_bound", "sa_get_timing", "sa_get_prune_stats", "sa_measure_fp64_peak", "sa_measure_mufu_peak", "sa_get_traffic", "sa_event_record", "sa_event_elapsed_ms",
     "sa_host_non_collapse_probs", "sa_host_make_reverse", "sa_host_parse_cmap", "sa_host_score_thresholds",
     "sa_host_format_float", "sa_digest",
 ]
@@ -84,6 +84,8 @@ def load_library() -> C.CDLL:
     lib.sa_get_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.sa_get_prune_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.sa_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.sa_measure_mufu_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.sa_get_traffic.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.sa_digest.argtypes = [vp, vp, i64, C.c_char_p, i32, i32, i64, vp, C.POINTER(i64)]
     lib.sa_event_record.argtypes = [vp, i32]
     lib.sa_event_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -412,4 +414,15 @@ class Context:
     def fp64_peak(self) -> float:
         v = C.c_double()
         self._check(self.lib.sa_measure_fp64_peak(self.h, C.byref(v)), "sa_measure_fp64_peak")
+        return v.value
+
+    def traffic(self):
+        """(h2d bytes, d2h bytes) copied by this context so far."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.sa_get_traffic(self.h, C.byref(a), C.byref(b)), "sa_get_traffic")
+        return a.value, b.value
+
+    def mufu_peak(self) -> float:
+        v = C.c_double()
+        self._check(self.lib.sa_measure_mufu_peak(self.h, C.byref(v)), "sa_measure_mufu_peak")
         return v.value

@@ -749,7 +749,17 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
         pt.lap("phase 4 tip alignment");
     }
     printf("elapsed seconds for run %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
-    if (getenv("SA_VERBOSE")) fprintf(stderr, "SegAligner(b200): wall %.3f s on %d GPU(s)\n", wall_now() - w0, (int)eng.ctx.size());
+    if (getenv("SA_VERBOSE")) {
+        uint64_t h2d = 0, d2h = 0;
+        for (sa_ctx *c : eng.ctx) {
+            uint64_t a = 0, b = 0;
+            sa_get_traffic(c, &a, &b);
+            h2d += a;
+            d2h += b;
+        }
+        fprintf(stderr, "SegAligner(b200): copied H2D %llu bytes, D2H %llu bytes\n", (unsigned long long)h2d, (unsigned long long)d2h);
+        fprintf(stderr, "SegAligner(b200): wall %.3f s on %d GPU(s)\n", wall_now() - w0, (int)eng.ctx.size());
+    }
     fflush(stdout);
     fflush(stderr);
     if (!keep_open) eng.close();  // orderly teardown: abandoning the context only moves the cost to the next start

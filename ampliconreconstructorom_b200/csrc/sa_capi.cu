@@ -114,7 +114,15 @@ struct sa_ctx {
     HostBuf h_res, h_start, h_pj, h_pq, h_ps;  // packed alignment output of the last sa_align_batch* call
     sa_timing timing = {0, 0, 0, 0};
     size_t store_budget_cells = 0;  // max cells of stored matrices per chunk
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes moved by this context since it was created (sa_get_traffic)
 };
+
+// every host<->device copy of the library goes through here so that the traffic of a run can be reported exactly
+static inline cudaError_t cpy(sa_ctx *ctx, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+    if (kind == cudaMemcpyHostToDevice) ctx->h2d_bytes += bytes;
+    else if (kind == cudaMemcpyDeviceToHost) ctx->d2h_bytes += bytes;
+    return cudaMemcpyAsync(dst, src, bytes, kind, st);
+}
 
 struct sa_plan;
 
@@ -437,12 +445,12 @@ int sa_set_maps(sa_ctx *ctx, int side, int32_t n_maps, const int64_t *off, const
     CU(S.d_prob.reserve(sizeof(float) * (size_t)std::max<int64_t>(n_lab, 1)));
     CU(S.d_ops.reserve(sizeof(LabelOps) * ops.size()));
     CU(S.d_off.reserve(sizeof(int64_t) * (size_t)(n_maps + 1)));
-    CU(cudaMemcpyAsync(S.d_pos.p, pos, sizeof(float) * (size_t)n_pos, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cpy(ctx, S.d_pos.p, pos, sizeof(float) * (size_t)n_pos, cudaMemcpyHostToDevice, ctx->stream));
     if (n_lab > 0) {
-        CU(cudaMemcpyAsync(S.d_prob.p, prob, sizeof(float) * (size_t)n_lab, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(S.d_ops.p, ops.data(), sizeof(LabelOps) * (size_t)n_lab, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cpy(ctx, S.d_prob.p, prob, sizeof(float) * (size_t)n_lab, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cpy(ctx, S.d_ops.p, ops.data(), sizeof(LabelOps) * (size_t)n_lab, cudaMemcpyHostToDevice, ctx->stream));
     }
-    CU(cudaMemcpyAsync(S.d_off.p, off, sizeof(int64_t) * (size_t)(n_maps + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cpy(ctx, S.d_off.p, off, sizeof(int64_t) * (size_t)(n_maps + 1), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SA_OK;
 }
@@ -461,9 +469,9 @@ int sa_plan_create(sa_ctx *ctx, const sa_problem *problems, int64_t n, sa_plan *
     if (e == cudaSuccess) e = pl->d_order.reserve(sizeof(int32_t) * (size_t)n);
     if (e == cudaSuccess) e = pl->d_results.reserve(sizeof(sa_result) * (size_t)n);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(pl->d_problems.p, problems, sizeof(sa_problem) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+        e = cpy(ctx, pl->d_problems.p, problems, sizeof(sa_problem) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(pl->d_order.p, pl->plan.order.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+        e = cpy(ctx, pl->d_order.p, pl->plan.order.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         pl->d_problems.release();
@@ -508,7 +516,7 @@ int sa_plan_score(sa_ctx *ctx, sa_plan *pl, const sa_mode *mode) {
 int sa_plan_results(sa_ctx *ctx, sa_plan *pl, sa_result *results) {
     if (!ctx || !pl || !results) return SA_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    CU(cudaMemcpyAsync(results, pl->d_results.p, sizeof(sa_result) * (size_t)pl->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cpy(ctx, results, pl->d_results.p, sizeof(sa_result) * (size_t)pl->n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SA_OK;
 }
@@ -557,7 +565,7 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
             return fail(ctx, SA_EINVAL, "used-label bitmaps exceed 2^31 words");
         const size_t bytes = sizeof(uint32_t) * (size_t)(used_words_per_slot * n_used_slots);
         CU(ctx->d_used.reserve(bytes));
-        CU(cudaMemcpyAsync(ctx->d_used.p, used_bits, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cpy(ctx, ctx->d_used.p, used_bits, bytes, cudaMemcpyHostToDevice, ctx->stream));
         P.used_bits = ctx->d_used.as<uint32_t>();
         P.used_words_per_slot = used_words_per_slot;
     }
@@ -603,9 +611,9 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
         if (unbanded) CU(ctx->d_prev32.reserve(sizeof(int32_t) * (size_t)cells));
         else CU(ctx->d_code.reserve((size_t)cells));
         CU(ctx->d_path_off.reserve(sizeof(int64_t) * (size_t)(m + 1)));
-        CU(cudaMemcpyAsync(ctx->d_problems.p, problems + k0, sizeof(sa_problem) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_order.p, order.data(), sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_cell_off.p, cell_off.data(), sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cpy(ctx, ctx->d_problems.p, problems + k0, sizeof(sa_problem) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cpy(ctx, ctx->d_order.p, order.data(), sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cpy(ctx, ctx->d_cell_off.p, cell_off.data(), sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
         P.problems = ctx->d_problems.as<sa_problem>();
         P.order = ctx->d_order.as<int32_t>();
         P.cell_off = ctx->d_cell_off.as<int64_t>();
@@ -652,7 +660,7 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
         if (exclusive_scan_i64(d_start, m + 1, ctx->d_tmp2.p, ctx->d_tmp2.cap, nullptr, ctx->stream))
             return fail(ctx, SA_ECUDA, "prefix sum of the path lengths failed");
         int64_t n_path = 0;
-        CU(cudaMemcpyAsync(&n_path, d_start + m, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cpy(ctx, &n_path, d_start + m, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         // pass 2: write the paths packed
         CU(ctx->d_path_j.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(n_path, 1)));
@@ -670,12 +678,12 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
         launch_traceback(T, ctx->stream);
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-        CU(cudaMemcpyAsync(ctx->h_res.as<sa_result>() + k0, ctx->d_results.p, sizeof(sa_result) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->h_start.as<int64_t>() + k0, d_start, sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cpy(ctx, ctx->h_res.as<sa_result>() + k0, ctx->d_results.p, sizeof(sa_result) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cpy(ctx, ctx->h_start.as<int64_t>() + k0, d_start, sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyDeviceToHost, ctx->stream));
         if (n_path > 0) {
-            CU(cudaMemcpyAsync(ctx->h_pj.as<int32_t>() + total, ctx->d_path_j.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaMemcpyAsync(ctx->h_pq.as<int32_t>() + total, ctx->d_path_q.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaMemcpyAsync(ctx->h_ps.as<float>() + total, ctx->d_path_s.p, sizeof(float) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cpy(ctx, ctx->h_pj.as<int32_t>() + total, ctx->d_path_j.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cpy(ctx, ctx->h_pq.as<int32_t>() + total, ctx->d_path_q.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cpy(ctx, ctx->h_ps.as<float>() + total, ctx->d_path_s.p, sizeof(float) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
         }
         CU(cudaStreamSynchronize(ctx->stream));
         if (total > 0) {  // chunk-local start offsets -> global
@@ -837,12 +845,12 @@ int sa_detect_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
         CU(ctx->d_path_s.reserve(sizeof(float) * (size_t)n_sc));           // reused: scores_out
         CU(ctx->d_path_j.reserve(sizeof(int32_t) * (size_t)m));            // reused: n_want
         CU(ctx->d_path_q.reserve(sizeof(int32_t) * (size_t)m));            // reused: n_got
-        CU(cudaMemcpyAsync(ctx->d_problems.p, problems + k0, sizeof(sa_problem) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_order.p, plan.order.data(), sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_cell_off.p, cell_off.data(), sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_row_off.p, row_off.data(), sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_path_off.p, soff.data(), sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_path_j.p, n_want + k0, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cpy(ctx, ctx->d_problems.p, problems + k0, sizeof(sa_problem) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cpy(ctx, ctx->d_order.p, plan.order.data(), sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cpy(ctx, ctx->d_cell_off.p, cell_off.data(), sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cpy(ctx, ctx->d_row_off.p, row_off.data(), sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cpy(ctx, ctx->d_path_off.p, soff.data(), sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cpy(ctx, ctx->d_path_j.p, n_want + k0, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
         P.problems = ctx->d_problems.as<sa_problem>();
         P.cell_off = ctx->d_cell_off.as<int64_t>();
         P.row_off = ctx->d_row_off.as<int64_t>();
@@ -885,8 +893,8 @@ int sa_detect_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev[2], ctx->stream));
         if (soff[(size_t)m] > 0)
-            CU(cudaMemcpyAsync(scores_out + scores_off[k0], ctx->d_path_s.p, sizeof(float) * (size_t)soff[(size_t)m], cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(n_got + k0, ctx->d_path_q.p, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cpy(ctx, scores_out + scores_off[k0], ctx->d_path_s.p, sizeof(float) * (size_t)soff[(size_t)m], cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cpy(ctx, n_got + k0, ctx->d_path_q.p, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
@@ -908,10 +916,10 @@ int sa_powf12(sa_ctx *ctx, const float *x, int64_t n, float *out, int use_fast_p
     CU(cudaSetDevice(ctx->device));
     CU(ctx->d_tmp0.reserve(sizeof(float) * (size_t)n));
     CU(ctx->d_tmp1.reserve(sizeof(float) * (size_t)n));
-    CU(cudaMemcpyAsync(ctx->d_tmp0.p, x, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cpy(ctx, ctx->d_tmp0.p, x, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     launch_powf12(ctx->d_tmp0.as<float>(), n, ctx->d_tmp1.as<float>(), use_fast_path, ctx->stream);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out, ctx->d_tmp1.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cpy(ctx, out, ctx->d_tmp1.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SA_OK;
 }
@@ -925,8 +933,8 @@ int sa_powf12_range(sa_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, float *out_
     CU(ctx->d_tmp1.reserve(sizeof(float) * n));
     launch_powf12_range(lo_bits, hi_bits, ctx->d_tmp0.as<float>(), ctx->d_tmp1.as<float>(), ctx->stream);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out_fast, ctx->d_tmp0.p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(out_generic, ctx->d_tmp1.p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cpy(ctx, out_fast, ctx->d_tmp0.p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cpy(ctx, out_generic, ctx->d_tmp1.p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SA_OK;
 }
@@ -942,12 +950,12 @@ int sa_check_prune_bound(sa_ctx *ctx, uint32_t lo_bits, uint32_t hi_bits, uint64
     float *d_r = reinterpret_cast<float *>(d_n + 1);
     const float two = 2.0f;
     CU(cudaMemsetAsync(d_n, 0, 8, ctx->stream));
-    CU(cudaMemcpyAsync(d_r, &two, 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cpy(ctx, d_r, &two, 4, cudaMemcpyHostToDevice, ctx->stream));
     launch_prune_bound(lo_bits, hi_bits, d_n, d_r, ctx->stream);
     CU(cudaGetLastError());
     unsigned long long h_n = 0;
-    CU(cudaMemcpyAsync(&h_n, d_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(min_ratio, d_r, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cpy(ctx, &h_n, d_n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cpy(ctx, min_ratio, d_r, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     *n_violations = h_n;
     return SA_OK;
@@ -959,7 +967,7 @@ int sa_get_prune_stats(sa_ctx *ctx, uint64_t *n_replays, uint64_t *n_rescans) {
     if (!ctx->d_counter.p) return SA_OK;
     CU(cudaSetDevice(ctx->device));
     unsigned long long h[2] = {0, 0};
-    CU(cudaMemcpyAsync(h, ctx->d_counter.as<unsigned long long>() + 4, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cpy(ctx, h, ctx->d_counter.as<unsigned long long>() + 4, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     *n_replays = h[0];
     *n_rescans = h[1];
@@ -989,7 +997,7 @@ int sa_digest(sa_ctx *ctx, const char *seq, int64_t n, const char *motif, int32_
     const int64_t dev_cap = std::max<int64_t>(cap, 1);
     CU(ctx->d_path_s.reserve(sizeof(long long) * (size_t)dev_cap));
     CU(cudaMemsetAsync(reinterpret_cast<char *>(ctx->d_S.p) + ((size_t)n / 16) * 16, 0, padded - ((size_t)n / 16) * 16, ctx->stream));
-    if (n > 0) CU(cudaMemcpyAsync(ctx->d_S.p, seq, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0) CU(cpy(ctx, ctx->d_S.p, seq, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_tmp2.p, 0, 64, ctx->stream));
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = sa_digest_run(ctx->stream, ctx->n_sms, ctx->d_S.as<uint8_t>(), n, motif, motif_len, offset,
@@ -998,7 +1006,7 @@ int sa_digest(sa_ctx *ctx, const char *seq, int64_t n, const char *motif, int32_
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     unsigned long long cnt = 0;
-    CU(cudaMemcpyAsync(&cnt, ctx->d_tmp2.p, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cpy(ctx, &cnt, ctx->d_tmp2.p, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
@@ -1051,6 +1059,35 @@ int sa_measure_fp64_peak(sa_ctx *ctx, double *dfma_per_s) {
     }
     CU(cudaGetLastError());
     *dfma_per_s = best;
+    return SA_OK;
+}
+
+int sa_get_traffic(sa_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
+    if (!ctx || !h2d_bytes || !d2h_bytes) return SA_EINVAL;
+    *h2d_bytes = ctx->h2d_bytes;
+    *d2h_bytes = ctx->d2h_bytes;
+    return SA_OK;
+}
+
+int sa_measure_mufu_peak(sa_ctx *ctx, double *mufu_per_s) {
+    if (!ctx || !mufu_per_s) return SA_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->d_tmp2.reserve(64));
+    const int iters = 1024, ctas = ctx->n_sms * 8;
+    launch_mufu_peak(ctx->d_tmp2.as<float>(), 16, ctas, ctx->stream);  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+        launch_mufu_peak(ctx->d_tmp2.as<float>(), iters, ctas, ctx->stream);
+        CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CU(cudaEventSynchronize(ctx->ev[1]));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        const double inst = (double)ctas * 256.0 * iters * 64.0;  // per thread: iters x 4 x (8 lg2 + 8 ex2)
+        best = std::max(best, inst / (ms * 1e-3));
+    }
+    CU(cudaGetLastError());
+    *mufu_per_s = best;
     return SA_OK;
 }
 

@@ -1320,6 +1320,26 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *sink, int iters)
     if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
 }
 
+// Sustained MUFU (XU pipe) issue rate: 8 independent lg2/ex2 chains per thread, 1024 threads per SM.
+__global__ void __launch_bounds__(256) mufu_peak_kernel(float *sink, int iters) {
+    float a[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) a[u] = 1.5f + threadIdx.x * 1e-3f + u;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(a[u]));
+#pragma unroll
+            for (int u = 0; u < 8; u++) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[u]));
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int u = 0; u < 8; u++) s += a[u];
+    if (s == 123.456f) sink[0] = s;  // never true; keeps the chains alive
+}
+
 // dynamic shared memory of a fill CTA with `wpc` warps: table region + mirrored ring + row operands
 static size_t fill_dyn_smem(int wpc, bool store = true) {
     return TAB_SMEM_BYTES + (size_t)wpc * (2 * LB * RING_W + 2 * LB * 32) * sizeof(float) +
@@ -1405,6 +1425,9 @@ void launch_prune_bound(uint32_t lo, uint32_t hi, unsigned long long *n_viol, fl
 }
 void launch_dfma_peak(double *sink, int iters, int n_ctas, cudaStream_t st) {
     dfma_peak_kernel<<<n_ctas, 256, 0, st>>>(sink, iters);
+}
+void launch_mufu_peak(float *sink, int iters, int n_ctas, cudaStream_t st) {
+    mufu_peak_kernel<<<n_ctas, 256, 0, st>>>(sink, iters);
 }
 int max_clusters() {
     cudaLaunchConfig_t cfg = {};

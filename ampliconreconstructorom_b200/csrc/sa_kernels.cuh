@@ -94,6 +94,7 @@ int exclusive_scan_i64(int64_t *d_vals, int64_t n_plus_1, void *d_tmp, size_t tm
 void launch_powf12(const float *x, long long n, float *out, int fast, cudaStream_t st);
 void launch_powf12_range(uint32_t lo, uint32_t hi, float *out_fast, float *out_generic, cudaStream_t st);
 void launch_prune_bound(uint32_t lo, uint32_t hi, unsigned long long *n_viol, float *min_ratio, cudaStream_t st);
+void launch_mufu_peak(float *sink, int iters, int n_ctas, cudaStream_t st);
 void launch_dfma_peak(double *sink, int iters, int n_ctas, cudaStream_t st);
 int fill_ctas_per_sm();
 void fill_powf_constants(double *pk);

@@ -149,8 +149,17 @@ int sa_get_timing(sa_ctx *ctx, sa_timing *t);
  * n_replays = bit-exact powf replays (about one per cell), n_rescans = cells rescanned exactly after a (near-)tie. */
 int sa_get_prune_stats(sa_ctx *ctx, uint64_t *n_replays, uint64_t *n_rescans);
 
+/* Bytes this context has copied host->device and device->host since sa_ctx_create (every copy the library makes is
+ * on the scoring / alignment / detection paths is counted: maps, label operand tables, problem lists, bitmaps, results,
+ * packed tracebacks; the sa_fill_one and sa_digest helpers are not). */
+int sa_get_traffic(sa_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
+
 /* Microbenchmark: sustained fp64 FMA issue rate (DFMA instructions/s, whole GPU) used as roofline peak. */
 int sa_measure_fp64_peak(sa_ctx *ctx, double *dfma_per_s);
+/* Microbenchmark: sustained MUFU (lg2/ex2, the XU pipe) issue rate, thread-instructions/s over the whole GPU.  The
+ * pruning fill kernel spends two MUFU per predecessor candidate (its fp32 score bound), which makes the XU pipe -- not
+ * fp64 issue -- the binding resource of the executed work; bench.py reports the kernel against this peak. */
+int sa_measure_mufu_peak(sa_ctx *ctx, double *mufu_per_s);
 
 /* ---- host-side (CPU) preparation helpers: the executable's own code behind extern "C" -------------------------
  * None of these is on the DP hot path; they exist so that every caller prepares inputs identically.
