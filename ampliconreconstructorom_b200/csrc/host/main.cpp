@@ -299,6 +299,65 @@ struct Engine {
             if (rc) die(ctx[(size_t)g], "sa_align_batch_packed", rc);
         });
     }
+
+    // Device-resident alignment loop (sa_align_rounds): every round of every pair in one call per GPU.  out.nr(k) = number
+    // of rounds of pair k (-1: the pair did not fit the device scratch, the caller runs it through align()).
+    struct RoundsOut {
+        std::vector<sa_rounds_out> ro;  // per GPU
+        std::vector<int32_t> gpu_of;    // per pair (multi-GPU only)
+        std::vector<int64_t> local_of;
+        int max_alns = 0;
+        int nr(size_t k) const {
+            const size_t g = gpu_of.empty() ? 0 : (size_t)gpu_of[k];
+            const size_t l = gpu_of.empty() ? k : (size_t)local_of[k];
+            return ro[g].n_rounds[l];
+        }
+        struct View {
+            const sa_round *rec;
+            const int32_t *pj, *pq;
+            const float *ps;
+        };
+        View get(size_t k, int r) const {
+            const size_t g = gpu_of.empty() ? 0 : (size_t)gpu_of[k];
+            const size_t l = gpu_of.empty() ? k : (size_t)local_of[k];
+            const sa_rounds_out &o = ro[g];
+            const sa_round *rec = o.rounds + l * (size_t)max_alns + (size_t)r;
+            return View{rec, o.path_j + rec->path_off, o.path_q + rec->path_off, o.path_s + rec->path_off};
+        }
+    };
+    void align_rounds(const sa_mode &mode, const std::vector<sa_problem> &pr, const std::vector<float> &thr, int max_alns,
+                      const std::vector<uint32_t> &arena, RoundsOut &out) {
+        const size_t n = pr.size(), G = ctx.size();
+        out.ro.assign(G, sa_rounds_out{});
+        out.gpu_of.clear();
+        out.local_of.clear();
+        out.max_alns = max_alns;
+        if (n == 0) return;
+        const uint32_t *bits = arena.empty() ? nullptr : arena.data();
+        const int64_t n_words = (int64_t)arena.size();
+        if (G == 1) {
+            int rc = sa_align_rounds(ctx[0], &mode, pr.data(), (int64_t)n, thr.data(), max_alns, bits, 1, n_words, &out.ro[0]);
+            if (rc) die(ctx[0], "sa_align_rounds", rc);
+            return;
+        }
+        auto sh = shard(pr);
+        out.gpu_of.resize(n);
+        out.local_of.resize(n);
+        parallel([&](int g) {
+            const auto &idx = sh[(size_t)g];
+            if (idx.empty()) return;
+            std::vector<sa_problem> p(idx.size());
+            std::vector<float> t(idx.size());
+            for (size_t k = 0; k < idx.size(); k++) {
+                p[k] = pr[(size_t)idx[k]];
+                t[k] = thr[(size_t)idx[k]];
+                out.gpu_of[(size_t)idx[k]] = g;
+                out.local_of[(size_t)idx[k]] = (int64_t)k;
+            }
+            int rc = sa_align_rounds(ctx[(size_t)g], &mode, p.data(), (int64_t)p.size(), t.data(), max_alns, bits, 1, n_words, &out.ro[(size_t)g]);
+            if (rc) die(ctx[(size_t)g], "sa_align_rounds", rc);
+        });
+    }
 };
 
 using Bitmap = std::vector<uint32_t>;
@@ -365,6 +424,124 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
     mode.lookback = o.lookback;
     mode.swap_b_x = o.swap_b_x ? 1 : 0;
 
+    // compute_partial_score_threshold (SegAligner.cpp:23-36) on a flat path (end -> start): max of the two, main.cpp:290
+    auto partial_thresh = [&](const PairState &p, int len, const int32_t *pj) -> float {
+        const float *contig = contigs.map(p.c);
+        const int contig_size = contigs.size(p.c);
+        const int first_lab = pj[len - 1], last_lab = pj[0];
+        const int aln_span_labs = last_lab - first_lab + 1;
+        const float tot_labs = (float)(contig_size - 1);
+        const float by_lab = p.thr * (aln_span_labs / tot_labs);
+        const float aln_span_bases = contig[last_lab] - contig[first_lab];
+        const float by_len = p.thr * (aln_span_bases / contig[contig_size - 1]);
+        return fmaxf(by_lab, by_len);
+    };
+    // An ACCEPTED alignment (p.count already incremented): the tip / length / score filters of main.cpp:303-325, the file,
+    // and the labels of the written alignment (SAHelper.cpp:115).
+    auto emit = [&](const PairState &p, int len, const int32_t *pj, const int32_t *pq, const float *ps, std::vector<AlnEntry> &aln,
+                    std::vector<std::pair<int, int>> &disc) {
+        if (tip_aln) {  // must touch a contig end (:303-308)
+            const size_t last_lab_gap = (size_t)(contigs.size(p.c) - 2) - (size_t)pj[0];
+            if (last_lab_gap > 3 && pj[len - 1] > 2) return;
+        }
+        if (len < min_tip_aln_labels || (!tip_aln && len < min_aln_labels)) return;
+        aln.resize((size_t)len);
+        for (int t = 0; t < len; t++) aln[(size_t)t] = AlnEntry{pj[t], pq[t], ps[t]};
+        const float mean = aln[0].s / (float)(aln.size() - 1);
+        const float median = aln_median(aln);
+        if (aln.size() < 5) {
+            const float min_score = aln_min(aln);
+            if (mean < 9400 || median < 9400 || min_score < 9200) return;
+        } else if (mean < mean_thresh || median < med_thresh) {
+            return;
+        }
+        const int x = segs.ids[(size_t)p.s];
+        const int contig_id = contigs.ids[(size_t)p.c];
+        std::string seg_id = std::to_string(x < 0 ? -x : x);
+        if (x < 0) seg_id += "_r";
+        const std::string outname = o.sample_prefix + "_" + std::to_string(contig_id) + "_" + seg_id + "_" + std::to_string(p.count) +
+                                    (tip_aln ? "_tip" : "") + "_aln.txt";
+        print_alignment(outname, aln, contig_id, x, segs.size(p.s), p.curr_best);
+        for (auto &e : aln) disc.emplace_back(p.c, e.j);
+    };
+
+    // ---- device-resident loop: every round of every pair in ONE call per GPU (sa_align_rounds); the host replays the
+    // bookkeeping on the returned rounds to apply the filters and write the files.  Semi-global, banded, unswapped runs only
+    // (-local / -detection / -nl keep the batched rounds below); pairs too large for the device scratch come back as -1.
+    bool use_rounds = !o.local_aln && !o.swap_b_x && o.lookback == 6 && !st.empty();
+    if (const char *e = getenv("SA_NO_ROUNDS")) use_rounds = use_rounds && atoi(e) == 0;
+    for (int sidx = 0; use_rounds && sidx < segs.n_maps(); sidx++) use_rounds = segs.labels(sidx) >= 2;
+    if (use_rounds) {
+        std::vector<sa_problem> rp(st.size());
+        std::vector<float> rthr(st.size());
+        for (size_t k = 0; k < st.size(); k++) {
+            rp[k] = sa_problem{st[k].c, st[k].s, (int32_t)st[k].used_off, 0};
+            rthr[k] = st[k].thr;
+        }
+        const double t_r0 = wall_now();
+        Engine::RoundsOut ro;
+        eng.align_rounds(mode, rp, rthr, max_alns, arena, ro);
+        const double t_r1 = wall_now();
+        const size_t n_pairs = st.size();
+        const int n_workers = (int)std::max<size_t>(1, std::min<size_t>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u),
+                                                                        n_pairs / 50000 + 1));
+        std::vector<std::vector<std::pair<int, int>>> disc((size_t)n_workers);
+        std::vector<int> bad((size_t)n_workers, 0);
+        size_t n_fallback = 0;
+        auto work = [&](int wi) {
+            std::vector<AlnEntry> aln;
+            const size_t lo = n_pairs * (size_t)wi / (size_t)n_workers, hi = n_pairs * ((size_t)wi + 1) / (size_t)n_workers;
+            for (size_t k = lo; k < hi; k++) {
+                PairState &p = st[k];
+                const int nr = ro.nr(k);
+                if (nr < 0) continue;  // left to the batched rounds below
+                p.live = false;
+                bool more = p.curr_best >= p.exp_thresh && p.count < max_alns;  // main.cpp:268 (false for a NaN threshold)
+                int r = 0;
+                for (; more && r < nr; r++) {
+                    const Engine::RoundsOut::View v = ro.get(k, r);
+                    const int len = v.rec->path_len;
+                    if (len <= 0) {  // no backtrack start (cannot happen with >= 1 label each): the device stopped here too
+                        more = false;
+                        r++;
+                        break;
+                    }
+                    p.exp_thresh = partial_thresh(p, len, v.pj);
+                    p.curr_best = v.rec->score;
+                    if (!(p.curr_best > p.exp_thresh)) {  // not accepted: the loop ends (equality would spin in the reference)
+                        more = false;
+                        r++;
+                        break;
+                    }
+                    p.count += 1;
+                    emit(p, len, v.pj, v.pq, v.ps, aln, disc[(size_t)wi]);
+                    more = p.count < max_alns;
+                }
+                if (more || r != nr) bad[(size_t)wi]++;  // the device loop and this replay must agree on the number of rounds
+            }
+        };
+        if (n_workers == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int wi = 0; wi < n_workers; wi++) th.emplace_back(work, wi);
+            for (auto &t : th) t.join();
+        }
+        int n_bad = 0;
+        for (int wi = 0; wi < n_workers; wi++) {
+            n_bad += bad[(size_t)wi];
+            for (auto &e : disc[(size_t)wi]) bm_set(discovered[(size_t)e.first], e.second);
+        }
+        for (size_t k = 0; k < n_pairs; k++) n_fallback += st[k].live ? 1 : 0;
+        if (getenv("SA_VERBOSE"))
+            fprintf(stderr, "  device-resident alignment loop: %zu pairs, device call %.3f s, host replay + files %.3f s, %zu pairs left to batched rounds\n",
+                    n_pairs, t_r1 - t_r0, wall_now() - t_r1, n_fallback);
+        if (n_bad) {
+            fprintf(stderr, "SegAligner(b200): internal error: device alignment loop and host replay disagree on %d pairs\n", n_bad);
+            throw JobExit{2, true};
+        }
+    }
+
     Engine::AlignOut out;  // reused across rounds
     std::vector<size_t> live;
     std::vector<sa_problem> pr;
@@ -424,17 +601,7 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
                     continue;
                 }
                 const int32_t *pj = v.pj;
-                {   // compute_partial_score_threshold (SegAligner.cpp:23-36) on the flat path: first = last entry
-                    const float *contig = contigs.map(p.c);
-                    const int contig_size = contigs.size(p.c);
-                    const int first_lab = pj[len - 1], last_lab = pj[0];
-                    const int aln_span_labs = last_lab - first_lab + 1;
-                    const float tot_labs = (float)(contig_size - 1);
-                    const float by_lab = p.thr * (aln_span_labs / tot_labs);
-                    const float aln_span_bases = contig[last_lab] - contig[first_lab];
-                    const float by_len = p.thr * (aln_span_bases / contig[contig_size - 1]);
-                    p.exp_thresh = fmaxf(by_lab, by_len);  // main.cpp:290
-                }
+                p.exp_thresh = partial_thresh(p, len, pj);
                 p.curr_best = v.res->score;
                 if (!(p.curr_best > p.exp_thresh)) {
                     // equality would spin forever in the reference (same DP, same result); we stop instead
@@ -456,31 +623,7 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
                     bits = arena.data() + p.used_off;  // the arena itself is not resized while the workers run
                 }
                 for (int t = 0; t < len; t++) bits[(size_t)pj[t] >> 5] |= 1u << (pj[t] & 31);  // main.cpp:298-300
-                if (tip_aln) {                                                              // must touch a contig end (:303-308)
-                    const size_t last_lab_gap = (size_t)(contigs.size(p.c) - 2) - (size_t)pj[0];
-                    if (last_lab_gap > 3 && pj[len - 1] > 2) continue;
-                }
-                if (len < min_tip_aln_labels || (!tip_aln && len < min_aln_labels)) continue;
-                const int32_t *pq = v.pq;
-                const float *ps = v.ps;
-                aln.resize((size_t)len);
-                for (int t = 0; t < len; t++) aln[(size_t)t] = AlnEntry{pj[t], pq[t], ps[t]};
-                const float mean = aln[0].s / (float)(aln.size() - 1);
-                const float median = aln_median(aln);
-                if (aln.size() < 5) {
-                    const float min_score = aln_min(aln);
-                    if (mean < 9400 || median < 9400 || min_score < 9200) continue;
-                } else if (mean < mean_thresh || median < med_thresh) {
-                    continue;
-                }
-                const int x = segs.ids[(size_t)p.s];
-                const int contig_id = contigs.ids[(size_t)p.c];
-                std::string seg_id = std::to_string(x < 0 ? -x : x);
-                if (x < 0) seg_id += "_r";
-                const std::string outname = o.sample_prefix + "_" + std::to_string(contig_id) + "_" + seg_id + "_" +
-                                            std::to_string(p.count) + (tip_aln ? "_tip" : "") + "_aln.txt";
-                print_alignment(outname, aln, contig_id, x, segs.size(p.s), p.curr_best);
-                for (auto &e : aln) W.disc.emplace_back(p.c, e.j);  // SAHelper.cpp:115
+                emit(p, len, pj, v.pq, v.ps, aln, W.disc);
             }
         };
         if (n_workers == 1) {

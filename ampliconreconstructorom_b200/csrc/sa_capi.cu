@@ -112,6 +112,10 @@ struct sa_ctx {
     DevBuf d_problems, d_order, d_results, d_halo, d_counter, d_cell_off, d_S, d_code, d_used, d_path_off, d_path_j,
         d_path_q, d_path_s, d_tmp0, d_tmp1, d_tmp2, d_halo2, d_row_off, d_rowmax_s, d_rowmax_q, d_prev32, d_halo3, d_mail;
     HostBuf h_res, h_start, h_pj, h_pq, h_ps;  // packed alignment output of the last sa_align_batch* call
+    // sa_align_rounds: per-worker scratch that persists across the rounds of a pair, the packed path arena, its host mirrors
+    DevBuf d_r_code, d_r_halo, d_r_col2, d_r_lastrow, d_r_used, d_r_path, d_r_ps, d_r_thr, d_r_rounds, d_r_nrounds, d_r_pj, d_r_pq,
+        d_r_psc, d_r_ctl;
+    HostBuf h_nr, h_rounds;
     sa_timing timing = {0, 0, 0, 0};
     size_t store_budget_cells = 0;  // max cells of stored matrices per chunk
     uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes moved by this context since it was created (sa_get_traffic)
@@ -397,9 +401,11 @@ void sa_ctx_destroy(sa_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->d_problems, &ctx->d_order,  &ctx->d_results,  &ctx->d_halo,   &ctx->d_counter, &ctx->d_cell_off,
                       &ctx->d_S,        &ctx->d_code,   &ctx->d_used,     &ctx->d_path_off, &ctx->d_path_j,  &ctx->d_path_q,
                       &ctx->d_path_s,   &ctx->d_tmp0,   &ctx->d_tmp1,     &ctx->d_tmp2,     &ctx->d_halo2,  &ctx->d_row_off, &ctx->d_rowmax_s,
-                      &ctx->d_rowmax_q, &ctx->d_prev32, &ctx->d_halo3, &ctx->d_mail};
+                      &ctx->d_rowmax_q, &ctx->d_prev32, &ctx->d_halo3, &ctx->d_mail, &ctx->d_r_code, &ctx->d_r_halo, &ctx->d_r_col2,
+                      &ctx->d_r_lastrow, &ctx->d_r_used, &ctx->d_r_path, &ctx->d_r_ps, &ctx->d_r_thr, &ctx->d_r_rounds, &ctx->d_r_nrounds,
+                      &ctx->d_r_pj, &ctx->d_r_pq, &ctx->d_r_psc, &ctx->d_r_ctl};
     for (auto b : bufs) b->release();
-    HostBuf *hbufs[] = {&ctx->h_res, &ctx->h_start, &ctx->h_pj, &ctx->h_pq, &ctx->h_ps};
+    HostBuf *hbufs[] = {&ctx->h_res, &ctx->h_start, &ctx->h_pj, &ctx->h_pq, &ctx->h_ps, &ctx->h_nr, &ctx->h_rounds};
     for (auto b : hbufs) b->release();
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -747,6 +753,202 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
         memcpy(path_q + path_off[k], pk.path_q + pk.start[k], sizeof(int32_t) * (size_t)len);
         memcpy(path_s + path_off[k], pk.path_s + pk.start[k], sizeof(float) * (size_t)len);
     }
+    return SA_OK;
+}
+
+// The whole per-pair loop of run_SA_aln on the device (see include/segaligner_b200.h and rounds_finish in sa_kernels.cu).
+int sa_align_rounds(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const float *thr, int32_t max_alns,
+                    const uint32_t *used_bits, int64_t used_words_per_slot, int64_t n_used_slots, sa_rounds_out *out) {
+    if (!ctx || !out) return SA_EINVAL;
+    memset(out, 0, sizeof(*out));
+    if (n <= 0) return SA_OK;
+    if (!problems || !mode || !thr) return fail(ctx, SA_EINVAL, "NULL buffer");
+    if (mode->init_mode != SA_INIT_SEMIGLOBAL || mode->start_mode != SA_START_SEMIGLOBAL || mode->fitting || mode->swap_b_x ||
+        mode->lookback != LB)
+        return fail(ctx, SA_EINVAL, "sa_align_rounds: semi-global init and start, lookback 6, no swap_b_x, no fitting");
+    if (max_alns < 1 || max_alns > 64) return fail(ctx, SA_EINVAL, "sa_align_rounds: max_alns must be 1..64");
+    CU(cudaSetDevice(ctx->device));
+    int rc = check_problems(ctx, problems, n, used_bits ? n_used_slots : 0);
+    if (rc) return rc;
+    for (int64_t k = 0; k < n; k++)
+        if (ctx->sides[1].labels(problems[k].seg) < 2) return fail(ctx, SA_EINVAL, "sa_align_rounds: segments need >= 2 labels");
+    FillParams P;
+    rc = prepare_fill(ctx, P, mode);
+    if (rc) return rc;
+    if (used_bits && n_used_slots > 0) {
+        if ((double)used_words_per_slot * (double)n_used_slots >= 2147483648.0)
+            return fail(ctx, SA_EINVAL, "used-label bitmaps exceed 2^31 words");
+        const size_t bytes = sizeof(uint32_t) * (size_t)(used_words_per_slot * n_used_slots);
+        CU(ctx->d_used.reserve(bytes));
+        CU(cpy(ctx, ctx->d_used.p, used_bits, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        P.used_bits = ctx->d_used.as<uint32_t>();
+        P.used_words_per_slot = used_words_per_slot;
+    }
+    ctx->timing = {0, 0, 0, 0};
+    const int n_ctas = (int)std::min<int64_t>((n + FILL_WARPS - 1) / FILL_WARPS, n_fill_ctas(ctx));
+    const long long workers = (long long)n_ctas * FILL_WARPS;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    // per-worker scratch ~ 2 bytes per cell of the largest accepted matrix (codes + one 32-byte halo slot per strip column);
+    // pairs whose matrix would not fit half of the free memory are left to the caller (n_rounds = -1)
+    double scratch_budget = 0.5 * (double)free_b;
+    if (const char *e = getenv("SA_ROUNDS_SCRATCH_BYTES")) scratch_budget = atof(e);
+    const double cap_cells = scratch_budget / (double)workers / 2.2 - 65536.0;
+    std::vector<int64_t> acc;  // accepted problems
+    acc.reserve((size_t)n);
+    int max_nb = 1, max_nx = 2, max_path = 1;
+    long long max_cells = 1, max_halo = 8;
+    for (int64_t k = 0; k < n; k++) {
+        const long long nb = ctx->sides[0].labels(problems[k].contig), nx = ctx->sides[1].labels(problems[k].seg);
+        if ((double)nb * (double)nx > cap_cells) continue;
+        acc.push_back(k);
+        max_nb = std::max<int>(max_nb, (int)nb);
+        max_nx = std::max<int>(max_nx, (int)nx);
+        max_path = std::max<int>(max_path, (int)std::min(nb, nx));
+        max_cells = std::max(max_cells, nb * nx);
+        max_halo = std::max(max_halo, ((nb + 31) / 32) * nx * 8);
+    }
+    CU(ctx->h_nr.reserve(sizeof(int32_t) * (size_t)n));
+    CU(ctx->h_rounds.reserve(sizeof(sa_round) * (size_t)n * (size_t)max_alns));
+    int32_t *h_nr = ctx->h_nr.as<int32_t>();
+    sa_round *h_rounds = ctx->h_rounds.as<sa_round>();
+    for (int64_t k = 0; k < n; k++) h_nr[k] = -1;
+    int64_t total = 0;
+    if (!acc.empty()) {
+        const int used_words = (max_nb + 31) / 32;
+        CU(ctx->d_r_code.reserve((size_t)workers * (size_t)max_cells));
+        CU(ctx->d_r_halo.reserve(sizeof(float) * (size_t)workers * (size_t)max_halo));
+        CU(ctx->d_r_col2.reserve(sizeof(float) * (size_t)workers * 2 * (size_t)max_nb));
+        CU(ctx->d_r_lastrow.reserve(sizeof(float) * (size_t)workers * (size_t)max_nx));
+        CU(ctx->d_r_used.reserve(sizeof(uint32_t) * (size_t)workers * (size_t)used_words));
+        CU(ctx->d_r_path.reserve(sizeof(int32_t) * (size_t)workers * 2 * (size_t)max_path));
+        CU(ctx->d_r_ps.reserve(sizeof(float) * (size_t)workers * (size_t)max_path));
+        CU(ctx->d_r_ctl.reserve(64));
+        P.r_code = ctx->d_r_code.as<uint8_t>();
+        P.r_halo = ctx->d_r_halo.as<float>();
+        P.r_col2 = ctx->d_r_col2.as<float>();
+        P.r_lastrow = ctx->d_r_lastrow.as<float>();
+        P.r_used = ctx->d_r_used.as<uint32_t>();
+        P.r_path = ctx->d_r_path.as<int32_t>();
+        P.r_ps = ctx->d_r_ps.as<float>();
+        P.r_cells = max_cells;
+        P.r_halo_floats = max_halo;
+        P.r_max_nb = max_nb;
+        P.r_max_nx = max_nx;
+        P.r_used_words = used_words;
+        P.r_max_path = max_path;
+        P.r_max_alns = max_alns;
+        // the packed path arena is sized for the worst case of a chunk (every round of every pair a full-length path)
+        cudaMemGetInfo(&free_b, &total_b);
+        double arena_budget = 0.25 * (double)free_b;
+        if (const char *e = getenv("SA_ROUNDS_ARENA_BYTES")) arena_budget = atof(e);
+        const long long arena_cap = std::max<long long>((long long)(arena_budget / 12.0), (long long)max_alns * max_path);
+        std::vector<sa_problem> cp;
+        std::vector<float> cthr;
+        size_t k0 = 0;
+        while (k0 < acc.size()) {
+            long long worst = 0;
+            size_t k1 = k0;
+            cp.clear();
+            cthr.clear();
+            while (k1 < acc.size()) {
+                const sa_problem &pr = problems[acc[k1]];
+                const long long w = (long long)max_alns * std::min(ctx->sides[0].labels(pr.contig), ctx->sides[1].labels(pr.seg));
+                if (k1 > k0 && worst + w > arena_cap) break;
+                worst += w;
+                cp.push_back(pr);
+                cthr.push_back(thr[acc[k1]]);
+                k1++;
+            }
+            const int64_t m = (int64_t)(k1 - k0);
+            Plan plan;
+            build_plan(ctx, cp.data(), m, n_fill_ctas(ctx) * FILL_WARPS, plan);
+            // one queue, largest first: the size classes of the plan in descending order (huge, large, bulk)
+            std::vector<int32_t> order;
+            order.reserve((size_t)m);
+            order.insert(order.end(), plan.order.begin() + plan.n_bulk + plan.n_large, plan.order.end());
+            order.insert(order.end(), plan.order.begin() + plan.n_bulk, plan.order.begin() + plan.n_bulk + plan.n_large);
+            order.insert(order.end(), plan.order.begin(), plan.order.begin() + plan.n_bulk);
+            CU(ctx->d_problems.reserve(sizeof(sa_problem) * (size_t)m));
+            CU(ctx->d_order.reserve(sizeof(int32_t) * (size_t)m));
+            CU(ctx->d_r_thr.reserve(sizeof(float) * (size_t)m));
+            CU(ctx->d_r_nrounds.reserve(sizeof(int32_t) * (size_t)m));
+            CU(ctx->d_r_rounds.reserve(sizeof(sa_round) * (size_t)m * (size_t)max_alns));
+            CU(ctx->d_r_pj.reserve(sizeof(int32_t) * (size_t)std::min(worst, arena_cap)));
+            CU(ctx->d_r_pq.reserve(sizeof(int32_t) * (size_t)std::min(worst, arena_cap)));
+            CU(ctx->d_r_psc.reserve(sizeof(float) * (size_t)std::min(worst, arena_cap)));
+            CU(cpy(ctx, ctx->d_problems.p, cp.data(), sizeof(sa_problem) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cpy(ctx, ctx->d_order.p, order.data(), sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cpy(ctx, ctx->d_r_thr.p, cthr.data(), sizeof(float) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemsetAsync(ctx->d_r_ctl.p, 0, 64, ctx->stream));
+            CU(cudaMemsetAsync(ctx->d_counter.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+            P.problems = ctx->d_problems.as<sa_problem>();
+            P.order = ctx->d_order.as<int32_t>();
+            P.n_problems = m;
+            P.counter = ctx->d_counter.as<unsigned long long>();
+            P.stats = ctx->d_counter.as<unsigned long long>() + 4;
+            P.r_thr = ctx->d_r_thr.as<float>();
+            P.r_rounds = ctx->d_r_rounds.as<sa_round>();
+            P.r_n_rounds = ctx->d_r_nrounds.as<int32_t>();
+            P.r_arena_top = ctx->d_r_ctl.as<unsigned long long>();
+            P.r_overflow = reinterpret_cast<int32_t *>(ctx->d_r_ctl.as<unsigned long long>() + 1);
+            P.r_arena_cap = std::min(worst, arena_cap);
+            P.r_pj = ctx->d_r_pj.as<int32_t>();
+            P.r_pq = ctx->d_r_pq.as<int32_t>();
+            P.r_psc = ctx->d_r_psc.as<float>();
+            CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+            launch_fill(P, 3, false, 0, (int)std::min<int64_t>((m + FILL_WARPS - 1) / FILL_WARPS, n_ctas), ctx->stream);
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+            unsigned long long ctl[2] = {0, 0};
+            CU(cpy(ctx, ctl, ctx->d_r_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, ctx->stream));
+            std::vector<int32_t> nr((size_t)m);
+            CU(cpy(ctx, nr.data(), ctx->d_r_nrounds.p, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            if ((int32_t)ctl[1] != 0) return fail(ctx, SA_ECUDA, "sa_align_rounds: path arena overflow (internal sizing error)");
+            const int64_t n_path = (int64_t)ctl[0];
+            CU(ctx->h_pj.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(total + n_path, 1), true));
+            CU(ctx->h_pq.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(total + n_path, 1), true));
+            CU(ctx->h_ps.reserve(sizeof(float) * (size_t)std::max<int64_t>(total + n_path, 1), true));
+            // the round records land in a staging area at the END of the pinned buffer region of this chunk's first problem:
+            // records of problem acc[k0 + i] go to h_rounds[acc[k0 + i] * max_alns]; copy the chunk contiguously, then scatter
+            std::vector<sa_round> rr((size_t)m * (size_t)max_alns);
+            CU(cpy(ctx, rr.data(), ctx->d_r_rounds.p, sizeof(sa_round) * rr.size(), cudaMemcpyDeviceToHost, ctx->stream));
+            if (n_path > 0) {
+                CU(cpy(ctx, ctx->h_pj.as<int32_t>() + total, ctx->d_r_pj.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cpy(ctx, ctx->h_pq.as<int32_t>() + total, ctx->d_r_pq.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cpy(ctx, ctx->h_ps.as<float>() + total, ctx->d_r_psc.p, sizeof(float) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            CU(cudaStreamSynchronize(ctx->stream));
+            for (int64_t i = 0; i < m; i++) {
+                const int64_t g = acc[k0 + (size_t)i];
+                h_nr[g] = nr[(size_t)i];
+                for (int r = 0; r < nr[(size_t)i]; r++) {
+                    sa_round v = rr[(size_t)i * (size_t)max_alns + (size_t)r];
+                    v.path_off += total;
+                    h_rounds[(size_t)g * (size_t)max_alns + (size_t)r] = v;
+                }
+            }
+            total += n_path;
+            float a = 0;
+            cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+            ctx->timing.fill_ms += a;
+            ctx->timing.n_launches += 1;
+            if (getenv("SA_VERBOSE"))
+                fprintf(stderr, "  sa_align_rounds chunk: %lld pairs, kernel %.2f ms, %lld path entries, %d workers x %.1f MB scratch\n",
+                        (long long)m, a, (long long)n_path, (int)workers,
+                        ((double)max_cells + 4.0 * (double)max_halo + 8.0 * max_nb + 4.0 * max_nx + 4.0 * used_words + 12.0 * max_path) / 1e6);
+            k0 = k1;
+        }
+    }
+    out->n = n;
+    out->max_alns = max_alns;
+    out->total = total;
+    out->n_rounds = h_nr;
+    out->rounds = h_rounds;
+    out->path_j = ctx->h_pj.as<int32_t>();
+    out->path_q = ctx->h_pq.as<int32_t>();
+    out->path_s = ctx->h_ps.as<float>();
     return SA_OK;
 }
 

@@ -389,6 +389,134 @@ __device__ __noinline__ CellRes cell_slow(bool swap, uint32_t a_row, float dx0, 
     return res;
 }
 
+// ---- the per-pair alignment loop on the device ("rounds", STORE_MODE 3) ---------------------------------------------------
+// After a (full or windowed) sweep of the pair's matrix: sg_aln_backtrack_start (SegAligner.cpp:172-195) over the persisted
+// last row and last two columns, get_aln_list (SAHelper.cpp:83-95) over the persisted predecessor codes with the scores
+// along the path recomputed exactly (as trace_kernel does), compute_partial_score_threshold (SegAligner.cpp:23-36), the
+// loop bookkeeping of run_SA_aln (main.cpp:268-300), and the window of strips the NEXT round has to re-sweep.
+// Why a window is exact: dp_align's cell (j, q) reads rows j-6..j-1 of columns < q only, so by induction it depends on rows
+// >= j - 6q.  Masking the contig labels of a path that spans rows [j_lo, j_hi] therefore cannot change any row < j_lo nor
+// any row > j_hi + 6 (nx - 1); rows in between are re-swept strip by strip, the strip above the window supplying its
+// (unchanged) bottom rows from the per-strip halo slots.
+// Called by all 32 lanes of the warp; returns true when the pair is finished.  count / sb / se are warp-uniform.
+__device__ __noinline__ bool rounds_finish(const FillParams &P, long long gunit, long long pidx, int contig, int nb, int seg, int nx,
+                                           float thr, int round, int &count, int &sb, int &se) {
+    const int lane = threadIdx.x & 31;
+    const float *col2 = P.r_col2 + gunit * 2 * P.r_max_nb;
+    const float *lastrow = P.r_lastrow + gunit * P.r_max_nx;
+    // backtrack start: scan position e = the reference's scan order (last row by q, then rows by j over the last 2 columns);
+    // strict '>' keeps the first maximum; -inf cells are never selected
+    float st_s = NEG_INF_F;
+    int st_e = -1;
+    const int n_e = nx + 2 * nb;
+    for (int e = lane; e < n_e; e += 32) {
+        const float v = (e < nx) ? __ldcg(lastrow + e) : __ldcg(col2 + (e - nx));
+        if (v > st_s) {
+            st_s = v;
+            st_e = e;
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, st_s, m);
+        const int oe = __shfl_xor_sync(0xffffffffu, st_e, m);
+        if (oe >= 0 && (st_e < 0 || os > st_s || (os == st_s && oe < st_e))) {
+            st_s = os;
+            st_e = oe;
+        }
+    }
+    int st_j = -1, st_q = -1;
+    if (st_e >= 0) {
+        if (st_e < nx) st_j = nb - 1, st_q = st_e;
+        else st_j = (st_e - nx) >> 1, st_q = nx - 2 + ((st_e - nx) & 1);
+    }
+    int stop = 1, n_sb = 0, n_se = 0, n_count = count;
+    if (lane == 0) {
+        int n = 0;
+        long long aoff = 0;
+        float exp_thresh = 0.0f;
+        int32_t *pj = P.r_path + gunit * 2 * P.r_max_path, *pq = pj + P.r_max_path;
+        float *ps = P.r_ps + gunit * P.r_max_path;
+        if (st_e >= 0) {
+            const uint8_t *C = P.r_code + gunit * P.r_cells;
+            int j = st_j, q = st_q;
+            for (;;) {  // get_aln_list: follow `previous` until {-1,-1}
+                pj[n] = j;
+                pq[n] = q;
+                n++;
+                const int cd = __ldcg(C + (long long)j * nx + q);
+                if (cd == 0 || n >= P.r_max_path) break;
+                j -= (cd - 1) / LB + 1;
+                q -= (cd - 1) % LB + 1;
+            }
+            // scores along the path, start -> end, exactly as dp_align produced them (see trace_kernel)
+            const int64_t boff = P.contigs.pos_off[contig], xoff = P.segs.pos_off[seg];
+            const LabelOps *bops = P.contigs.ops + (boff - contig);
+            const LabelOps *xops = P.segs.ops + (xoff - seg);
+            float sv = (pj[n - 1] == 0 || pq[n - 1] < 2) ? 0.0f : NEG_INF_F;  // init_semiglobal_aln
+            ps[n - 1] = sv;
+            int jp = pj[n - 1], qp = pq[n - 1];
+            for (int t = n - 2; t >= 0; t--) {
+                const int jc = pj[t], qc = pq[t];
+                const int dj = jc - jp, dq = qc - qp;
+                const float discrep = fabsf(__fsub_rn(bops[jc].d[dj - 1], xops[qc].d[dq - 1]));
+                const float delta = powf12_slow(discrep);
+                const float fnfp = (dj == 1) ? xops[qc].f[dq - 1] : __fadd_rn(5000.0f * (float)(dj - 1), xops[qc].f[dq - 1]);
+                sv = __fadd_rn(sv, __fsub_rn(10000.0f, __fadd_rn(fnfp, delta)));
+                ps[t] = sv;
+                jp = jc;
+                qp = qc;
+            }
+            aoff = (long long)atomicAdd(P.r_arena_top, (unsigned long long)n);
+            if (aoff + n <= P.r_arena_cap) {
+                for (int t = 0; t < n; t++) {
+                    P.r_pj[aoff + t] = pj[t];
+                    P.r_pq[aoff + t] = pq[t];
+                    P.r_psc[aoff + t] = ps[t];
+                }
+            } else {
+                *P.r_overflow = 1;
+            }
+            // compute_partial_score_threshold (SegAligner.cpp:23-36) on the path; aln_list is end -> start
+            const float *cpos = P.contigs.pos + boff;  // nb + 1 entries, the last one is the contig length
+            const int first_lab = pj[n - 1], last_lab = pj[0];
+            const float by_lab = __fmul_rn(thr, __fdiv_rn((float)(last_lab - first_lab + 1), (float)nb));
+            const float by_len = __fmul_rn(thr, __fdiv_rn(__fsub_rn(cpos[last_lab], cpos[first_lab]), cpos[nb]));
+            exp_thresh = fmaxf(by_lab, by_len);  // main.cpp:290
+        }
+        sa_round rec;
+        rec.score = st_s;
+        rec.j = st_j;
+        rec.q = st_q;
+        rec.path_len = n;
+        rec.path_off = aoff;
+        P.r_rounds[pidx * P.r_max_alns + round] = rec;
+        if (n > 0 && st_s > exp_thresh) {  // main.cpp:295: accepted -> count, the path's contig labels join the used set
+            n_count = count + 1;
+            uint32_t *ub = P.r_used + gunit * P.r_used_words;
+            for (int t = 0; t < n; t++) {
+                const int jj = pj[t];
+                __stcg(ub + (jj >> 5), __ldcg(ub + (jj >> 5)) | (1u << (jj & 31)));
+            }
+            if (n_count < P.r_max_alns) {  // main.cpp:268: another round, over the rows this path can influence
+                stop = 0;
+                const int j_lo = pj[n - 1], j_hi = pj[0];
+                const int nstrips = (nb + 31) >> 5;
+                n_sb = j_lo >> 5;
+                n_se = ((j_hi + LB * (nx - 1)) >> 5) + 1;
+                if (n_se > nstrips) n_se = nstrips;
+            }
+        }
+        if (stop) P.r_n_rounds[pidx] = round + 1;
+    }
+    __syncwarp();
+    stop = __shfl_sync(0xffffffffu, stop, 0);
+    count = __shfl_sync(0xffffffffu, n_count, 0);
+    sb = __shfl_sync(0xffffffffu, n_sb, 0);
+    se = __shfl_sync(0xffffffffu, n_se, 0);
+    return stop != 0;
+}
+
 constexpr int RING_W = 40;  // 6 halo rows + 32 lanes + 2 pad
 // STORE staging per warp: scores [32][9] floats + codes [32][12] bytes + the problem's cell offset (8 B, read back at every
 // flush from shared memory instead of living in registers or being re-fetched from global memory)
@@ -407,10 +535,15 @@ constexpr int STAGE_BYTES_PER_WARP = 32 * 9 * 4 + 32 * 12 + 16;
 //             L2-resident mailbox.  Used for chromosome-sized problems whose single-SM time would be the tail.
 // STORE_MODE: 0 = nothing per cell (scoring), 1 = predecessor codes only (alignment), 2 = codes + scores + per-row maxima
 // (detection, -nl-free test hook).  Separate instantiations keep the alignment kernel free of the registers mode 2 needs.
+// STORE_MODE 3 = "rounds" (NW == 1 only): the warp keeps its pair and runs the whole run_SA_aln loop on it (main.cpp:262-300):
+// codes go to per-worker scratch, every strip's bottom rows / the last row / the last two columns persist in HBM, and each
+// later round re-sweeps only the strips its predecessor's path can influence (see rounds_finish below).
 template <int STORE_MODE, bool SWAP, int NW, int MINB, int CS>
 __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_kernel(const FillParams P) {
     constexpr bool STORE = STORE_MODE != 0;
     constexpr bool STORE_S = STORE_MODE == 2;
+    constexpr bool ROUNDS = STORE_MODE == 3;
+    static_assert(!ROUNDS || (NW == 1 && CS == 1 && !SWAP), "the rounds variant is one warp per pair, semi-global, no swap");
     constexpr int WPC = (NW == 1) ? FILL_WARPS : NW;  // warps per CTA
     constexpr int NWT = NW * CS;                        // warps in the wavefront
     static_assert(CS == 1 || NW > 1, "clusters only for the cooperative shape");
@@ -444,7 +577,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
     const uint32_t a_tile_c = a_tile_s + 32 * 9 * 4;                                                    // [32][12] bytes
 
     const long long gunit = (NW == 1) ? ((long long)blockIdx.x * FILL_WARPS + warp) : (long long)(blockIdx.x / CS);
-    float *halo = P.halo + gunit * P.halo_stride;
+    // rounds: one slot per strip ([strip][q][8]) in the worker's scratch, so a later round finds the rows above its window
+    float *halo = ROUNDS ? P.r_halo + gunit * P.r_halo_floats : P.halo + gunit * P.halo_stride;
     const int w = (NW == 1) ? 0 : crank * NW + warp;  // position in the wavefront
     // cluster mailbox (CS > 1): [0..CS) next-problem broadcast slot 0, then per-CTA exchange [CS][2][8] floats,
     // then per-CTA start candidates
@@ -485,7 +619,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         // instead of living in four registers through the bound pass -- the kernel is compiled for 80 registers)
         if (STORE) {
             if (lane == 0) {
-                const long long coff = P.cell_off[pidx];
+                const long long coff = ROUNDS ? gunit * P.r_cells : P.cell_off[pidx];
                 asm volatile("st.shared.s64 [%0], %1;" ::"r"(a_tile_c + 32 * 12), "l"(coff) : "memory");
             }
             __syncwarp();
@@ -506,10 +640,23 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         const int nstrips = (nb + 31) >> 5;
         const int R = (NW == 1) ? nx : (nx > NWT ? nx : NWT);  // steps per round
         const int rounds = (nstrips + NWT - 1) / NWT;
-        const int T = rounds * R + (NWT - 1);  // < 2^31: check_problems() rejects problems with more than 2^35 cells
+        // rounds variant: strips [r_sb, r_se) are swept in this pass; accepted alignments so far; pass number
+        int r_sb = 0, r_se = nstrips, r_count = 0, r_round = 0;
+        if (ROUNDS) {
+            uint32_t *ub = P.r_used + gunit * P.r_used_words;  // the pair's used labels: a copy of its seed bitmap (or none)
+            for (int i = lane; i < ((nb + 31) >> 5); i += 32) __stcg(ub + i, used_off >= 0 ? P.used_bits[used_off + i] : 0u);
+            __syncwarp();
+            const float thr0 = P.r_thr[pidx];
+            if (!(thr0 >= thr0)) {  // NaN threshold: `curr_best_score >= exp_thresh` is false from the start (main.cpp:268)
+                if (lane == 0) P.r_n_rounds[pidx] = 0;
+                continue;
+            }
+        }
+        for (;;) {  // one pass, except in the rounds variant
+        const int T = ROUNDS ? (r_se - r_sb) * nx : rounds * R + (NWT - 1);  // < 2^31: check_problems() rejects problems with more than 2^35 cells
 
         // per-warp sweep state
-        int strip = w;
+        int strip = ROUNDS ? r_sb : w;
         int q = 0;  // column within the current round (>= nx: idle tail of a short round)
         int j = 0, jc = 0;
         bool row_ok = false, row_used = false;
@@ -548,7 +695,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                         sts_f32(a_row + 6 * 128, b4.z), sts_f32(a_row + 7 * 128, b4.w), sts_f32(a_row + 8 * 128, c4.x);
                         sts_f32(a_row + 9 * 128, c4.y), sts_f32(a_row + 10 * 128, c4.z), sts_f32(a_row + 11 * 128, c4.w);
                     }
-                    row_used = used_off >= 0 ? ((P.used_bits[used_off + (jc >> 5)] >> (jc & 31)) & 1u) : false;
+                    if (ROUNDS) row_used = (__ldcg(P.r_used + gunit * P.r_used_words + (jc >> 5)) >> (jc & 31)) & 1u;
+                    else row_used = used_off >= 0 ? ((P.used_bits[used_off + (jc >> 5)] >> (jc & 31)) & 1u) : false;
                     __syncwarp();
 #pragma unroll
                     for (int s = 0; s < 2 * LB; s++) {
@@ -573,7 +721,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                 }
                 // rows above the strip at column q (bottom rows of strip-1)
                 if (strip > 0 && lane < 6) {
-                    if (NW == 1 || w == 0) hv = __ldcg(halo + (long long)q * 8 + lane);
+                    if (ROUNDS) hv = __ldcg(halo + ((long long)(strip - 1) * nx + q) * 8 + lane);
+                    else if (NW == 1 || w == 0) hv = __ldcg(halo + (long long)q * 8 + lane);
                     else if (CS > 1 && warp == 0) hv = __ldcg(cmail + 16 + ((crank - 1) * 2 + ((t - 1) & 1)) * 8 + lane);
                     else hv = s_xbuf[warp - 1][(t - 1) & 1][lane];
                 }
@@ -727,7 +876,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     sts_f32(pbase - 24 + LB * RING_W * 4, hv);
                 }
                 if (lane >= 26) {
-                    if (NW == 1 || w == NWT - 1) __stcg(halo + (long long)q * 8 + (lane - 26), rv);
+                    if (ROUNDS) __stcg(halo + ((long long)strip * nx + q) * 8 + (lane - 26), rv);
+                    else if (NW == 1 || w == NWT - 1) __stcg(halo + (long long)q * 8 + (lane - 26), rv);
                     else if (CS > 1 && warp == NW - 1) __stcg(cmail + 16 + (crank * 2 + (t & 1)) * 8 + (lane - 26), rv);
                     else s_xbuf[warp][t & 1][lane - 26] = rv;
                 }
@@ -747,7 +897,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                         long long coff;
                         asm volatile("ld.shared.s64 %0, [%1];" : "=l"(coff) : "r"(a_tile_c + 32 * 12));
                         float *Sout = STORE_S ? P.S + coff : nullptr;
-                        uint8_t *Cout = P.code + coff;
+                        uint8_t *Cout = (ROUNDS ? P.r_code : P.code) + coff;
                         const int q0 = q - cq, col = lane & 7;
 #pragma unroll
                         for (int it = 0; it < 8; it++) {
@@ -777,7 +927,10 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                             }
                         }
                     }
-                    if (P.start_mode == SA_START_LOCAL) {
+                    if (ROUNDS) {  // what the backtrack-start scan reads persists per pair (rounds_finish)
+                        if (q >= nx - 2) __stcg(P.r_col2 + gunit * 2 * P.r_max_nb + 2 * j + (q - (nx - 2)), val);
+                        if (j == nb - 1) __stcg(P.r_lastrow + gunit * P.r_max_nx + q, val);
+                    } else if (P.start_mode == SA_START_LOCAL) {
                         if (val > st_s) {  // per lane (j,q) arrives in increasing row-major order
                             st_s = val;
                             st_j = j;
@@ -806,6 +959,18 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     strip += NWT;
                 }
             }
+        }
+        if (!ROUNDS) break;
+        __syncwarp();
+        if (rounds_finish(P, gunit, pidx, pr.contig, nb, pr.seg, nx, P.r_thr[pidx], r_round, r_count, r_sb, r_se)) break;
+        r_round++;
+        }  // rounds
+        if (ROUNDS) {
+            if (P.stats) {
+                const unsigned a = __reduce_add_sync(0xffffffffu, n_replay);
+                if (lane == 0) atomicAdd(P.stats, (unsigned long long)a);
+            }
+            continue;
         }
 
         // reduce the start over lanes (and warps): max score, ties -> smallest scan order
@@ -1365,7 +1530,9 @@ static void launch_fill_t(const FillParams &p, int store, bool swap, int n_ctas,
         cudaFuncSetAttribute(fill_kernel<S_, W_, NW, MINB, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
         cudaLaunchKernelEx(&cfg, fill_kernel<S_, W_, NW, MINB, CS>, p);                                                \
     } while (0)
-    if (store == 2) {
+    if (store == 3) {  // the rounds variant exists for the bulk shape only (one warp per pair), semi-global, no swap
+        if constexpr (NW == 1 && CS == 1) SA_LAUNCH_FILL(3, false);
+    } else if (store == 2) {
         if (swap) SA_LAUNCH_FILL(2, true);
         else SA_LAUNCH_FILL(2, false);
     } else if (store == 1) {

@@ -49,6 +49,25 @@ struct FillParams {
     int32_t *rowmax_q;
     const int64_t *row_off;  // per problem offset into the rowmax arrays
     double pk[12];  // fp64 constants of the powf replay (kernel-parameter bank => direct DFMA operands)
+    // ---- STORE_MODE 3 ("rounds", sa_align_rounds): the whole `while` loop of run_SA_aln (main.cpp:268-300) per pair on one
+    // warp.  Per-worker scratch (one slot per resident warp) that persists across the rounds of a pair:
+    uint8_t *r_code;        // [workers][r_cells]         predecessor codes of the pair's whole matrix
+    float *r_halo;          // [workers][r_halo_floats]   bottom 6 rows of EVERY strip: [strip][q][8]
+    float *r_col2;          // [workers][2 * r_max_nb]    S[j][nx-2], S[j][nx-1] for every row
+    float *r_lastrow;       // [workers][r_max_nx]        S[nb-1][q]
+    uint32_t *r_used;       // [workers][r_used_words]    used contig labels of the pair (seed + accepted paths)
+    int32_t *r_path;        // [workers][2 * r_max_path]  traceback of the current round: j's then q's
+    float *r_ps;            // [workers][r_max_path]      scores along it
+    long long r_cells, r_halo_floats;
+    int r_max_nb, r_max_nx, r_used_words, r_max_path, r_max_alns;
+    const float *r_thr;     // per problem: the segment's score threshold (curr_best_score / exp_thresh start value)
+    sa_round *r_rounds;     // [n_problems][r_max_alns]
+    int32_t *r_n_rounds;    // [n_problems]
+    unsigned long long *r_arena_top;  // bump allocator over the packed path arena
+    long long r_arena_cap;
+    int32_t *r_pj, *r_pq;   // packed paths of all rounds of all pairs
+    float *r_psc;
+    int32_t *r_overflow;    // set when the arena was too small (host-sized for the worst case, so never)
 };
 
 struct TraceParams {

@@ -114,6 +114,39 @@ typedef struct sa_packed_paths {
 int sa_align_batch_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const uint32_t *used_bits,
                           int64_t used_words_per_slot, int64_t n_used_slots, sa_packed_paths *out);
 
+/* All alignment rounds of a batch of (segment, contig) pairs in ONE call: the whole per-pair loop of run_SA_aln
+ * (main.cpp:262-300) -- `while (curr_best_score >= exp_thresh && count < max_alns)`: init S (semi-global), dp_align
+ * honouring the pair's used contig labels, sg_aln_backtrack_start, get_aln_list, compute_partial_score_threshold
+ * (SegAligner.cpp:23-36), and on `best > exp_thresh` count++ and the path's contig labels join the used set -- runs on the
+ * device, one pair per warp.  Round 1 fills the whole matrix; a later round recomputes only the rows its predecessor's
+ * path can influence ([first path label, last path label + 6*(nx-1)], exact by the look-back cone of dp_align) from
+ * per-pair state kept in HBM (predecessor codes, strip-boundary rows, last row and last two columns).
+ *   thr[k]        the segment's score threshold (start value of curr_best_score and exp_thresh, main.cpp:262,266)
+ *   used_slot     seed bitmap of the pair (tip phase: labels already taken on the contig) or -1; the seed is not modified
+ * Output (pinned host memory owned by the context, valid until the next sa_align* call): n_rounds[k] rounds per pair
+ * (0 when thr is NaN) in rounds[k * max_alns ...]; round r's traceback (end -> start, like aln_list) is
+ * path_j/q/s[path_off .. path_off + path_len).  The last round of a pair is the one that failed `best > exp_thresh`
+ * (or the max_alns-th accepted one).  Semi-global mode, lookback 6, no swap_b_x, every segment >= 2 labels; a pair whose
+ * matrix exceeds the per-worker scratch gets n_rounds = -1 (the caller falls back to sa_align_batch_packed rounds). */
+typedef struct sa_round {
+    float score;       /* S at the backtrack start = curr_best_score of the round */
+    int32_t j, q;      /* backtrack start */
+    int32_t path_len;
+    int64_t path_off;
+} sa_round;
+typedef struct sa_rounds_out {
+    int64_t n;
+    int32_t max_alns;
+    int32_t reserved;
+    int64_t total;             /* packed path entries */
+    const int32_t *n_rounds;   /* n */
+    const sa_round *rounds;    /* n * max_alns */
+    const int32_t *path_j, *path_q;
+    const float *path_s;
+} sa_rounds_out;
+int sa_align_rounds(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const float *thr, int32_t max_alns,
+                    const uint32_t *used_bits, int64_t used_words_per_slot, int64_t n_used_slots, sa_rounds_out *out);
+
 /* Detection-mode scoring (run_SA_score with detection=true, main.cpp:155-159): semiglobal init, dp_align,
  * then multi_backtrack_scores (SegAligner.cpp:208-233) harvesting n_want[k] path scores per problem in the
  * reference's order (including its skip of the single best cell).  scores_off[n+1] gives each problem's slot

@@ -100,9 +100,13 @@ def test_c1_gbm39_segments_vs_bspqi_assembly(tmp_path):
 
 def test_c5_shaped_cohort_vs_reference(tmp_path, monkeypatch):
     """A C5-shaped subsample (BASELINE.json configs[4]: cohort sweep of many short segments x many short contigs) at a
-    size where the cohort-scale host path takes its big-batch branches: > 100,000 pairs per tip-alignment round (pinned
-    pre-sizing, several post-processing workers splicing private bitmaps into the arena), stored matrices split into
-    many chunks (SA_STORE_BUDGET_CELLS), packed tracebacks -- byte-identical to the unmodified reference binary."""
+    size where the cohort-scale host path takes its big-batch branches, byte-identical to the unmodified reference binary
+    through BOTH alignment engines:
+      * the device-resident loop (sa_align_rounds; default for standard runs): > 100,000 pairs in the tip pass, several
+        replay workers, the packed path arena split into chunks (SA_ROUNDS_ARENA_BYTES);
+      * the batched rounds (sa_align_batch_packed, what -local / -detection / oversized pairs use; forced here with
+        SA_NO_ROUNDS=1): > 100,000 pairs per round (pinned pre-sizing, post-processing workers splicing private bitmaps
+        into the arena), stored matrices split into many chunks (SA_STORE_BUDGET_CELLS)."""
     import os
     _need_bins()
     segs, contigs = cc.make_c5_shaped()
@@ -110,13 +114,24 @@ def test_c5_shaped_cohort_vs_reference(tmp_path, monkeypatch):
     flags = cc.C5_FLAGS + [f"-nthreads={min(os.cpu_count() or 1, 32)}"]
     r = cc.run_bin(cc.REF_BIN, tmp_path / "ref", seg_f, con_f, flags)
     assert r.returncode == 0, r.stderr[-2000:]
-    monkeypatch.setenv("SA_STORE_BUDGET_CELLS", "4000000")
     monkeypatch.setenv("SA_VERBOSE", "1")
+    monkeypatch.setenv("SA_ROUNDS_ARENA_BYTES", "20000000")
     n = cc.run_bin(cc.NEW_BIN, tmp_path / "new", seg_f, con_f, flags + ["-ngpus=1"])
     assert n.returncode == 0, n.stderr[-2000:]
     only_ref, only_new, diff, n_files = cc.compare_dirs(tmp_path / "ref", tmp_path / "new")
     assert not only_ref and not only_new and not diff, (only_ref[:5], only_new[:5], diff[:5])
     assert n_files > 300
+    loops = [int(l.split()[3]) for l in n.stderr.splitlines() if l.strip().startswith("device-resident alignment loop:")]
+    chunks = [l for l in n.stderr.splitlines() if "sa_align_rounds chunk" in l]
+    assert len(loops) == 2 and max(loops) > 100000, f"device-resident loop sizes {loops}: the big-batch branches were not taken"
+    assert len(chunks) > 3, "the path arena was not chunked"
+    monkeypatch.delenv("SA_ROUNDS_ARENA_BYTES")
+    monkeypatch.setenv("SA_NO_ROUNDS", "1")
+    monkeypatch.setenv("SA_STORE_BUDGET_CELLS", "4000000")
+    n = cc.run_bin(cc.NEW_BIN, tmp_path / "old", seg_f, con_f, flags + ["-ngpus=1"])
+    assert n.returncode == 0, n.stderr[-2000:]
+    only_ref, only_new, diff, n_files = cc.compare_dirs(tmp_path / "ref", tmp_path / "old")
+    assert not only_ref and not only_new and not diff, (only_ref[:5], only_new[:5], diff[:5])
     rounds = [int(l.split()[2]) for l in n.stderr.splitlines() if l.strip().startswith("alignment round:")]
     chunks = [l for l in n.stderr.splitlines() if "sa_align_batch chunk" in l]
     assert max(rounds) > 100000, f"largest alignment round has {max(rounds)} pairs: the big-batch branches were not taken"

@@ -1,0 +1,152 @@
+"""GPU parity of sa_align_rounds -- the whole per-pair loop of run_SA_aln (/root/reference/SegAligner/main.cpp:262-300) on the
+device, later rounds re-sweeping only the rows the previous path can influence -- against the oracle run round by round with
+FULL matrices: every round's backtrack start, score bits, traceback and scores along it must be identical, and so must the
+number of rounds (acceptance rule `best > exp_thresh`, compute_partial_score_threshold in fp32, max_alns cap)."""
+import numpy as np
+import pytest
+
+import helpers
+from ampliconreconstructorom_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def reference_rounds(oracle, b, x, bp, xp, thr, max_alns, seed):
+    """run_SA_aln's while loop (main.cpp:268-300) with the oracle's full-matrix dp_align per round."""
+    b32 = np.asarray(b, dtype=np.float32)
+    nb = b32.size - 1
+    used = set(seed)
+    count = 0
+    thr = f32(thr)
+    curr_best, exp_thresh = thr, thr
+    out = []
+    while curr_best >= exp_thresh and count < max_alns:
+        S, prev = oracle.fill(b, x, bp, xp, 0, 0, 6, sorted(used) if used else None, 0)
+        st = oracle.start(S, 0)
+        oj, oq, os_ = oracle.traceback(S, prev, *st)
+        first_lab, last_lab = int(oj[-1]), int(oj[0])
+        by_lab = thr * (f32(last_lab - first_lab + 1) / f32(nb))
+        by_len = thr * ((b32[last_lab] - b32[first_lab]) / b32[nb])
+        exp_thresh = max(by_lab, by_len)
+        curr_best = S[st]
+        out.append((curr_best, st, oj, oq, os_))
+        if curr_best > exp_thresh:
+            count += 1
+            used |= set(int(v) for v in oj)
+        else:
+            break
+    return out
+
+
+def make_pairs(rng, n_pairs, nb_range, nx_range):
+    g = synth.genome_positions(rng, 30_000)
+    contigs, segs = {}, {}
+    for k in range(n_pairs):
+        nb = int(rng.integers(*nb_range))
+        nx = int(rng.integers(*nx_range))
+        s0 = int(rng.integers(10, 29_000 - nb))
+        contigs[k + 1] = synth.noisy_contig(rng, g, s0, nb)
+        # the segment lies inside the contig's window (a real alignment exists), sometimes twice over (repeat -> later rounds)
+        segs[k + 1] = synth.window_map(g, s0 + int(rng.integers(0, max(nb - nx, 1))), nx)
+        if k % 5 == 0:
+            contigs[k + 1] = np.round(contigs[k + 1])  # integer positions: exact ties
+    return contigs, segs
+
+
+def upload(ctx, maps, probs, side):
+    ids = sorted(maps)
+    off = np.zeros(len(ids) + 1, dtype=np.int64)
+    for k, i in enumerate(ids):
+        off[k + 1] = off[k] + len(maps[i])
+    ctx.set_maps(side, off, np.concatenate([maps[i] for i in ids]).astype(np.float32),
+                 np.concatenate([probs[i] for i in ids]).astype(np.float32))
+    return ids
+
+
+def check(ctx, oracle, contigs, segs, cids, sids, cp, sp, pr, thr, max_alns, seeds, env_note=""):
+    words = (max(len(contigs[c]) for c in cids) + 31) // 32
+    used_bits = None
+    if seeds is not None:
+        used_bits = np.zeros((pr.size, words), dtype=np.uint32)
+        for k, u in enumerate(seeds):
+            for j in u:
+                used_bits[k, j >> 5] |= np.uint32(1 << (j & 31))
+        pr = pr.copy()
+        pr["used_slot"] = np.arange(pr.size)
+    mode = ctx.mode(capi.SA_INIT_SEMIGLOBAL, capi.SA_START_SEMIGLOBAL, 0, 6, 0)
+    nr, rounds, pj, pq, ps = ctx.align_rounds(mode, pr, thr, max_alns, None if used_bits is None else used_bits.ravel(), words)
+    n_multi = 0
+    for k in range(pr.size):
+        c, s = int(pr["contig"][k]), int(pr["seg"][k])
+        exp = reference_rounds(oracle, contigs[cids[c]], segs[sids[s]], cp[cids[c]], sp[sids[s]], thr[k], max_alns,
+                               seeds[k] if seeds is not None else [])
+        assert nr[k] == len(exp), f"pair {k}{env_note}: {nr[k]} rounds on the device, {len(exp)} in the reference loop"
+        n_multi += len(exp) > 1
+        for r, (best, st, oj, oq, os_) in enumerate(exp):
+            rec = rounds[k, r]
+            assert (int(rec["j"]), int(rec["q"])) == st, f"pair {k} round {r}: start {(rec['j'], rec['q'])} vs {st}"
+            assert bits(rec["score"]) == bits(best)
+            L, o = int(rec["path_len"]), int(rec["path_off"])
+            assert L == oj.size
+            assert np.array_equal(pj[o:o + L], oj) and np.array_equal(pq[o:o + L], oq)
+            assert np.array_equal(bits(ps[o:o + L]), bits(os_))
+    return n_multi
+
+
+@pytest.mark.parametrize("gen", [1, 2])
+def test_rounds_match_full_matrix_reference_loop(ctx, oracle, gen):
+    rng = np.random.default_rng(500 + gen)
+    contigs, segs = make_pairs(rng, 36, (40, 420), (4, 45))
+    cp, sp = oracle.probs(contigs, gen), oracle.probs(segs, gen)
+    cids = upload(ctx, contigs, cp, capi.SA_SIDE_CONTIG)
+    sids = upload(ctx, segs, sp, capi.SA_SIDE_SEG)
+    # every contig against its own segment and two others
+    cc = np.repeat(np.arange(len(cids)), 3)
+    ss = (cc + np.tile([0, 7, 19], len(cids))) % len(sids)
+    pr = ctx.problems(cc, ss)
+    mode = ctx.mode(capi.SA_INIT_SEMIGLOBAL, capi.SA_START_SEMIGLOBAL, 0, 6, 0)
+    first = ctx.score_batch(mode, pr)["score"]
+    thr = (first * rng.uniform(0.05, 1.6, size=pr.size)).astype(np.float32)
+    thr[3] = np.nan        # NaN threshold: the loop never starts
+    thr[5] = first[5]      # best == thr on round 1: exp_thresh <= thr, so round 1 is accepted unless the path spans the contig
+    n_multi = check(ctx, oracle, contigs, segs, cids, sids, cp, sp, pr, thr, 6, None)
+    assert n_multi > 20, "too few pairs ran more than one round: the windowed re-sweep is not exercised"
+    # tip-phase form: seed bitmaps (labels already taken), gen-2 standard cap of 12 rounds
+    seeds = [sorted(set(rng.integers(0, len(contigs[cids[int(c)]]) - 1, size=int(rng.integers(0, 12))).tolist())) for c in pr["contig"]]
+    check(ctx, oracle, contigs, segs, cids, sids, cp, sp, pr, thr, 12, seeds)
+
+
+def test_rounds_scratch_and_arena_limits(ctx, oracle, monkeypatch):
+    """Pairs whose matrix exceeds the per-worker scratch come back with n_rounds = -1 (the caller falls back to
+    sa_align_batch_packed rounds); a small path arena splits the batch into chunks without changing any result."""
+    rng = np.random.default_rng(77)
+    contigs, segs = make_pairs(rng, 24, (60, 300), (6, 30))
+    cp, sp = oracle.probs(contigs, 2), oracle.probs(segs, 2)
+    cids = upload(ctx, contigs, cp, capi.SA_SIDE_CONTIG)
+    sids = upload(ctx, segs, sp, capi.SA_SIDE_SEG)
+    pr = ctx.problems(np.arange(24), np.arange(24))
+    mode = ctx.mode(capi.SA_INIT_SEMIGLOBAL, capi.SA_START_SEMIGLOBAL, 0, 6, 0)
+    first = ctx.score_batch(mode, pr)["score"]
+    thr = (first * 0.2).astype(np.float32)
+    base = ctx.align_rounds(mode, pr, thr, 6)
+    monkeypatch.setenv("SA_ROUNDS_ARENA_BYTES", "4000")
+    small = ctx.align_rounds(mode, pr, thr, 6)
+    assert np.array_equal(base[0], small[0])
+    for k in range(24):
+        for r in range(base[0][k]):
+            a, b = base[1][k, r], small[1][k, r]
+            assert (a["j"], a["q"], a["path_len"]) == (b["j"], b["q"], b["path_len"]) and bits(a["score"]) == bits(b["score"])
+            assert np.array_equal(base[2][a["path_off"]:a["path_off"] + a["path_len"]], small[2][b["path_off"]:b["path_off"] + b["path_len"]])
+    monkeypatch.delenv("SA_ROUNDS_ARENA_BYTES")
+    cells = np.array([(len(contigs[cids[k]]) - 1) * (len(segs[sids[k]]) - 1) for k in range(24)])
+    cut = float(np.median(cells)) + 0.25
+    workers = 8 * ((24 + 7) // 8)
+    monkeypatch.setenv("SA_ROUNDS_SCRATCH_BYTES", str((cut + 65536.0) * 2.2 * workers))
+    nr = ctx.align_rounds(mode, pr, thr, 6)[0]
+    assert np.array_equal(nr == -1, cells > cut), "the scratch cap did not reject exactly the oversized pairs"
+    assert np.array_equal(nr[cells <= cut], base[0][cells <= cut])
