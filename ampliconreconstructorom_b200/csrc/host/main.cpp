@@ -20,9 +20,12 @@
 #include <map>
 #include <set>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <unordered_map>
 #include <vector>
+#include <sched.h>
+#include <sys/wait.h>
 #include <unistd.h>
 #include "cmap.h"
 #include "segaligner_b200.h"
@@ -97,266 +100,187 @@ void parse_args(int argc, char **argv, Options &o) {
     }
 }
 
-// ---- multi-GPU engine: one context + one host thread per device, problems dealt largest-first ----------------
-struct Engine {
-    std::vector<sa_ctx *> ctx;
-    const MapSet *contigs = nullptr, *segs = nullptr;
+// ---- one process per GPU -------------------------------------------------------------------------------------------
+// A multi-GPU run is SPMD: main() forks one process per GPU BEFORE the first CUDA call, each process sees exactly one device
+// (CUDA_VISIBLE_DEVICES), parses the inputs itself and runs the same run_job; they differ only in which shard of every
+// problem list they compute (problems sharded by index, no device collective -- the problems are independent).  Driver
+// initialisation then costs what it costs for ONE device, in parallel, instead of enumerating every GPU of the box in one
+// process (measured: 5-6 s on an 8-GPU box), and the host work of the alignment passes (replay, filters, ~10^4 output files)
+// is spread over the processes too.  The three exchange points of SURVEY.md 8(e) go through a MAP_SHARED region created
+// before the fork: (1) all phase-1 scores, (2) the used contig labels after the standard alignment pass, (3) the end.
+struct SpmdCtl {  // first page of the shared region
+    std::atomic<int> arrived, generation, error;
+    std::atomic<unsigned long long> h2d, d2h;
+};
+struct Spmd {
+    int rank = 0, world = 1;  // world starts as the number of processes forked and may shrink to 1 for small runs
+    SpmdCtl *ctl = nullptr;
+    char *region = nullptr;
+    size_t region_bytes = 0, top = 4096;
+    std::vector<pid_t> kids;  // rank 0 only
 
-    void die(sa_ctx *c, const char *what, int rc) {
-        fprintf(stderr, "SegAligner(b200): %s failed (%d): %s\n", what, rc, c ? sa_last_error(c) : "");
+    // Sense-reversing barrier over the first `world` ranks.  A rank that fails sets ctl->error, which releases everybody
+    // else with exit code 2; rank 0 also notices children that died without saying so.
+    void barrier() {
+        if (world <= 1) return;
+        const int gen = ctl->generation.load();
+        if (ctl->arrived.fetch_add(1) + 1 == world) {
+            ctl->arrived.store(0);
+            ctl->generation.fetch_add(1);
+            return;
+        }
+        for (unsigned spin = 0; ctl->generation.load() == gen; spin++) {
+            if (ctl->error.load()) throw JobExit{2, true};
+            if (rank == 0 && (spin & 1023) == 1023) {
+                for (pid_t k : kids) {
+                    int st = 0;
+                    if (waitpid(k, &st, WNOHANG) == k && !(WIFEXITED(st) && WEXITSTATUS(st) == 0)) {
+                        ctl->error.store(1);
+                        fprintf(stderr, "SegAligner(b200): a GPU worker process died\n");
+                        throw JobExit{2, true};
+                    }
+                }
+            }
+            if (spin < 2000) sched_yield();
+            else usleep(100);
+        }
+        if (ctl->error.load()) throw JobExit{2, true};
+    }
+    // Bump allocation inside the shared region; every rank calls it with the same sizes in the same order, so they all
+    // get the same offsets without talking to each other.
+    template <class T>
+    T *alloc(size_t n) {
+        top = (top + 63) & ~(size_t)63;
+        const size_t at = top;
+        top += n * sizeof(T);
+        if (world > 1 && top > region_bytes) {
+            fprintf(stderr, "SegAligner(b200): the inter-process exchange region (%zu bytes) is too small\n", region_bytes);
+            throw JobExit{2, true};
+        }
+        return reinterpret_cast<T *>(region + at);
+    }
+};
+
+// shard[g] = indices of the problems rank g handles.  Problems are dealt round-robin WITHIN size classes (1/4-octave of
+// cells), largest classes first, so every GPU gets the same mix of sizes in O(n) (the library orders each shard
+// largest-first itself); a full sort of 10^7 problems would cost more than their scoring.  Deterministic: every rank
+// computes the same partition.
+std::vector<int64_t> my_shard(const std::vector<sa_problem> &pr, const MapSet &contigs, const MapSet &segs, int world, int rank) {
+    std::vector<int64_t> mine;
+    if (world <= 1) {
+        mine.resize(pr.size());
+        for (size_t k = 0; k < pr.size(); k++) mine[k] = (int64_t)k;
+        return mine;
+    }
+    const int NB = 4 * 64;
+    std::vector<uint8_t> cls(pr.size());
+    std::vector<int64_t> cnt((size_t)NB + 1, 0);
+    for (size_t k = 0; k < pr.size(); k++) {
+        const double cells = (double)contigs.labels(pr[k].contig) * (double)segs.labels(pr[k].seg);
+        int b = cells > 1.0 ? (int)(std::log2(cells) * 4.0) : 0;
+        b = NB - 1 - std::min(b, NB - 1);  // descending size
+        cls[k] = (uint8_t)b;
+        cnt[(size_t)b + 1]++;
+    }
+    for (int b = 0; b < NB; b++) cnt[(size_t)b + 1] += cnt[(size_t)b];
+    mine.reserve(pr.size() / (size_t)world + 1);
+    for (size_t k = 0; k < pr.size(); k++) {
+        const int64_t r = cnt[cls[k]]++;  // position in the size-class order
+        if (r % world == rank) mine.push_back((int64_t)k);
+    }
+    return mine;
+}
+
+// ---- this process's GPU: one context behind the C ABI ----------------------------------------------------------------
+struct Engine {
+    sa_ctx *ctx = nullptr;
+
+    void die(const char *what, int rc) {
+        fprintf(stderr, "SegAligner(b200): %s failed (%d): %s\n", what, rc, ctx ? sa_last_error(ctx) : "");
         throw JobExit{2, true};
     }
-    // SA_GPU_OVERSUBSCRIBE=1 (testing aid): -ngpus=N may exceed the visible devices; context g then lives on device
-    // g % visible, so the sharded multi-GPU path (shard / score / align below) can be exercised on a one-GPU box.
-    static bool oversubscribe() {
-        const char *e = getenv("SA_GPU_OVERSUBSCRIBE");
-        return e && atoi(e) != 0;
-    }
-    void open_range(int have, int n, int avail) {
-        ctx.resize((size_t)n, nullptr);
-        std::vector<std::thread> th;
-        std::vector<int> rcs((size_t)n, 0);
-        for (int g = have; g < n; g++) th.emplace_back([&, g]() { rcs[(size_t)g] = sa_ctx_create(g % avail, &ctx[(size_t)g]); });
-        for (auto &t : th) t.join();
-        for (int g = have; g < n; g++)
-            if (rcs[(size_t)g]) die(nullptr, "sa_ctx_create (need an sm_100 GPU)", rcs[(size_t)g]);
-    }
-    void open(int n) {
-        if (!ctx.empty()) return;  // resident server: contexts stay open between jobs
-        const int avail = sa_device_count();
-        if (avail <= 0) {
+    void open() {
+        if (ctx) return;  // resident server: the context stays open between jobs
+        if (sa_device_count() <= 0) {
             fprintf(stderr, "SegAligner(b200): no CUDA device visible; this build has no CPU fallback\n");
             throw JobExit{2, true};
         }
-        n = std::max(1, oversubscribe() ? std::min(n, 64) : std::min(n, avail));
-        open_range(0, n, avail);
-    }
-    void open_more(int n) {  // device 0 is already open; add devices 1..n-1
-        const int avail = sa_device_count();
-        n = std::max(1, oversubscribe() ? std::min(n, 64) : std::min(n, avail));
-        const int have = (int)ctx.size();
-        if (n <= have) return;
-        open_range(have, n, avail);
+        const int rc = sa_ctx_create(0, &ctx);
+        if (rc) {
+            ctx = nullptr;
+            die("sa_ctx_create (need an sm_100 GPU)", rc);
+        }
     }
     void close() {
-        for (auto c : ctx) sa_ctx_destroy(c);
-        ctx.clear();
+        if (ctx) sa_ctx_destroy(ctx);
+        ctx = nullptr;
     }
     void set_maps(const MapSet &c, const MapSet &s) {
-        contigs = &c;
-        segs = &s;
-        parallel([&](int g) {
-            int rc = sa_set_maps(ctx[(size_t)g], SA_SIDE_CONTIG, c.n_maps(), c.off.data(), c.pos.data(), c.prob.data());
-            if (rc) die(ctx[(size_t)g], "sa_set_maps(contigs)", rc);
-            rc = sa_set_maps(ctx[(size_t)g], SA_SIDE_SEG, s.n_maps(), s.off.data(), s.pos.data(), s.prob.data());
-            if (rc) die(ctx[(size_t)g], "sa_set_maps(segments)", rc);
-        });
+        int rc = sa_set_maps(ctx, SA_SIDE_CONTIG, c.n_maps(), c.off.data(), c.pos.data(), c.prob.data());
+        if (rc) die("sa_set_maps(contigs)", rc);
+        rc = sa_set_maps(ctx, SA_SIDE_SEG, s.n_maps(), s.off.data(), s.pos.data(), s.prob.data());
+        if (rc) die("sa_set_maps(segments)", rc);
     }
-    // f(g) on one host thread per GPU.  die() throws JobExit; an exception must not escape a std::thread (that would be
-    // std::terminate instead of the documented exit code 2), so each worker parks its JobExit and the first one is
-    // rethrown on the calling thread after the join.
-    template <class F>
-    void parallel(F f) {
-        if (ctx.size() == 1) {
-            f(0);
-            return;
-        }
-        std::vector<std::thread> th;
-        std::vector<JobExit> errs(ctx.size(), JobExit{0, false});
-        for (int g = 0; g < (int)ctx.size(); g++)
-            th.emplace_back([&, g]() {
-                try {
-                    f(g);
-                } catch (const JobExit &e) {
-                    errs[(size_t)g] = e.code ? e : JobExit{2, true};
-                }
-            });
-        for (auto &t : th) t.join();
-        for (const JobExit &e : errs)
-            if (e.code) throw e;
-    }
-    // shard[g] = indices of the problems GPU g handles.  Problems are dealt round-robin WITHIN size classes
-    // (1/4-octave of cells), largest classes first, so every GPU gets the same mix of sizes in O(n) (the library
-    // orders each shard largest-first itself); a full sort of 10^7 problems would cost more than their scoring.
-    std::vector<std::vector<int64_t>> shard(const std::vector<sa_problem> &pr) const {
-        const int G = (int)ctx.size();
-        std::vector<std::vector<int64_t>> sh((size_t)G);
-        if (G == 1) {
-            sh[0].resize(pr.size());
-            for (size_t k = 0; k < pr.size(); k++) sh[0][k] = (int64_t)k;
-            return sh;
-        }
-        const int NB = 4 * 64;
-        std::vector<uint8_t> cls(pr.size());
-        std::vector<int64_t> cnt((size_t)NB + 1, 0);
-        for (size_t k = 0; k < pr.size(); k++) {
-            const double cells = (double)contigs->labels(pr[k].contig) * (double)segs->labels(pr[k].seg);
-            int b = cells > 1.0 ? (int)(std::log2(cells) * 4.0) : 0;
-            b = NB - 1 - std::min(b, NB - 1);  // descending size
-            cls[k] = (uint8_t)b;
-            cnt[(size_t)b + 1]++;
-        }
-        for (int b = 0; b < NB; b++) cnt[(size_t)b + 1] += cnt[(size_t)b];
-        std::vector<int64_t> rank(pr.size());  // position in the size-class order
-        for (size_t k = 0; k < pr.size(); k++) rank[k] = cnt[cls[k]]++;
-        for (auto &v : sh) v.reserve(pr.size() / (size_t)G + 1);
-        std::vector<int64_t> by_rank(pr.size());
-        for (size_t k = 0; k < pr.size(); k++) by_rank[(size_t)rank[k]] = (int64_t)k;
-        for (size_t r = 0; r < by_rank.size(); r++) sh[r % (size_t)G].push_back(by_rank[r]);
-        return sh;
-    }
-
     void score(const sa_mode &mode, const std::vector<sa_problem> &pr, std::vector<sa_result> &res) {
         res.assign(pr.size(), sa_result{0, -1, -1, 0});
         if (pr.empty()) return;
-        auto sh = shard(pr);
-        parallel([&](int g) {
-            const auto &idx = sh[(size_t)g];
-            if (idx.empty()) return;
-            std::vector<sa_problem> p(idx.size());
-            std::vector<sa_result> r(idx.size());
-            for (size_t k = 0; k < idx.size(); k++) p[k] = pr[(size_t)idx[k]];
-            int rc = sa_score_batch(ctx[(size_t)g], &mode, p.data(), (int64_t)p.size(), r.data());
-            if (rc) die(ctx[(size_t)g], "sa_score_batch", rc);
-            for (size_t k = 0; k < idx.size(); k++) res[(size_t)idx[k]] = r[k];
-        });
+        const int rc = sa_score_batch(ctx, &mode, pr.data(), (int64_t)pr.size(), res.data());
+        if (rc) die("sa_score_batch", rc);
     }
-
-    // detection scoring: out[k] = the scores multi_backtrack_scores harvests for problem k, in order
-    void detect(const sa_mode &mode, const std::vector<sa_problem> &pr, const std::vector<int32_t> &n_want,
-                std::vector<std::vector<float>> &out) {
-        out.assign(pr.size(), {});
-        if (pr.empty()) return;
-        auto sh = shard(pr);
-        parallel([&](int g) {
-            const auto &idx = sh[(size_t)g];
-            if (idx.empty()) return;
-            const size_t m = idx.size();
-            std::vector<sa_problem> p(m);
-            std::vector<int32_t> want(m), got(m);
-            std::vector<int64_t> off(m + 1, 0);
-            for (size_t k = 0; k < m; k++) {
-                p[k] = pr[(size_t)idx[k]];
-                want[k] = n_want[(size_t)idx[k]];
-                off[k + 1] = off[k] + want[k];
-            }
-            std::vector<float> sc((size_t)std::max<int64_t>(off[m], 1));
-            int rc = sa_detect_batch(ctx[(size_t)g], &mode, p.data(), (int64_t)m, want.data(), off.data(), sc.data(), got.data());
-            if (rc) die(ctx[(size_t)g], "sa_detect_batch", rc);
-            for (size_t k = 0; k < m; k++) out[(size_t)idx[k]].assign(sc.begin() + off[k], sc.begin() + off[k] + got[k]);
-        });
+    // detection scoring: sc[off[k] .. off[k] + got[k]) = the scores multi_backtrack_scores harvests for problem k, in order
+    void detect(const sa_mode &mode, const std::vector<sa_problem> &pr, const std::vector<int32_t> &want, std::vector<int64_t> &off,
+                std::vector<float> &sc, std::vector<int32_t> &got) {
+        const size_t m = pr.size();
+        off.assign(m + 1, 0);
+        for (size_t k = 0; k < m; k++) off[k + 1] = off[k] + want[k];
+        sc.assign((size_t)std::max<int64_t>(off[m], 1), 0.0f);
+        got.assign(m, 0);
+        if (m == 0) return;
+        const int rc = sa_detect_batch(ctx, &mode, pr.data(), (int64_t)m, want.data(), off.data(), sc.data(), got.data());
+        if (rc) die("sa_detect_batch", rc);
     }
-
-    // alignment: out.get(k) = result and traceback (end->start) of problem k, read in place from the pinned buffers
-    // of the context that computed it (valid until the next align call).
+    // alignment: out.get(k) = result and traceback (end->start) of problem k, read in place from the context's pinned
+    // buffers (valid until the next align call).
     struct AlignOut {
         struct View {
             const sa_result *res;
             const int32_t *pj, *pq;
             const float *ps;
         };
-        std::vector<sa_packed_paths> pk;        // per GPU
-        std::vector<std::vector<int64_t>> idx;  // per GPU: the problems it handled (empty for a single GPU)
-        std::vector<int32_t> gpu_of;            // per problem (multi-GPU only)
-        std::vector<int64_t> local_of;
-        View get(size_t k) const {
-            const size_t g = gpu_of.empty() ? 0 : (size_t)gpu_of[k];
-            const size_t l = gpu_of.empty() ? k : (size_t)local_of[k];
-            const sa_packed_paths &p = pk[g];
-            return View{p.results + l, p.path_j + p.start[l], p.path_q + p.start[l], p.path_s + p.start[l]};
-        }
+        sa_packed_paths pk{};
+        View get(size_t k) const { return View{pk.results + k, pk.path_j + pk.start[k], pk.path_q + pk.start[k], pk.path_s + pk.start[k]}; }
     };
     // pr[k].used_slot = WORD offset of the problem's skip bitmap inside `arena` (or -1): the C ABI is used with one
     // word per slot, so bitmaps of different lengths sit packed and the arena is uploaded as it is.
     void align(const sa_mode &mode, std::vector<sa_problem> &pr, const std::vector<uint32_t> &arena, AlignOut &out) {
-        const size_t n = pr.size();
-        const size_t G = ctx.size();
-        out.pk.assign(G, sa_packed_paths{});
-        out.idx.clear();
-        out.gpu_of.clear();
-        out.local_of.clear();
-        if (n == 0) return;
-        const uint32_t *bits = arena.empty() ? nullptr : arena.data();
-        const int64_t n_words = (int64_t)arena.size();
-        if (G == 1) {
-            int rc = sa_align_batch_packed(ctx[0], &mode, pr.data(), (int64_t)n, bits, 1, n_words, &out.pk[0]);
-            if (rc) die(ctx[0], "sa_align_batch_packed", rc);
-            return;
-        }
-        out.idx = shard(pr);
-        out.gpu_of.resize(n);
-        out.local_of.resize(n);
-        parallel([&](int g) {
-            const auto &idx = out.idx[(size_t)g];
-            if (idx.empty()) return;
-            std::vector<sa_problem> p(idx.size());
-            for (size_t k = 0; k < idx.size(); k++) {
-                p[k] = pr[(size_t)idx[k]];
-                out.gpu_of[(size_t)idx[k]] = g;
-                out.local_of[(size_t)idx[k]] = (int64_t)k;
-            }
-            int rc = sa_align_batch_packed(ctx[(size_t)g], &mode, p.data(), (int64_t)p.size(), bits, 1, n_words, &out.pk[(size_t)g]);
-            if (rc) die(ctx[(size_t)g], "sa_align_batch_packed", rc);
-        });
+        out.pk = sa_packed_paths{};
+        if (pr.empty()) return;
+        const int rc = sa_align_batch_packed(ctx, &mode, pr.data(), (int64_t)pr.size(), arena.empty() ? nullptr : arena.data(), 1,
+                                             (int64_t)arena.size(), &out.pk);
+        if (rc) die("sa_align_batch_packed", rc);
     }
-
-    // Device-resident alignment loop (sa_align_rounds): every round of every pair in one call per GPU.  out.nr(k) = number
-    // of rounds of pair k (-1: the pair did not fit the device scratch, the caller runs it through align()).
+    // Device-resident alignment loop (sa_align_rounds): every round of every pair in one call.  out.nr(k) = number of
+    // rounds of pair k (-1: the pair did not fit the device scratch, the caller runs it through align()).
     struct RoundsOut {
-        std::vector<sa_rounds_out> ro;  // per GPU
-        std::vector<int32_t> gpu_of;    // per pair (multi-GPU only)
-        std::vector<int64_t> local_of;
-        int max_alns = 0;
-        int nr(size_t k) const {
-            const size_t g = gpu_of.empty() ? 0 : (size_t)gpu_of[k];
-            const size_t l = gpu_of.empty() ? k : (size_t)local_of[k];
-            return ro[g].n_rounds[l];
-        }
+        sa_rounds_out ro{};
+        int nr(size_t k) const { return ro.n_rounds[k]; }
         struct View {
             const sa_round *rec;
             const int32_t *pj, *pq;
             const float *ps;
         };
         View get(size_t k, int r) const {
-            const size_t g = gpu_of.empty() ? 0 : (size_t)gpu_of[k];
-            const size_t l = gpu_of.empty() ? k : (size_t)local_of[k];
-            const sa_rounds_out &o = ro[g];
-            const sa_round *rec = o.rounds + l * (size_t)max_alns + (size_t)r;
-            return View{rec, o.path_j + rec->path_off, o.path_q + rec->path_off, o.path_s + rec->path_off};
+            const sa_round *rec = ro.rounds + k * (size_t)ro.max_alns + (size_t)r;
+            return View{rec, ro.path_j + rec->path_off, ro.path_q + rec->path_off, ro.path_s + rec->path_off};
         }
     };
     void align_rounds(const sa_mode &mode, const std::vector<sa_problem> &pr, const std::vector<float> &thr, int max_alns,
                       const std::vector<uint32_t> &arena, RoundsOut &out) {
-        const size_t n = pr.size(), G = ctx.size();
-        out.ro.assign(G, sa_rounds_out{});
-        out.gpu_of.clear();
-        out.local_of.clear();
-        out.max_alns = max_alns;
-        if (n == 0) return;
-        const uint32_t *bits = arena.empty() ? nullptr : arena.data();
-        const int64_t n_words = (int64_t)arena.size();
-        if (G == 1) {
-            int rc = sa_align_rounds(ctx[0], &mode, pr.data(), (int64_t)n, thr.data(), max_alns, bits, 1, n_words, &out.ro[0]);
-            if (rc) die(ctx[0], "sa_align_rounds", rc);
-            return;
-        }
-        auto sh = shard(pr);
-        out.gpu_of.resize(n);
-        out.local_of.resize(n);
-        parallel([&](int g) {
-            const auto &idx = sh[(size_t)g];
-            if (idx.empty()) return;
-            std::vector<sa_problem> p(idx.size());
-            std::vector<float> t(idx.size());
-            for (size_t k = 0; k < idx.size(); k++) {
-                p[k] = pr[(size_t)idx[k]];
-                t[k] = thr[(size_t)idx[k]];
-                out.gpu_of[(size_t)idx[k]] = g;
-                out.local_of[(size_t)idx[k]] = (int64_t)k;
-            }
-            int rc = sa_align_rounds(ctx[(size_t)g], &mode, p.data(), (int64_t)p.size(), t.data(), max_alns, bits, 1, n_words, &out.ro[(size_t)g]);
-            if (rc) die(ctx[(size_t)g], "sa_align_rounds", rc);
-        });
+        out.ro = sa_rounds_out{};
+        if (pr.empty()) return;
+        const int rc = sa_align_rounds(ctx, &mode, pr.data(), (int64_t)pr.size(), thr.data(), max_alns, arena.empty() ? nullptr : arena.data(),
+                                       1, (int64_t)arena.size(), &out.ro);
+        if (rc) die("sa_align_rounds", rc);
     }
 };
 
@@ -483,8 +407,9 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
         eng.align_rounds(mode, rp, rthr, max_alns, arena, ro);
         const double t_r1 = wall_now();
         const size_t n_pairs = st.size();
+        // replay + file writing: a worker per 4096 pairs (a standard pass writes about one file per pair)
         const int n_workers = (int)std::max<size_t>(1, std::min<size_t>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u),
-                                                                        n_pairs / 50000 + 1));
+                                                                        n_pairs / 4096 + 1));
         std::vector<std::vector<std::pair<int, int>>> disc((size_t)n_workers);
         std::vector<int> bad((size_t)n_workers, 0);
         size_t n_fallback = 0;
@@ -659,9 +584,10 @@ struct PhaseTimer {  // SA_VERBOSE=1: per-phase wall times on stderr
 
 }  // namespace
 
-// One SegAligner run (the body of the reference's main, main.cpp:453-656).  `eng` may already hold open contexts
-// (resident server); `keep_open` leaves them open on return.
-static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
+// One SegAligner run (the body of the reference's main, main.cpp:453-656).  `eng` may already hold an open context
+// (resident server); `keep_open` leaves it open on return.  `sp`: this process's place among the GPU processes of the run
+// (rank 0 alone prints and writes the score files; every rank writes the alignment files of its own pairs).
+static int run_job(int argc, char *argv[], Engine &eng, bool keep_open, Spmd &sp) {
     if (argc < 3) {  // the reference tests argc < 2 and then dereferences argv[2] regardless (main.cpp:454-468)
         printf("wrong number of arguments\n");
         fflush(stdout);
@@ -680,39 +606,27 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
     if (o.inst_gen == 2) o.max_seg_contig_alns *= 2;  // main.cpp:479-481
 
     PhaseTimer pt;
-    // A run that was told to use one GPU hides the others from the CUDA driver before its first CUDA call: driver
-    // initialisation enumerates every visible device, which costs seconds on an 8-GPU box (measured: 5-6 s to open
-    // one context there vs 0.4-2 s on a single-GPU box).  Only when nothing is open yet (not in the resident server).
-    {
-        int want = o.n_gpus;
-        if (want <= 0)
-            if (const char *e = getenv("SA_NGPUS")) want = atoi(e);
-        if (want == 1 && eng.ctx.empty() && !keep_open) {
-            const char *vis = getenv("CUDA_VISIBLE_DEVICES");
-            std::string first = "0";
-            if (vis && *vis) {
-                first = vis;
-                const size_t comma = first.find(',');
-                if (comma != std::string::npos) first.resize(comma);
-            }
-            setenv("CUDA_VISIBLE_DEVICES", first.c_str(), 1);
-        }
-    }
-    // CUDA start-up (driver init + context, ~0.3 s) overlaps with CMAP parsing: open device 0 right away
+    pt.on = pt.on && sp.rank == 0;
+    // CUDA start-up (driver init + context, ~0.3-0.6 s for the one device this process sees) overlaps with CMAP parsing.
+    // Rank 0 starts it right away; the other ranks wait until they know the run is big enough to need them.
     JobExit open_err{0, false};
-    std::thread gpu_open([&eng, &open_err]() {
-        try {
-            eng.open(1);
-        } catch (const JobExit &e) {
-            open_err = e;
-        }
-    });
+    std::thread gpu_open;
+    auto start_open = [&]() {
+        gpu_open = std::thread([&eng, &open_err]() {
+            try {
+                eng.open();
+            } catch (const JobExit &e) {
+                open_err = e;
+            }
+        });
+    };
     struct Joiner {  // the opener thread must be joined on every exit path (exceptions included)
         std::thread &t;
         ~Joiner() {
             if (t.joinable()) t.join();
         }
     } joiner{gpu_open};
+    if (sp.rank == 0) start_open();
     MapSet segs_raw, segs, contigs;
     parse_cmap(ref_cmap_file, segs_raw);
     if (!o.fitting_aln) segs = make_reverse_cmap(segs_raw, o.min_map_len);
@@ -731,6 +645,26 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
     }
     printf("Running SegAligner on %d segments and %d contigs.\n", segs.n_maps(), contigs.n_maps());
     fflush(stdout);
+
+    // GPUs: every process that was forked for big runs, one otherwise (a small run is over before a second context is up).
+    // Every rank takes the same decision from the same inputs; the ranks that are not needed leave before touching CUDA.
+    double total_cells = 0;
+    {
+        double sl = 0, cl = 0;
+        for (int m = 0; m < segs.n_maps(); m++) sl += segs.labels(m);
+        for (int m = 0; m < contigs.n_maps(); m++) cl += contigs.labels(m);
+        total_cells = sl * cl;
+    }
+    {
+        int asked = o.n_gpus;
+        if (asked <= 0)
+            if (const char *e = getenv("SA_NGPUS")) asked = atoi(e);
+        if (asked <= 0 && total_cells <= 2e10) sp.world = 1;
+        if (o.fitting_aln || segs.n_maps() == 0 || contigs.n_maps() == 0) sp.world = 1;
+    }
+    if (sp.rank >= sp.world) return 0;
+    if (sp.rank > 0) start_open();
+
     if (segs.n_maps() == 0 || contigs.n_maps() == 0) {
         // nothing to align; the reference still writes the (empty) score files unless -fitting
         if (!o.fitting_aln) {  // same progress lines as the reference's (empty) phases (main.cpp:528-649)
@@ -750,23 +684,9 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
         if (!keep_open) eng.close();
         return 0;
     }
-
-    // GPUs: all visible ones for big runs, one otherwise (context creation costs more than a small run)
-    double total_cells = 0;
-    {
-        double sl = 0, cl = 0;
-        for (int m = 0; m < segs.n_maps(); m++) sl += segs.labels(m);
-        for (int m = 0; m < contigs.n_maps(); m++) cl += contigs.labels(m);
-        total_cells = sl * cl;
-    }
-    int n_gpus = o.n_gpus;
-    if (const char *e = getenv("SA_NGPUS"))
-        if (n_gpus <= 0) n_gpus = atoi(e);
-    if (n_gpus <= 0) n_gpus = total_cells > 2e10 ? sa_device_count() : 1;
     gpu_open.join();
     if (open_err.code) throw open_err;
-    if (n_gpus > 1) eng.open_more(n_gpus);
-    pt.lap("open GPU context(s)");
+    pt.lap("open GPU context");
     eng.set_maps(contigs, segs);
     pt.lap("upload maps");
 
@@ -826,35 +746,71 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
         mode.fitting = 0;
         mode.lookback = o.lookback;
         mode.swap_b_x = o.swap_b_x ? 1 : 0;
+        // this rank scores its shard of the problem list; exchange 1: every rank needs every score for the
+        // thresholds, so the shards meet in the shared region (a private vector when the run has one process)
+        const std::vector<int64_t> mine = my_shard(pr, contigs, segs, sp.world, sp.rank);
+        std::vector<sa_problem> mp(mine.size());
+        for (size_t k = 0; k < mine.size(); k++) mp[k] = pr[(size_t)mine[k]];
         if (o.detection) {
             int total_labels = 0;
             for (int c = 0; c < contigs.n_maps(); c++) total_labels += contigs.size(c);  // main.cpp:118-121
-            std::vector<int32_t> want(pr.size());
+            std::vector<int64_t> off(pr.size() + 1, 0);  // global slots: n_want scores per problem
             for (size_t k = 0; k < pr.size(); k++)
-                want[k] = int(roundf(o.n_detect_scores * float(contigs.size(pr[k].contig)) / float(total_labels))) + 1;
-            std::vector<std::vector<float>> sc;
-            eng.detect(mode, pr, want, sc);
+                off[k + 1] = off[k] + int(roundf(o.n_detect_scores * float(contigs.size(pr[k].contig)) / float(total_labels))) + 1;
+            std::vector<float> own_sc;
+            std::vector<int32_t> own_got;
+            float *all_sc;
+            int32_t *all_got;
+            if (sp.world > 1) {
+                all_sc = sp.alloc<float>((size_t)off[pr.size()]);
+                all_got = sp.alloc<int32_t>(pr.size());
+            } else {
+                own_sc.resize((size_t)off[pr.size()]);
+                own_got.resize(pr.size());
+                all_sc = own_sc.data();
+                all_got = own_got.data();
+            }
+            std::vector<int32_t> want(mp.size()), got;
+            for (size_t k = 0; k < mp.size(); k++) want[k] = (int32_t)(off[(size_t)mine[k] + 1] - off[(size_t)mine[k]]);
+            std::vector<int64_t> loff;
+            std::vector<float> sc;
+            eng.detect(mode, mp, want, loff, sc, got);
+            for (size_t k = 0; k < mp.size(); k++) {
+                std::copy(sc.begin() + loff[k], sc.begin() + loff[k] + got[k], all_sc + off[(size_t)mine[k]]);
+                all_got[(size_t)mine[k]] = got[k];
+            }
+            sp.barrier();
             for (size_t k = 0; k < pr.size(); k++)
-                for (float v : sc[k]) rows.push_back(ScoreRow{segs.ids[(size_t)pr[k].seg], contigs.ids[(size_t)pr[k].contig], v});
+                for (int32_t t = 0; t < all_got[k]; t++)
+                    rows.push_back(ScoreRow{segs.ids[(size_t)pr[k].seg], contigs.ids[(size_t)pr[k].contig], all_sc[off[k] + t]});
         } else {
+            std::vector<float> own;
+            float *all;
+            if (sp.world > 1) all = sp.alloc<float>(pr.size());
+            else {
+                own.resize(pr.size());
+                all = own.data();
+            }
             std::vector<sa_result> res;
-            eng.score(mode, pr, res);
+            eng.score(mode, mp, res);
+            for (size_t k = 0; k < mp.size(); k++) all[(size_t)mine[k]] = res[k].score;
+            sp.barrier();
             rows.reserve(pr.size());
             for (size_t k = 0; k < pr.size(); k++)
-                rows.push_back(ScoreRow{segs.ids[(size_t)pr[k].seg], contigs.ids[(size_t)pr[k].contig], res[k].score});
+                rows.push_back(ScoreRow{segs.ids[(size_t)pr[k].seg], contigs.ids[(size_t)pr[k].contig], all[k]});
         }
     }
     pt.lap("phase 1 scoring (GPU)");
-    write_all_scores(rows, o.sample_prefix);
+    if (sp.rank == 0) write_all_scores(rows, o.sample_prefix);
     pt.lap("write all_scores");
 
-    // ---------------- phase 2: thresholds (main.cpp:555-557) ---------------------------------------------------
+    // ---------------- phase 2: thresholds (main.cpp:555-557); every rank computes the same values ---------------------
     std::vector<std::vector<std::pair<int, float>>> thr2;
     compute_score_thresholds_multi(rows, segs, contigs, {(double)o.p_val, (double)o.p_val_tip}, o.n_detect_scores, thr2);
     const auto &score_thresholds = thr2[0];
     const auto &tip_thresholds = thr2[1];
     printf("Writing scoring distribution.\n");
-    write_score_thresholds(score_thresholds, o.sample_prefix + o.detection_label);
+    if (sp.rank == 0) write_score_thresholds(score_thresholds, o.sample_prefix + o.detection_label);
     printf("Completed generating scores.\n");
     printf("elapsed seconds for scoring %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
     fflush(stdout);
@@ -869,9 +825,60 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
     std::vector<std::pair<int, int>> uniq = pairs_list;
     std::sort(uniq.begin(), uniq.end());
     uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    // Pairs that cannot produce an alignment file are not aligned at all.  A file needs >= 5 labels (tip, -gen=1: >= 3) and a
+    // mean score per step >= 8750 (7000 in the standard pass; 9400 below 5 labels), i.e. a round's best score >= 35000 (18800).
+    // Every round's best score is <= the pair's phase-1 score: both are the maximum of the same semi-global DP, and masking
+    // contig labels only removes candidates (each cell is a max over predecessor + constant; fp32 '+' and max are monotone).
+    // So a pair whose phase-1 score is below that bound can neither write a file nor contribute used labels, in any round;
+    // whether the reference grinds through its rounds or not is unobservable.  Not for -local / -detection, whose alignment
+    // rounds use a different initialisation than phase 1.  (1 % slack for the rounding of the mean's division.)
+    std::vector<float> phase1;  // by (segment idx, contig idx); +inf = unknown
+    float min_file_score = 0.0f;
+    if (!o.local_aln && !getenv("SA_NO_SKIP")) {
+        phase1.assign((size_t)segs.n_maps() * (size_t)contigs.n_maps(), INFINITY);
+        for (size_t k = 0; k < pr.size(); k++) phase1[(size_t)pr[k].seg * (size_t)contigs.n_maps() + (size_t)pr[k].contig] = rows[k].score;
+    }
+    auto can_write_a_file = [&](const std::vector<std::pair<int, int>> &all) {
+        if (phase1.empty()) return all;
+        std::vector<std::pair<int, int>> out;
+        out.reserve(all.size());
+        for (auto &e : all)
+            if (!(phase1[(size_t)e.first * (size_t)contigs.n_maps() + (size_t)e.second] < min_file_score)) out.push_back(e);
+        if (getenv("SA_VERBOSE") && sp.rank == 0)
+            fprintf(stderr, "  %zu of %zu pairs can reach the score an alignment file needs (%.0f); the others are skipped\n", out.size(),
+                    all.size(), (double)min_file_score);
+        return out;
+    };
+    // this rank's share of a pair list (same deterministic partition on every rank)
+    auto my_pairs = [&](const std::vector<std::pair<int, int>> &all) {
+        if (sp.world <= 1) return all;
+        std::vector<sa_problem> as_pr(all.size());
+        for (size_t k = 0; k < all.size(); k++) as_pr[k] = sa_problem{all[k].second, all[k].first, -1, 0};
+        std::vector<std::pair<int, int>> out;
+        for (int64_t k : my_shard(as_pr, contigs, segs, sp.world, sp.rank)) out.push_back(all[(size_t)k]);
+        return out;
+    };
     printf("Performing alignments\n");
     fflush(stdout);
-    std::vector<Bitmap> contig_used = run_alignment_pass(eng, o, segs, contigs, uniq, score_thresholds, nullptr, false);
+    min_file_score = 0.99f * 35000.0f;  // standard pass: >= 6 labels, mean >= 7000 (main.cpp:218-222,249-255,310-325)
+    std::vector<Bitmap> contig_used =
+        run_alignment_pass(eng, o, segs, contigs, my_pairs(can_write_a_file(uniq)), score_thresholds, nullptr, false);
+    if (sp.world > 1) {  // exchange 2 (main.cpp:597-602): union of the labels of the written alignments
+        size_t words = 0;
+        for (auto &b : contig_used) words += b.size();
+        uint32_t *all = sp.alloc<uint32_t>(words * (size_t)sp.world);
+        uint32_t *own = all + words * (size_t)sp.rank;
+        for (auto &b : contig_used) {
+            std::copy(b.begin(), b.end(), own);
+            own += b.size();
+        }
+        sp.barrier();
+        for (int r = 0; r < sp.world; r++) {
+            const uint32_t *src = all + words * (size_t)r;
+            for (auto &b : contig_used)
+                for (auto &w : b) w |= *src++;
+        }
+    }
     printf("Finished standard alignment. \n");
     fflush(stdout);
     pt.lap("phase 3 alignment");
@@ -887,21 +894,26 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
             for (int c : tip_contigs) tip_pairs.emplace_back(s, c);  // every segment (+ and -) x every such contig
         printf("Performing alignments\n");
         fflush(stdout);
-        run_alignment_pass(eng, o, segs, contigs, tip_pairs, tip_thresholds, &contig_used, true);
+        min_file_score = 0.99f * ((o.inst_gen == 1) ? 2.0f * 9400.0f : 4.0f * 8750.0f);  // tip: >= 3 labels at 9400 / >= 5 at 8750
+        run_alignment_pass(eng, o, segs, contigs, my_pairs(can_write_a_file(tip_pairs)), tip_thresholds, &contig_used, true);
         printf("Finished tip alignments.\n\n");
         pt.lap("phase 4 tip alignment");
     }
-    printf("elapsed seconds for run %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
-    if (getenv("SA_VERBOSE")) {
+    {   // exchange 3: the run is over when every rank has written its files
         uint64_t h2d = 0, d2h = 0;
-        for (sa_ctx *c : eng.ctx) {
-            uint64_t a = 0, b = 0;
-            sa_get_traffic(c, &a, &b);
-            h2d += a;
-            d2h += b;
+        sa_get_traffic(eng.ctx, &h2d, &d2h);
+        if (sp.world > 1) {
+            sp.ctl->h2d.fetch_add(h2d);
+            sp.ctl->d2h.fetch_add(d2h);
+            sp.barrier();
+            h2d = sp.ctl->h2d.load();
+            d2h = sp.ctl->d2h.load();
         }
-        fprintf(stderr, "SegAligner(b200): copied H2D %llu bytes, D2H %llu bytes\n", (unsigned long long)h2d, (unsigned long long)d2h);
-        fprintf(stderr, "SegAligner(b200): wall %.3f s on %d GPU(s)\n", wall_now() - w0, (int)eng.ctx.size());
+        printf("elapsed seconds for run %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
+        if (getenv("SA_VERBOSE") && sp.rank == 0) {
+            fprintf(stderr, "SegAligner(b200): copied H2D %llu bytes, D2H %llu bytes\n", (unsigned long long)h2d, (unsigned long long)d2h);
+            fprintf(stderr, "SegAligner(b200): wall %.3f s on %d GPU(s)\n", wall_now() - w0, sp.world);
+        }
     }
     fflush(stdout);
     fflush(stderr);
@@ -924,6 +936,7 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open) {
 #include <poll.h>
 #include <signal.h>
 #include <sys/mman.h>
+#include <sys/prctl.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
 #include <sys/un.h>
@@ -951,6 +964,31 @@ std::string server_socket_path() {
     if (dir.empty()) dir = "/tmp/segaligner_b200_" + std::to_string((long)getuid());
     if (!private_dir_ok(dir)) return "";
     return dir + "/server.sock";
+}
+
+// The GPUs this run may use, as CUDA_VISIBLE_DEVICES tokens, WITHOUT initialising CUDA (that is the expensive step a
+// multi-GPU run wants to do once per process, in parallel): the caller's own CUDA_VISIBLE_DEVICES list, else one entry
+// per /dev/nvidia<N> device node.  Empty when neither exists (CUDA then reports the absence of a device itself).
+std::vector<std::string> visible_devices() {
+    std::vector<std::string> out;
+    if (const char *vis = getenv("CUDA_VISIBLE_DEVICES")) {
+        std::string t;
+        for (const char *c = vis;; c++) {
+            if (*c == ',' || *c == 0) {
+                if (!t.empty()) out.push_back(t);
+                t.clear();
+                if (*c == 0) break;
+            } else {
+                t += *c;
+            }
+        }
+        return out;
+    }
+    for (int n = 0; n < 64; n++) {
+        struct stat sb;
+        if (stat(("/dev/nvidia" + std::to_string(n)).c_str(), &sb) == 0) out.push_back(std::to_string((int)out.size()));
+    }
+    return out;
 }
 
 bool peer_is_me(int fd) {
@@ -1012,20 +1050,11 @@ int connect_server(const std::string &path) {
     umask(077);  // the socket is created 0600: no window between bind() and a later chmod()
     if (ls < 0 || bind(ls, (sockaddr *)&a, sizeof a) != 0 || listen(ls, 64) != 0) _exit(0);  // somebody else serves
     if (const char *e = getenv("SA_SERVER_IDLE")) idle_s = std::max(1, atoi(e));
-    // The server drives one GPU unless its environment asks for more (SA_NGPUS > 1): hiding the other devices before
-    // the first CUDA call saves seconds of driver initialisation on a multi-GPU box (see run_job).
+    // The server drives ONE GPU: hiding the other devices before the first CUDA call saves seconds of driver
+    // initialisation on a multi-GPU box (big multi-GPU runs are not what a resident server is for).
     {
-        const char *ng = getenv("SA_NGPUS");
-        if (!ng || atoi(ng) <= 1) {
-            const char *vis = getenv("CUDA_VISIBLE_DEVICES");
-            std::string first = "0";
-            if (vis && *vis) {
-                first = vis;
-                const size_t comma = first.find(',');
-                if (comma != std::string::npos) first.resize(comma);
-            }
-            setenv("CUDA_VISIBLE_DEVICES", first.c_str(), 1);
-        }
+        const std::vector<std::string> devs = visible_devices();
+        if (!devs.empty()) setenv("CUDA_VISIBLE_DEVICES", devs[0].c_str(), 1);
     }
     Engine eng;
     bool fatal = false;
@@ -1075,7 +1104,8 @@ int connect_server(const std::string &path) {
         av.push_back(nullptr);
         uint32_t code = 0;
         try {
-            code = (uint32_t)run_job((int)args.size(), av.data(), eng, true);
+            Spmd solo;  // the server drives one GPU from one process
+            code = (uint32_t)run_job((int)args.size(), av.data(), eng, true, solo);
         } catch (const JobExit &e) {
             code = (uint32_t)e.code;
             fatal = e.fatal;
@@ -1176,16 +1206,85 @@ int main(int argc, char *argv[]) {
     const char *sv = getenv("SA_SERVER");
     const bool forced = sv && atoi(sv) != 0, forbidden = sv && atoi(sv) == 0;
     bool fitting = false;
-    for (int i = 3; i < argc; i++) fitting = fitting || strcmp(argv[i], "-fitting") == 0;
+    int asked = 0;  // -ngpus=N, else SA_NGPUS, else 0 = all visible GPUs (big runs) / one (small runs), decided after parsing
+    for (int i = 3; i < argc; i++) {
+        fitting = fitting || strcmp(argv[i], "-fitting") == 0;
+        if (strncmp(argv[i], "-ngpus=", 7) == 0) asked = atoi(argv[i] + 7);
+    }
+    if (asked <= 0)
+        if (const char *e = getenv("SA_NGPUS")) asked = atoi(e);
     if (forced || (fitting && !forbidden) || (argc == 2 && strcmp(argv[1], "--server-stop") == 0)) {
         const int rc = run_via_server(argc, argv, forced ? 300 : 30);
         if (rc >= 0) return rc;
     }
-    Engine eng;
-    try {
-        return run_job(argc, argv, eng, false);
-    } catch (const JobExit &e) {
-        fflush(stdout);
-        return e.code;
+    // One process per GPU, forked before the first CUDA call (see Spmd).  SA_GPU_OVERSUBSCRIBE=1 (testing aid): -ngpus=N may
+    // exceed the visible devices; rank r then runs on device r % visible, which exercises the same sharded code on one GPU.
+    const std::vector<std::string> devs = visible_devices();
+    const int n_dev = (int)devs.size();
+    const char *ov = getenv("SA_GPU_OVERSUBSCRIBE");
+    const bool oversubscribe = ov && atoi(ov) != 0;
+    int n_proc = 1;
+    if (n_dev > 0 && argc >= 3 && !fitting)
+        n_proc = asked > 0 ? (oversubscribe ? std::min(asked, 64) : std::min(asked, n_dev)) : n_dev;
+    Spmd sp;
+    sp.world = n_proc;
+    if (n_proc > 1) {
+        // exchange region: virtual size only (pages appear when touched); scores of 10^9 problems would fit
+        for (size_t bytes = (size_t)16 << 30; bytes >= ((size_t)64 << 20) && !sp.region; bytes >>= 2) {
+            void *m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+            if (m != MAP_FAILED) {
+                sp.region = (char *)m;
+                sp.region_bytes = bytes;
+            }
+        }
+        if (!sp.region) {
+            sp.world = n_proc = 1;
+        } else {
+            sp.ctl = new (sp.region) SpmdCtl();
+            sp.ctl->arrived.store(0);
+            sp.ctl->generation.store(0);
+            sp.ctl->error.store(0);
+            sp.ctl->h2d.store(0);
+            sp.ctl->d2h.store(0);
+            fflush(stdout);
+            fflush(stderr);
+            for (int r = 1; r < n_proc; r++) {
+                const pid_t pid = fork();
+                if (pid == 0) {
+                    prctl(PR_SET_PDEATHSIG, SIGTERM);
+                    sp.rank = r;
+                    sp.kids.clear();
+                    const int dn = open("/dev/null", O_WRONLY);  // rank 0 alone reports progress on stdout
+                    if (dn >= 0) {
+                        dup2(dn, 1);
+                        close(dn);
+                    }
+                    break;
+                }
+                if (pid < 0) {  // could not fork: the ranks that exist would wait for this one forever
+                    sp.ctl->error.store(1);
+                    fprintf(stderr, "SegAligner(b200): fork failed\n");
+                    return 2;
+                }
+                sp.kids.push_back(pid);
+            }
+        }
     }
+    if (n_dev > 0) setenv("CUDA_VISIBLE_DEVICES", devs[(size_t)(sp.rank % n_dev)].c_str(), 1);
+    Engine eng;
+    int code = 0;
+    try {
+        code = run_job(argc, argv, eng, false, sp);
+    } catch (const JobExit &e) {
+        code = e.code;
+        if (sp.ctl) sp.ctl->error.store(1);  // releases the other ranks from their barrier
+    }
+    fflush(stdout);
+    fflush(stderr);
+    if (sp.rank > 0) _exit(code);
+    for (pid_t k : sp.kids) {  // the run is over when every rank's files are written
+        int st = 0;
+        if (waitpid(k, &st, 0) == k && !(WIFEXITED(st) && WEXITSTATUS(st) == 0) && code == 0) code = 2;
+    }
+    return code;
 }

@@ -115,7 +115,7 @@ struct sa_ctx {
     // sa_align_rounds: per-worker scratch that persists across the rounds of a pair, the packed path arena, its host mirrors
     DevBuf d_r_code, d_r_halo, d_r_col2, d_r_lastrow, d_r_used, d_r_path, d_r_ps, d_r_thr, d_r_rounds, d_r_nrounds, d_r_pj, d_r_pq,
         d_r_psc, d_r_ctl;
-    HostBuf h_nr, h_rounds;
+    HostBuf h_nr, h_rounds, h_stage;
     sa_timing timing = {0, 0, 0, 0};
     size_t store_budget_cells = 0;  // max cells of stored matrices per chunk
     uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes moved by this context since it was created (sa_get_traffic)
@@ -405,7 +405,7 @@ void sa_ctx_destroy(sa_ctx *ctx) {
                       &ctx->d_r_lastrow, &ctx->d_r_used, &ctx->d_r_path, &ctx->d_r_ps, &ctx->d_r_thr, &ctx->d_r_rounds, &ctx->d_r_nrounds,
                       &ctx->d_r_pj, &ctx->d_r_pq, &ctx->d_r_psc, &ctx->d_r_ctl};
     for (auto b : bufs) b->release();
-    HostBuf *hbufs[] = {&ctx->h_res, &ctx->h_start, &ctx->h_pj, &ctx->h_pq, &ctx->h_ps, &ctx->h_nr, &ctx->h_rounds};
+    HostBuf *hbufs[] = {&ctx->h_res, &ctx->h_start, &ctx->h_pj, &ctx->h_pq, &ctx->h_ps, &ctx->h_nr, &ctx->h_rounds, &ctx->h_stage};
     for (auto b : hbufs) b->release();
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -900,27 +900,29 @@ int sa_align_rounds(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
             launch_fill(P, 3, false, 0, (int)std::min<int64_t>((m + FILL_WARPS - 1) / FILL_WARPS, n_ctas), ctx->stream);
             CU(cudaGetLastError());
             CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-            unsigned long long ctl[2] = {0, 0};
-            CU(cpy(ctx, ctl, ctx->d_r_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, ctx->stream));
-            std::vector<int32_t> nr((size_t)m);
-            CU(cpy(ctx, nr.data(), ctx->d_r_nrounds.p, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+            // records come back through a pinned staging buffer: [ctl (16 B)][n_rounds (m)][rounds (m * max_alns)]
+            const size_t nr_at = 16, rr_at = (nr_at + sizeof(int32_t) * (size_t)m + 15) & ~(size_t)15;
+            CU(ctx->h_stage.reserve(rr_at + sizeof(sa_round) * (size_t)m * (size_t)max_alns));
+            char *stage = ctx->h_stage.as<char>();
+            unsigned long long *ctl = reinterpret_cast<unsigned long long *>(stage);
+            const int32_t *nr = reinterpret_cast<const int32_t *>(stage + nr_at);
+            const sa_round *rr = reinterpret_cast<const sa_round *>(stage + rr_at);
+            CU(cpy(ctx, ctl, ctx->d_r_ctl.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cpy(ctx, stage + nr_at, ctx->d_r_nrounds.p, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cpy(ctx, stage + rr_at, ctx->d_r_rounds.p, sizeof(sa_round) * (size_t)m * (size_t)max_alns, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
             if ((int32_t)ctl[1] != 0) return fail(ctx, SA_ECUDA, "sa_align_rounds: path arena overflow (internal sizing error)");
             const int64_t n_path = (int64_t)ctl[0];
             CU(ctx->h_pj.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(total + n_path, 1), true));
             CU(ctx->h_pq.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(total + n_path, 1), true));
             CU(ctx->h_ps.reserve(sizeof(float) * (size_t)std::max<int64_t>(total + n_path, 1), true));
-            // the round records land in a staging area at the END of the pinned buffer region of this chunk's first problem:
-            // records of problem acc[k0 + i] go to h_rounds[acc[k0 + i] * max_alns]; copy the chunk contiguously, then scatter
-            std::vector<sa_round> rr((size_t)m * (size_t)max_alns);
-            CU(cpy(ctx, rr.data(), ctx->d_r_rounds.p, sizeof(sa_round) * rr.size(), cudaMemcpyDeviceToHost, ctx->stream));
             if (n_path > 0) {
                 CU(cpy(ctx, ctx->h_pj.as<int32_t>() + total, ctx->d_r_pj.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
                 CU(cpy(ctx, ctx->h_pq.as<int32_t>() + total, ctx->d_r_pq.p, sizeof(int32_t) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
                 CU(cpy(ctx, ctx->h_ps.as<float>() + total, ctx->d_r_psc.p, sizeof(float) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
             }
             CU(cudaStreamSynchronize(ctx->stream));
-            for (int64_t i = 0; i < m; i++) {
+            for (int64_t i = 0; i < m; i++) {  // scatter the chunk's records to their problems, path offsets made global
                 const int64_t g = acc[k0 + (size_t)i];
                 h_nr[g] = nr[(size_t)i];
                 for (int r = 0; r < nr[(size_t)i]; r++) {

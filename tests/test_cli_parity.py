@@ -115,6 +115,15 @@ def test_c5_shaped_cohort_vs_reference(tmp_path, monkeypatch):
     r = cc.run_bin(cc.REF_BIN, tmp_path / "ref", seg_f, con_f, flags)
     assert r.returncode == 0, r.stderr[-2000:]
     monkeypatch.setenv("SA_VERBOSE", "1")
+    # default settings first: pairs whose phase-1 score rules out an alignment file are skipped (exactly: see run_job)
+    n = cc.run_bin(cc.NEW_BIN, tmp_path / "dflt", seg_f, con_f, flags + ["-ngpus=1"])
+    assert n.returncode == 0, n.stderr[-2000:]
+    only_ref, only_new, diff, n_files = cc.compare_dirs(tmp_path / "ref", tmp_path / "dflt")
+    assert not only_ref and not only_new and not diff, (only_ref[:5], only_new[:5], diff[:5])
+    skipped = [l for l in n.stderr.splitlines() if "can reach the score an alignment file needs" in l]
+    assert len(skipped) == 2 and int(skipped[1].split()[0]) < int(skipped[1].split()[2]), skipped
+    # ... then with every pair aligned (SA_NO_SKIP=1), which makes the tip pass big enough for the big-batch branches
+    monkeypatch.setenv("SA_NO_SKIP", "1")
     monkeypatch.setenv("SA_ROUNDS_ARENA_BYTES", "20000000")
     n = cc.run_bin(cc.NEW_BIN, tmp_path / "new", seg_f, con_f, flags + ["-ngpus=1"])
     assert n.returncode == 0, n.stderr[-2000:]
