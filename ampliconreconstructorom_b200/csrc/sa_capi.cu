@@ -903,6 +903,12 @@ int sa_align_rounds(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
             // records come back through a pinned staging buffer: [ctl (16 B)][n_rounds (m)][rounds (m * max_alns)]
             const size_t nr_at = 16, rr_at = (nr_at + sizeof(int32_t) * (size_t)m + 15) & ~(size_t)15;
             CU(ctx->h_stage.reserve(rr_at + sizeof(sa_round) * (size_t)m * (size_t)max_alns));
+            {   // pinned allocations cost ~0.3 s per GB: make them while the kernel runs, from a guess of the path volume
+                const int64_t guess = total + std::min<int64_t>((int64_t)std::min(worst, arena_cap), m * (int64_t)max_alns * 14);
+                CU(ctx->h_pj.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(guess, 1), true));
+                CU(ctx->h_pq.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(guess, 1), true));
+                CU(ctx->h_ps.reserve(sizeof(float) * (size_t)std::max<int64_t>(guess, 1), true));
+            }
             char *stage = ctx->h_stage.as<char>();
             unsigned long long *ctl = reinterpret_cast<unsigned long long *>(stage);
             const int32_t *nr = reinterpret_cast<const int32_t *>(stage + nr_at);
