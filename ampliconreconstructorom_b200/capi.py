@@ -39,7 +39,12 @@ class RoundsOut(C.Structure):
                 ("path_s", C.c_void_p)]
 
 
-round_dtype = np.dtype([("score", "<f4"), ("j", "<i4"), ("q", "<i4"), ("path_len", "<i4"), ("path_off", "<i8")])
+class RoundsFilter(C.Structure):
+    """sa_rounds_filter: which tracebacks sa_align_rounds_filtered returns (main.cpp:303-325)."""
+    _fields_ = [("tip", C.c_int32), ("min_len", C.c_int32), ("mean_min", C.c_float), ("mean_min_short", C.c_float)]
+
+
+round_dtype = np.dtype([("score", "<f4"), ("j", "<i4"), ("q", "<i4"), ("path_len", "<i4"), ("path_off", "<i8"), ("j_first", "<i4"), ("reserved", "<i4")])
 
 
 class Timing(C.Structure):
@@ -49,7 +54,7 @@ class Timing(C.Structure):
 # every symbol include/segaligner_b200.h declares (tests check the library exports exactly these)
 EXPORTS = [
     "sa_device_count", "sa_ctx_create", "sa_ctx_destroy", "sa_last_error", "sa_set_maps", "sa_score_batch",
-    "sa_plan_create", "sa_plan_destroy", "sa_plan_score", "sa_plan_results", "sa_plan_info", "sa_sync", "sa_align_batch", "sa_align_batch_packed", "sa_align_rounds", "sa_detect_batch", "sa_fill_one", "sa_powf12",
+    "sa_plan_create", "sa_plan_destroy", "sa_plan_score", "sa_plan_results", "sa_plan_info", "sa_sync", "sa_align_batch", "sa_align_batch_packed", "sa_align_rounds", "sa_align_rounds_filtered", "sa_detect_batch", "sa_fill_one", "sa_powf12",
     "sa_powf12_range", "sa_check_prune_bound", "sa_get_timing", "sa_get_prune_stats", "sa_measure_fp64_peak", "sa_measure_mufu_peak", "sa_get_traffic", "sa_event_record", "sa_event_elapsed_ms",
     "sa_host_non_collapse_probs", "sa_host_make_reverse", "sa_host_parse_cmap", "sa_host_score_thresholds",
     "sa_host_format_float", "sa_digest",
@@ -86,6 +91,7 @@ def load_library() -> C.CDLL:
     lib.sa_align_batch.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, i64, i64, vp, vp, vp, vp, vp]
     lib.sa_align_batch_packed.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, i64, i64, C.POINTER(PackedPaths)]
     lib.sa_align_rounds.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, i32, vp, i64, i64, C.POINTER(RoundsOut)]
+    lib.sa_align_rounds_filtered.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, i32, vp, i64, i64, C.POINTER(RoundsFilter), C.POINTER(RoundsOut)]
     lib.sa_detect_batch.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, vp, vp, vp]
     lib.sa_fill_one.argtypes = [vp, C.POINTER(Mode), vp, vp, i64, vp, vp, vp]
     lib.sa_powf12.argtypes = [vp, vp, i64, vp, C.c_int]
@@ -339,9 +345,9 @@ class Context:
                 view(pk.path_q, pk.total, np.int32), view(pk.path_s, pk.total, np.float32))
 
     def align_rounds(self, mode: Mode, problems: np.ndarray, thr: np.ndarray, max_alns: int,
-                     used_bits: np.ndarray | None = None, used_words_per_slot: int = 0):
-        """sa_align_rounds: the whole per-pair run_SA_aln loop on the device.  Returns copies
-        (n_rounds[n], rounds[n, max_alns] (round_dtype), path_j, path_q, path_s)."""
+                     used_bits: np.ndarray | None = None, used_words_per_slot: int = 0, flt: "RoundsFilter | None" = None):
+        """sa_align_rounds / sa_align_rounds_filtered (flt given): the whole per-pair run_SA_aln loop on the device.  Returns
+        copies (n_rounds[n], rounds[n, max_alns] (round_dtype), path_j, path_q, path_s)."""
         problems = np.ascontiguousarray(problems, dtype=problem_dtype)
         thr = np.ascontiguousarray(thr, dtype=np.float32)
         n = problems.size
@@ -350,8 +356,12 @@ class Context:
             used_bits = np.ascontiguousarray(used_bits, dtype=np.uint32)
             n_slots = used_bits.size // max(used_words_per_slot, 1)
         ro = RoundsOut()
-        self._check(self.lib.sa_align_rounds(self.h, C.byref(mode), _ptr(problems), n, _ptr(thr), max_alns, _ptr(used_bits),
-                                             used_words_per_slot, n_slots, C.byref(ro)), "sa_align_rounds")
+        if flt is None:
+            self._check(self.lib.sa_align_rounds(self.h, C.byref(mode), _ptr(problems), n, _ptr(thr), max_alns, _ptr(used_bits),
+                                                 used_words_per_slot, n_slots, C.byref(ro)), "sa_align_rounds")
+        else:
+            self._check(self.lib.sa_align_rounds_filtered(self.h, C.byref(mode), _ptr(problems), n, _ptr(thr), max_alns, _ptr(used_bits),
+                                                          used_words_per_slot, n_slots, C.byref(flt), C.byref(ro)), "sa_align_rounds_filtered")
 
         def view(addr, count, dtype):
             if count == 0 or not addr:

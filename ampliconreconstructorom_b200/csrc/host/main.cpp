@@ -111,6 +111,8 @@ void parse_args(int argc, char **argv, Options &o) {
 struct SpmdCtl {  // first page of the shared region
     std::atomic<int> arrived, generation, error;
     std::atomic<unsigned long long> h2d, d2h;
+    std::atomic<int> init_turn;        // CUDA start-up goes rank by rank (see Spmd::wait_init_turn)
+    std::atomic<long long> next_unit;  // phase 1: cursor into the shared problem order (see score_dynamic)
 };
 struct Spmd {
     int rank = 0, world = 1;  // world starts as the number of processes forked and may shrink to 1 for small runs
@@ -145,6 +147,24 @@ struct Spmd {
             else usleep(100);
         }
         if (ctl->error.load()) throw JobExit{2, true};
+    }
+    // CUDA start-up (driver initialisation + context creation) is serialised by the driver across the processes of a box:
+    // measured on a 4 x B200 box (profiles/r2_cuda_startup_probe_4gpu.txt) one process alone is ready after 0.5 s, four
+    // processes starting together are ALL ready only after 2.5-3.2 s, while four processes taking turns are ready after 0.5,
+    // 1.3, 2.1 and 2.9 s.  So the ranks take turns, rank 0 first, and phase 1 hands out work dynamically: the ranks that are
+    // up early start scoring while the later ones are still initialising.
+    void wait_init_turn() {
+        if (world <= 1 || !ctl) return;
+        for (unsigned spin = 0; ctl->init_turn.load() < rank; spin++) {
+            if (ctl->error.load()) throw JobExit{2, true};
+            usleep(spin < 50 ? 200 : 2000);
+        }
+    }
+    void pass_init_turn() {
+        if (!ctl) return;
+        int cur = ctl->init_turn.load();
+        while (cur <= rank && !ctl->init_turn.compare_exchange_weak(cur, rank + 1)) {
+        }
     }
     // Bump allocation inside the shared region; every rank calls it with the same sizes in the same order, so they all
     // get the same offsets without talking to each other.
@@ -189,6 +209,28 @@ std::vector<int64_t> my_shard(const std::vector<sa_problem> &pr, const MapSet &c
         if (r % world == rank) mine.push_back((int64_t)k);
     }
     return mine;
+}
+
+// The same size-class order as a list: order = problem indices, largest classes first (stable inside a class);
+// cum[k] = cells of order[0 .. k).  Every rank computes the same arrays.
+void size_class_order(const std::vector<sa_problem> &pr, const MapSet &contigs, const MapSet &segs, std::vector<int64_t> &order,
+                      std::vector<double> &cum) {
+    const int NB = 4 * 64;
+    std::vector<uint8_t> cls(pr.size());
+    std::vector<int64_t> cnt((size_t)NB + 1, 0);
+    std::vector<double> cells(pr.size());
+    for (size_t k = 0; k < pr.size(); k++) {
+        cells[k] = (double)contigs.labels(pr[k].contig) * (double)segs.labels(pr[k].seg);
+        int b = cells[k] > 1.0 ? (int)(std::log2(cells[k]) * 4.0) : 0;
+        b = NB - 1 - std::min(b, NB - 1);
+        cls[k] = (uint8_t)b;
+        cnt[(size_t)b + 1]++;
+    }
+    for (int b = 0; b < NB; b++) cnt[(size_t)b + 1] += cnt[(size_t)b];
+    order.resize(pr.size());
+    for (size_t k = 0; k < pr.size(); k++) order[(size_t)cnt[cls[k]]++] = (int64_t)k;
+    cum.assign(pr.size() + 1, 0.0);
+    for (size_t k = 0; k < pr.size(); k++) cum[k + 1] = cum[k] + cells[(size_t)order[k]];
 }
 
 // ---- this process's GPU: one context behind the C ABI ----------------------------------------------------------------
@@ -274,13 +316,14 @@ struct Engine {
             return View{rec, ro.path_j + rec->path_off, ro.path_q + rec->path_off, ro.path_s + rec->path_off};
         }
     };
+    // flt: tracebacks that cannot become a file any more stay on the device (their round record has path_off = -1)
     void align_rounds(const sa_mode &mode, const std::vector<sa_problem> &pr, const std::vector<float> &thr, int max_alns,
-                      const std::vector<uint32_t> &arena, RoundsOut &out) {
+                      const std::vector<uint32_t> &arena, const sa_rounds_filter &flt, RoundsOut &out) {
         out.ro = sa_rounds_out{};
         if (pr.empty()) return;
-        const int rc = sa_align_rounds(ctx, &mode, pr.data(), (int64_t)pr.size(), thr.data(), max_alns, arena.empty() ? nullptr : arena.data(),
-                                       1, (int64_t)arena.size(), &out.ro);
-        if (rc) die("sa_align_rounds", rc);
+        const int rc = sa_align_rounds_filtered(ctx, &mode, pr.data(), (int64_t)pr.size(), thr.data(), max_alns,
+                                                arena.empty() ? nullptr : arena.data(), 1, (int64_t)arena.size(), &flt, &out.ro);
+        if (rc) die("sa_align_rounds_filtered", rc);
     }
 };
 
@@ -349,10 +392,9 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
     mode.swap_b_x = o.swap_b_x ? 1 : 0;
 
     // compute_partial_score_threshold (SegAligner.cpp:23-36) on a flat path (end -> start): max of the two, main.cpp:290
-    auto partial_thresh = [&](const PairState &p, int len, const int32_t *pj) -> float {
+    auto partial_thresh = [&](const PairState &p, int first_lab, int last_lab) -> float {
         const float *contig = contigs.map(p.c);
         const int contig_size = contigs.size(p.c);
-        const int first_lab = pj[len - 1], last_lab = pj[0];
         const int aln_span_labs = last_lab - first_lab + 1;
         const float tot_labs = (float)(contig_size - 1);
         const float by_lab = p.thr * (aln_span_labs / tot_labs);
@@ -404,7 +446,13 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
         }
         const double t_r0 = wall_now();
         Engine::RoundsOut ro;
-        eng.align_rounds(mode, rp, rthr, max_alns, arena, ro);
+        // what emit() below tests first, from the path's ends, length and total score alone (the mean again, exactly, there)
+        sa_rounds_filter flt;
+        flt.tip = tip_aln ? 1 : 0;
+        flt.min_len = tip_aln ? min_tip_aln_labels : std::max(min_aln_labels, min_tip_aln_labels);
+        flt.mean_min = mean_thresh;
+        flt.mean_min_short = 9400.0f;
+        eng.align_rounds(mode, rp, rthr, max_alns, arena, flt, ro);
         const double t_r1 = wall_now();
         const size_t n_pairs = st.size();
         // replay + file writing: a worker per 4096 pairs (a standard pass writes about one file per pair)
@@ -431,7 +479,7 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
                         r++;
                         break;
                     }
-                    p.exp_thresh = partial_thresh(p, len, v.pj);
+                    p.exp_thresh = partial_thresh(p, v.rec->j_first, v.rec->j);
                     p.curr_best = v.rec->score;
                     if (!(p.curr_best > p.exp_thresh)) {  // not accepted: the loop ends (equality would spin in the reference)
                         more = false;
@@ -439,7 +487,7 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
                         break;
                     }
                     p.count += 1;
-                    emit(p, len, v.pj, v.pq, v.ps, aln, disc[(size_t)wi]);
+                    if (v.rec->path_off >= 0) emit(p, len, v.pj, v.pq, v.ps, aln, disc[(size_t)wi]);  // else: certified unwritable
                     more = p.count < max_alns;
                 }
                 if (more || r != nr) bad[(size_t)wi]++;  // the device loop and this replay must agree on the number of rounds
@@ -526,7 +574,7 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
                     continue;
                 }
                 const int32_t *pj = v.pj;
-                p.exp_thresh = partial_thresh(p, len, pj);
+                p.exp_thresh = partial_thresh(p, pj[len - 1], pj[0]);
                 p.curr_best = v.res->score;
                 if (!(p.curr_best > p.exp_thresh)) {
                     // equality would spin forever in the reference (same DP, same result); we stop instead
@@ -612,12 +660,14 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open, Spmd &sp
     JobExit open_err{0, false};
     std::thread gpu_open;
     auto start_open = [&]() {
-        gpu_open = std::thread([&eng, &open_err]() {
+        gpu_open = std::thread([&eng, &open_err, &sp]() {
             try {
+                if (!eng.ctx) sp.wait_init_turn();
                 eng.open();
             } catch (const JobExit &e) {
                 open_err = e;
             }
+            sp.pass_init_turn();  // also when it failed: the ranks behind must not wait for ever
         });
     };
     struct Joiner {  // the opener thread must be joined on every exit path (exceptions included)
@@ -662,7 +712,10 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open, Spmd &sp
         if (asked <= 0 && total_cells <= 2e10) sp.world = 1;
         if (o.fitting_aln || segs.n_maps() == 0 || contigs.n_maps() == 0) sp.world = 1;
     }
-    if (sp.rank >= sp.world) return 0;
+    if (sp.rank >= sp.world) {
+        sp.pass_init_turn();
+        return 0;
+    }
     if (sp.rank > 0) start_open();
 
     if (segs.n_maps() == 0 || contigs.n_maps() == 0) {
@@ -792,8 +845,42 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open, Spmd &sp
                 all = own.data();
             }
             std::vector<sa_result> res;
-            eng.score(mode, mp, res);
-            for (size_t k = 0; k < mp.size(); k++) all[(size_t)mine[k]] = res[k].score;
+            if (sp.world <= 1) {
+                eng.score(mode, mp, res);
+                for (size_t k = 0; k < mp.size(); k++) all[(size_t)mine[k]] = res[k].score;
+            } else {
+                // Dynamic units instead of the static shard: the ranks come up one after the other (Spmd::wait_init_turn), so
+                // each takes the next run of the shared largest-first order whenever it is free -- half an even share of what is
+                // left, at least ~40 ms of scoring -- through one atomic cursor in the exchange region.  Scores land by problem
+                // index, so the result does not depend on who computed what.
+                std::vector<int64_t> order;
+                std::vector<double> cum;
+                size_class_order(pr, contigs, segs, order, cum);
+                const long long n_all = (long long)pr.size();
+                const double total = cum.back(), min_unit = std::max(total / (64.0 * sp.world), 2.0e9);
+                int n_units = 0;
+                double my_cells = 0;
+                for (;;) {
+                    long long b = sp.ctl->next_unit.load(), e = b;
+                    for (;;) {
+                        if (b >= n_all) break;
+                        const double want = std::max(min_unit, (total - cum[(size_t)b]) / (2.0 * sp.world));
+                        e = (long long)(std::upper_bound(cum.begin() + b + 1, cum.end(), cum[(size_t)b] + want) - cum.begin());
+                        e = std::max(std::min(e, n_all), b + 1);
+                        if (sp.ctl->next_unit.compare_exchange_weak(b, e)) break;
+                    }
+                    if (b >= n_all) break;
+                    mp.resize((size_t)(e - b));
+                    for (long long k = b; k < e; k++) mp[(size_t)(k - b)] = pr[(size_t)order[(size_t)k]];
+                    eng.score(mode, mp, res);
+                    for (long long k = b; k < e; k++) all[(size_t)order[(size_t)k]] = res[(size_t)(k - b)].score;
+                    n_units++;
+                    my_cells += cum[(size_t)e] - cum[(size_t)b];
+                }
+                if (getenv("SA_VERBOSE"))
+                    fprintf(stderr, "  rank %d scored %d units, %.3g of %.3g cells, done %.3f s after start\n", sp.rank, n_units, my_cells, total,
+                            wall_now() - w0);
+            }
             sp.barrier();
             rows.reserve(pr.size());
             for (size_t k = 0; k < pr.size(); k++)
@@ -1246,6 +1333,8 @@ int main(int argc, char *argv[]) {
             sp.ctl->error.store(0);
             sp.ctl->h2d.store(0);
             sp.ctl->d2h.store(0);
+            sp.ctl->init_turn.store(0);
+            sp.ctl->next_unit.store(0);
             fflush(stdout);
             fflush(stderr);
             for (int r = 1; r < n_proc; r++) {

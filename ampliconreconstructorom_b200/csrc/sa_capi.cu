@@ -115,7 +115,9 @@ struct sa_ctx {
     // sa_align_rounds: per-worker scratch that persists across the rounds of a pair, the packed path arena, its host mirrors
     DevBuf d_r_code, d_r_halo, d_r_col2, d_r_lastrow, d_r_used, d_r_path, d_r_ps, d_r_thr, d_r_rounds, d_r_nrounds, d_r_pj, d_r_pq,
         d_r_psc, d_r_ctl;
-    HostBuf h_nr, h_rounds, h_stage;
+    HostBuf h_stage;                    // pinned D2H landing zone of a chunk's round records
+    std::vector<int32_t> h_nr;          // what sa_rounds_out points at (scatter targets: pageable memory is enough)
+    std::vector<sa_round> h_rounds;
     sa_timing timing = {0, 0, 0, 0};
     size_t store_budget_cells = 0;  // max cells of stored matrices per chunk
     uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes moved by this context since it was created (sa_get_traffic)
@@ -405,7 +407,7 @@ void sa_ctx_destroy(sa_ctx *ctx) {
                       &ctx->d_r_lastrow, &ctx->d_r_used, &ctx->d_r_path, &ctx->d_r_ps, &ctx->d_r_thr, &ctx->d_r_rounds, &ctx->d_r_nrounds,
                       &ctx->d_r_pj, &ctx->d_r_pq, &ctx->d_r_psc, &ctx->d_r_ctl};
     for (auto b : bufs) b->release();
-    HostBuf *hbufs[] = {&ctx->h_res, &ctx->h_start, &ctx->h_pj, &ctx->h_pq, &ctx->h_ps, &ctx->h_nr, &ctx->h_rounds, &ctx->h_stage};
+    HostBuf *hbufs[] = {&ctx->h_res, &ctx->h_start, &ctx->h_pj, &ctx->h_pq, &ctx->h_ps, &ctx->h_stage};
     for (auto b : hbufs) b->release();
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -759,6 +761,12 @@ int sa_align_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems,
 // The whole per-pair loop of run_SA_aln on the device (see include/segaligner_b200.h and rounds_finish in sa_kernels.cu).
 int sa_align_rounds(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const float *thr, int32_t max_alns,
                     const uint32_t *used_bits, int64_t used_words_per_slot, int64_t n_used_slots, sa_rounds_out *out) {
+    return sa_align_rounds_filtered(ctx, mode, problems, n, thr, max_alns, used_bits, used_words_per_slot, n_used_slots, nullptr, out);
+}
+
+int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const float *thr,
+                             int32_t max_alns, const uint32_t *used_bits, int64_t used_words_per_slot, int64_t n_used_slots,
+                             const sa_rounds_filter *filter, sa_rounds_out *out) {
     if (!ctx || !out) return SA_EINVAL;
     memset(out, 0, sizeof(*out));
     if (n <= 0) return SA_OK;
@@ -808,11 +816,18 @@ int sa_align_rounds(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
         max_cells = std::max(max_cells, nb * nx);
         max_halo = std::max(max_halo, ((nb + 31) / 32) * nx * 8);
     }
-    CU(ctx->h_nr.reserve(sizeof(int32_t) * (size_t)n));
-    CU(ctx->h_rounds.reserve(sizeof(sa_round) * (size_t)n * (size_t)max_alns));
-    int32_t *h_nr = ctx->h_nr.as<int32_t>();
-    sa_round *h_rounds = ctx->h_rounds.as<sa_round>();
-    for (int64_t k = 0; k < n; k++) h_nr[k] = -1;
+    if (filter) {
+        if (filter->min_len < 2) return fail(ctx, SA_EINVAL, "sa_align_rounds_filtered: min_len must be >= 2");
+        P.r_flt_on = 1;
+        P.r_flt_tip = filter->tip ? 1 : 0;
+        P.r_flt_min_len = filter->min_len;
+        P.r_flt_mean = filter->mean_min;
+        P.r_flt_mean_short = filter->mean_min_short;
+    }
+    ctx->h_nr.assign((size_t)n, -1);
+    if (ctx->h_rounds.size() < (size_t)n * (size_t)max_alns) ctx->h_rounds.resize((size_t)n * (size_t)max_alns);
+    int32_t *h_nr = ctx->h_nr.data();
+    sa_round *h_rounds = ctx->h_rounds.data();
     int64_t total = 0;
     if (!acc.empty()) {
         const int used_words = (max_nb + 31) / 32;
@@ -904,7 +919,8 @@ int sa_align_rounds(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
             const size_t nr_at = 16, rr_at = (nr_at + sizeof(int32_t) * (size_t)m + 15) & ~(size_t)15;
             CU(ctx->h_stage.reserve(rr_at + sizeof(sa_round) * (size_t)m * (size_t)max_alns));
             {   // pinned allocations cost ~0.3 s per GB: make them while the kernel runs, from a guess of the path volume
-                const int64_t guess = total + std::min<int64_t>((int64_t)std::min(worst, arena_cap), m * (int64_t)max_alns * 14);
+                // (with a filter only the tracebacks that can become files come back: a few entries per pair at most)
+                const int64_t guess = total + std::min<int64_t>((int64_t)std::min(worst, arena_cap), filter ? m * 4 + (1 << 20) : m * (int64_t)max_alns * 14);
                 CU(ctx->h_pj.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(guess, 1), true));
                 CU(ctx->h_pq.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(guess, 1), true));
                 CU(ctx->h_ps.reserve(sizeof(float) * (size_t)std::max<int64_t>(guess, 1), true));
@@ -933,7 +949,7 @@ int sa_align_rounds(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
                 h_nr[g] = nr[(size_t)i];
                 for (int r = 0; r < nr[(size_t)i]; r++) {
                     sa_round v = rr[(size_t)i * (size_t)max_alns + (size_t)r];
-                    v.path_off += total;
+                    if (v.path_off >= 0) v.path_off += total;
                     h_rounds[(size_t)g * (size_t)max_alns + (size_t)r] = v;
                 }
             }
@@ -1201,7 +1217,7 @@ int sa_digest(sa_ctx *ctx, const char *seq, int64_t n, const char *motif, int32_
               int64_t *pos_out, int64_t *n_out) {
     if (!ctx || !seq || !motif || !n_out || n < 0 || cap < 0 || (cap > 0 && !pos_out)) return ctx ? fail(ctx, SA_EINVAL, "bad argument") : SA_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    const size_t padded = ((size_t)n + 15) / 16 * 16 + 64;
+    const size_t padded = ((size_t)n + 31) / 32 * 32 + 64;  // the kernel reads whole 32-byte chunks plus 8 bytes of look-ahead
     CU(ctx->d_S.reserve(padded));  // sequence bytes (the DP matrices are not live during a digestion)
     CU(ctx->d_tmp2.reserve(64));
     const int64_t dev_cap = std::max<int64_t>(cap, 1);
@@ -1212,7 +1228,7 @@ int sa_digest(sa_ctx *ctx, const char *seq, int64_t n, const char *motif, int32_
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = sa_digest_run(ctx->stream, ctx->n_sms, ctx->d_S.as<uint8_t>(), n, motif, motif_len, offset,
                            ctx->d_path_s.as<long long>(), ctx->d_tmp2.as<unsigned long long>(), dev_cap);
-    if (rc) return fail(ctx, rc, "sa_digest: motif length must be 4..8");
+    if (rc) return fail(ctx, rc, "sa_digest: the motif must be 4..8 letters of ACGT");
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     unsigned long long cnt = 0;

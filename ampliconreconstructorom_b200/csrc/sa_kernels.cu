@@ -449,40 +449,55 @@ __device__ __noinline__ bool rounds_finish(const FillParams &P, long long gunit,
                 j -= (cd - 1) / LB + 1;
                 q -= (cd - 1) % LB + 1;
             }
-            // scores along the path, start -> end, exactly as dp_align produced them (see trace_kernel)
             const int64_t boff = P.contigs.pos_off[contig], xoff = P.segs.pos_off[seg];
-            const LabelOps *bops = P.contigs.ops + (boff - contig);
-            const LabelOps *xops = P.segs.ops + (xoff - seg);
-            float sv = (pj[n - 1] == 0 || pq[n - 1] < 2) ? 0.0f : NEG_INF_F;  // init_semiglobal_aln
-            ps[n - 1] = sv;
-            int jp = pj[n - 1], qp = pq[n - 1];
-            for (int t = n - 2; t >= 0; t--) {
-                const int jc = pj[t], qc = pq[t];
-                const int dj = jc - jp, dq = qc - qp;
-                const float discrep = fabsf(__fsub_rn(bops[jc].d[dj - 1], xops[qc].d[dq - 1]));
-                const float delta = powf12_slow(discrep);
-                const float fnfp = (dj == 1) ? xops[qc].f[dq - 1] : __fadd_rn(5000.0f * (float)(dj - 1), xops[qc].f[dq - 1]);
-                sv = __fadd_rn(sv, __fsub_rn(10000.0f, __fadd_rn(fnfp, delta)));
-                ps[t] = sv;
-                jp = jc;
-                qp = qc;
-            }
-            aoff = (long long)atomicAdd(P.r_arena_top, (unsigned long long)n);
-            if (aoff + n <= P.r_arena_cap) {
-                for (int t = 0; t < n; t++) {
-                    P.r_pj[aoff + t] = pj[t];
-                    P.r_pq[aoff + t] = pq[t];
-                    P.r_psc[aoff + t] = ps[t];
-                }
-            } else {
-                *P.r_overflow = 1;
-            }
             // compute_partial_score_threshold (SegAligner.cpp:23-36) on the path; aln_list is end -> start
             const float *cpos = P.contigs.pos + boff;  // nb + 1 entries, the last one is the contig length
             const int first_lab = pj[n - 1], last_lab = pj[0];
             const float by_lab = __fmul_rn(thr, __fdiv_rn((float)(last_lab - first_lab + 1), (float)nb));
             const float by_len = __fmul_rn(thr, __fdiv_rn(__fsub_rn(cpos[last_lab], cpos[first_lab]), cpos[nb]));
             exp_thresh = fmaxf(by_lab, by_len);  // main.cpp:290
+            // Does the traceback leave the device?  Always without a filter; with one only when the alignment was accepted and
+            // passes the file filters that need just its ends, length and total score (main.cpp:303-325; the mean with slack,
+            // the caller redoes it exactly): everything else the caller's replay reads is in the round record.
+            bool keep = true;
+            if (P.r_flt_on) {
+                keep = st_s > exp_thresh && n >= P.r_flt_min_len;
+                if (keep && P.r_flt_tip && (nb - 1) - last_lab > 3 && first_lab > 2) keep = false;  // touches neither contig end
+                if (keep) {
+                    const float mean = __fdiv_rn(st_s, (float)(n - 1));
+                    keep = mean >= 0.999f * (n < 5 ? P.r_flt_mean_short : P.r_flt_mean);
+                }
+            }
+            aoff = -1;
+            if (keep) {
+                // scores along the path, start -> end, exactly as dp_align produced them (see trace_kernel)
+                const LabelOps *bops = P.contigs.ops + (boff - contig);
+                const LabelOps *xops = P.segs.ops + (xoff - seg);
+                float sv = (pj[n - 1] == 0 || pq[n - 1] < 2) ? 0.0f : NEG_INF_F;  // init_semiglobal_aln
+                ps[n - 1] = sv;
+                int jp = pj[n - 1], qp = pq[n - 1];
+                for (int t = n - 2; t >= 0; t--) {
+                    const int jc = pj[t], qc = pq[t];
+                    const int dj = jc - jp, dq = qc - qp;
+                    const float discrep = fabsf(__fsub_rn(bops[jc].d[dj - 1], xops[qc].d[dq - 1]));
+                    const float delta = powf12_slow(discrep);
+                    const float fnfp = (dj == 1) ? xops[qc].f[dq - 1] : __fadd_rn(5000.0f * (float)(dj - 1), xops[qc].f[dq - 1]);
+                    sv = __fadd_rn(sv, __fsub_rn(10000.0f, __fadd_rn(fnfp, delta)));
+                    ps[t] = sv;
+                    jp = jc;
+                    qp = qc;
+                }
+                aoff = (long long)atomicAdd(P.r_arena_top, (unsigned long long)n);
+                if (aoff + n <= P.r_arena_cap) {
+                    for (int t = 0; t < n; t++) {
+                        P.r_pj[aoff + t] = pj[t];
+                        P.r_pq[aoff + t] = pq[t];
+                        P.r_psc[aoff + t] = ps[t];
+                    }
+                } else {
+                    *P.r_overflow = 1;
+                }
+            }
         }
         sa_round rec;
         rec.score = st_s;
@@ -490,6 +505,8 @@ __device__ __noinline__ bool rounds_finish(const FillParams &P, long long gunit,
         rec.q = st_q;
         rec.path_len = n;
         rec.path_off = aoff;
+        rec.j_first = n > 0 ? pj[n - 1] : -1;
+        rec.reserved = 0;
         P.r_rounds[pidx * P.r_max_alns + round] = rec;
         if (n > 0 && st_s > exp_thresh) {  // main.cpp:295: accepted -> count, the path's contig labels join the used set
             n_count = count + 1;

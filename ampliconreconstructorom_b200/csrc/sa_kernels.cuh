@@ -68,6 +68,9 @@ struct FillParams {
     int32_t *r_pj, *r_pq;   // packed paths of all rounds of all pairs
     float *r_psc;
     int32_t *r_overflow;    // set when the arena was too small (host-sized for the worst case, so never)
+    // sa_align_rounds_filtered: only tracebacks that can still become a file leave the device (r_flt_on)
+    int r_flt_on, r_flt_tip, r_flt_min_len;
+    float r_flt_mean, r_flt_mean_short;
 };
 
 struct TraceParams {

@@ -127,13 +127,28 @@ int sa_align_batch_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *pr
  * (0 when thr is NaN) in rounds[k * max_alns ...]; round r's traceback (end -> start, like aln_list) is
  * path_j/q/s[path_off .. path_off + path_len).  The last round of a pair is the one that failed `best > exp_thresh`
  * (or the max_alns-th accepted one).  Semi-global mode, lookback 6, no swap_b_x, every segment >= 2 labels; a pair whose
- * matrix exceeds the per-worker scratch gets n_rounds = -1 (the caller falls back to sa_align_batch_packed rounds). */
+ * matrix exceeds the per-worker scratch gets n_rounds = -1 (the caller falls back to sa_align_batch_packed rounds).
+ *
+ * sa_align_rounds_filtered: the same, but a round's traceback is only RETURNED when the alignment could still be written
+ * to a file -- the round was accepted and passes the filters of run_SA_aln that need nothing but the path's two ends, its
+ * length and its total score (main.cpp:303-325: tip alignments must touch a contig end, minimum label count, mean score
+ * per step; the mean is tested with 0.1 % slack, the caller applies the exact mean / median / minimum tests to what comes
+ * back).  Every other round has path_off = -1: its record (score, start, path_len, j_first) is all the caller's replay of
+ * the loop needs.  On C2-shaped runs this keeps > 99 % of the traceback entries on the device. */
 typedef struct sa_round {
     float score;       /* S at the backtrack start = curr_best_score of the round */
-    int32_t j, q;      /* backtrack start */
+    int32_t j, q;      /* backtrack start = LAST contig / segment label of the path */
     int32_t path_len;
-    int64_t path_off;
+    int64_t path_off;  /* -1: the traceback was not returned (sa_align_rounds_filtered) */
+    int32_t j_first;   /* FIRST contig label of the path (what compute_partial_score_threshold needs besides j) */
+    int32_t reserved;
 } sa_round;
+typedef struct sa_rounds_filter {
+    int32_t tip;           /* 1: run_SA_aln's tip_aln test (main.cpp:303-308) */
+    int32_t min_len;       /* fewer path entries cannot be written (main.cpp:310-312) */
+    float mean_min;        /* score / (path_len - 1) below this cannot be written, paths of >= 5 entries (main.cpp:322) */
+    float mean_min_short;  /* the same for paths of < 5 entries (main.cpp:318) */
+} sa_rounds_filter;
 typedef struct sa_rounds_out {
     int64_t n;
     int32_t max_alns;
@@ -146,6 +161,9 @@ typedef struct sa_rounds_out {
 } sa_rounds_out;
 int sa_align_rounds(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const float *thr, int32_t max_alns,
                     const uint32_t *used_bits, int64_t used_words_per_slot, int64_t n_used_slots, sa_rounds_out *out);
+int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const float *thr,
+                             int32_t max_alns, const uint32_t *used_bits, int64_t used_words_per_slot, int64_t n_used_slots,
+                             const sa_rounds_filter *filter, sa_rounds_out *out);
 
 /* Detection-mode scoring (run_SA_score with detection=true, main.cpp:155-159): semiglobal init, dp_align,
  * then multi_backtrack_scores (SegAligner.cpp:208-233) harvesting n_want[k] path scores per problem in the

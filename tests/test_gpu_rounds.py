@@ -150,3 +150,56 @@ def test_rounds_scratch_and_arena_limits(ctx, oracle, monkeypatch):
     nr = ctx.align_rounds(mode, pr, thr, 6)[0]
     assert np.array_equal(nr == -1, cells > cut), "the scratch cap did not reject exactly the oversized pairs"
     assert np.array_equal(nr[cells <= cut], base[0][cells <= cut])
+
+
+@pytest.mark.parametrize("tip", [0, 1])
+def test_filtered_rounds_return_exactly_the_writable_tracebacks(ctx, oracle, tip):
+    """sa_align_rounds_filtered: same round records as sa_align_rounds (incl. j_first = first contig label of the path); a
+    traceback comes back iff the round was accepted and passes the end / length / mean-score filters of run_SA_aln
+    (/root/reference/SegAligner/main.cpp:303-325), and then it is the same traceback."""
+    rng = np.random.default_rng(900 + tip)
+    contigs, segs = make_pairs(rng, 40, (40, 420), (4, 45))
+    cp, sp = oracle.probs(contigs, 2), oracle.probs(segs, 2)
+    cids = upload(ctx, contigs, cp, capi.SA_SIDE_CONTIG)
+    sids = upload(ctx, segs, sp, capi.SA_SIDE_SEG)
+    cc = np.repeat(np.arange(len(cids)), 3)
+    ss = (cc + np.tile([0, 5, 11], len(cids))) % len(sids)
+    pr = ctx.problems(cc, ss)
+    mode = ctx.mode(capi.SA_INIT_SEMIGLOBAL, capi.SA_START_SEMIGLOBAL, 0, 6, 0)
+    first = ctx.score_batch(mode, pr)["score"]
+    thr = (first * rng.uniform(0.05, 1.2, size=pr.size)).astype(np.float32)
+    min_len, mean_min, mean_short = 4, 2500.0, 3500.0  # looser than run_SA_aln's constants so that both outcomes are frequent here
+    flt = capi.RoundsFilter(tip, min_len, mean_min, mean_short)
+    nr0, r0, pj0, pq0, ps0 = ctx.align_rounds(mode, pr, thr, 6)
+    nr1, r1, pj1, pq1, ps1 = ctx.align_rounds(mode, pr, thr, 6, flt=flt)
+    assert np.array_equal(nr0, nr1)
+    kept = dropped = 0
+    for k in range(pr.size):
+        nb = len(contigs[cids[int(pr["contig"][k])]]) - 1
+        cpos = np.asarray(contigs[cids[int(pr["contig"][k])]], dtype=np.float32)
+        for r in range(nr0[k]):
+            a, b = r0[k, r], r1[k, r]
+            assert (a["j"], a["q"], a["path_len"], a["j_first"]) == (b["j"], b["q"], b["path_len"], b["j_first"])
+            assert bits(a["score"]) == bits(b["score"])
+            L, o = int(a["path_len"]), int(a["path_off"])
+            assert int(a["j_first"]) == int(pj0[o + L - 1]) and int(a["j"]) == int(pj0[o])
+            first_lab, last_lab = int(pj0[o + L - 1]), int(pj0[o])
+            by_lab = np.float32(thr[k]) * (np.float32(last_lab - first_lab + 1) / np.float32(nb))
+            by_len = np.float32(thr[k]) * ((cpos[last_lab] - cpos[first_lab]) / cpos[nb])
+            accepted = a["score"] > max(by_lab, by_len)
+            mean = float(a["score"]) / max(L - 1, 1)
+            bar = mean_short if L < 5 else mean_min
+            want = bool(accepted and L >= min_len and mean >= 0.999 * bar)
+            if tip and want and (nb - 1 - last_lab > 3 and first_lab > 2):
+                want = False
+            sure = abs(mean / bar - 0.999) > 1e-3  # the mean test carries 0.1 % slack: only check clear cases
+            if sure or not accepted:
+                assert (int(b["path_off"]) >= 0) == want, (k, r, accepted, L, mean, first_lab, last_lab, nb)
+            if int(b["path_off"]) >= 0:
+                kept += 1
+                o1 = int(b["path_off"])
+                assert np.array_equal(pj1[o1:o1 + L], pj0[o:o + L]) and np.array_equal(pq1[o1:o1 + L], pq0[o:o + L])
+                assert np.array_equal(bits(ps1[o1:o1 + L]), bits(ps0[o:o + L]))
+            else:
+                dropped += 1
+    assert kept > 5 and dropped > 5, (kept, dropped)
