@@ -115,6 +115,10 @@ struct sa_ctx {
     // sa_align_rounds: per-worker scratch that persists across the rounds of a pair, the packed path arena, its host mirrors
     DevBuf d_r_code, d_r_halo, d_r_col2, d_r_lastrow, d_r_used, d_r_path, d_r_ps, d_r_thr, d_r_rounds, d_r_nrounds, d_r_pj, d_r_pq,
         d_r_psc, d_r_ctl;
+    DevBuf d_units, d_mbox, d_cpl_res, d_cpl_done;  // coupled units: queue, mailboxes, per-unit start candidates, per-problem counters
+    HostBuf h_cpl_err;                              // the handshake-timeout flag of the last coupled launch lands here
+    bool cpl_pending = false;
+    uint32_t cpl_epoch = 0;
     HostBuf h_stage;                    // pinned D2H landing zone of a chunk's round records
     std::vector<int32_t> h_nr;          // what sa_rounds_out points at (scatter targets: pageable memory is enough)
     std::vector<sa_round> h_rounds;
@@ -172,10 +176,26 @@ void build_label_ops(const float *pos, const float *prob, int n, LabelOps *out) 
 // (cells_p * n_warp_slots > alpha * total_cells), so that no single problem can become the tail.
 //   huge   -> cluster-cooperative kernel (CLUSTER_CTAS SMs per problem) when even ONE SM would need longer for
 //             the problem than the whole batch needs on the whole GPU (cells_p * n_sms > alpha * total_cells).
+// Since round 2 the default for problems that are too large for one warp is "coupled units" (SA_SHAPES=coupled, the
+// default): the problem is cut into U units of row strips that any U warps sweep as a wavefront, handing rows over through
+// tagged mailboxes in L2 (see fill_kernel, CPL).  A problem is coupled when one warp would need more than cpl_alpha x the
+// batch's ideal makespan for it; U is chosen so that a unit is half of that (and U <= 64, <= its strips, <= nx / 2 so the ring
+// of units never waits for its own tail).  SA_SHAPES=legacy keeps the two barrier-synchronised shapes above.
 struct Plan {
-    std::vector<int32_t> order;  // bulk problems first, then the large ones, then the huge ones
-    int64_t n_bulk = 0, n_large = 0, n_huge = 0;
+    std::vector<int32_t> order;  // bulk problems first, then the large ones, then the huge ones (or the coupled ones)
+    int64_t n_bulk = 0, n_large = 0, n_huge = 0, n_cpl = 0;
+    std::vector<CplUnit> units;  // coupled mode: the unit queue, largest problems first, units of a problem consecutive
+    int cpl_max_nx = 0;
     double total_cells = 0;
+    // every problem, largest classes first (one-warp-per-problem consumers: the rounds kernel)
+    std::vector<int32_t> big_first() const {
+        std::vector<int32_t> o;
+        o.reserve(order.size());
+        o.insert(o.end(), order.begin() + n_bulk + n_large, order.end());
+        o.insert(o.end(), order.begin() + n_bulk, order.begin() + n_bulk + n_large);
+        o.insert(o.end(), order.begin(), order.begin() + n_bulk);
+        return o;
+    }
 };
 
 void build_plan(const sa_ctx *c, const sa_problem *pr, int64_t n, int n_warp_slots, Plan &plan) {
@@ -187,6 +207,65 @@ void build_plan(const sa_ctx *c, const sa_problem *pr, int64_t n, int n_warp_slo
     for (int64_t k = 0; k < n; k++) {
         cells[(size_t)k] = (double)c->sides[0].labels(pr[k].contig) * (double)c->sides[1].labels(pr[k].seg);
         total += cells[(size_t)k];
+    }
+    bool legacy = false;
+    if (const char *e = getenv("SA_SHAPES")) legacy = strcmp(e, "legacy") == 0;
+    plan.units.clear();
+    plan.n_cpl = 0;
+    plan.cpl_max_nx = 0;
+    if (!legacy) {
+        double a = 0.25;
+        if (const char *e = getenv("SA_CPL_ALPHA")) a = atof(e);
+        const double makespan = total / (double)n_warp_slots;
+        struct Big {
+            double neg_cells;
+            int32_t k, U;
+        };
+        std::vector<Big> big;
+        double unit_frac = 0.5, u_max = 64.0;  // a unit is this fraction of the coupling threshold; at most this many units
+        if (const char *e = getenv("SA_CPL_UNIT")) unit_frac = atof(e);
+        if (const char *e = getenv("SA_CPL_UMAX")) u_max = std::max(2.0, std::min(64.0, atof(e)));
+        for (double target = std::max(a * makespan * unit_frac, 2048.0);; target *= 2.0) {  // (the loop only bounds the mailbox memory)
+            big.clear();
+            std::fill(cnt.begin(), cnt.end(), 0);
+            int64_t n_units = 0;
+            for (int64_t k = 0; k < n; k++) {
+                const double cl = cells[(size_t)k];
+                const int nb = c->sides[0].labels(pr[k].contig), nx = c->sides[1].labels(pr[k].seg);
+                const int nstrips = (nb + 31) / 32;
+                int U = 0;
+                if (a > 0 && cl > a * makespan && nstrips >= 2 && nx >= 4 && (double)nstrips * nx < 268435456.0)  // 28-bit step tags
+                    U = (int)std::min<double>(std::min<double>(std::ceil(cl / target), u_max), (double)std::min(nstrips, std::max(2, nx / 2)));
+                if (U >= 2) {
+                    big.push_back(Big{-cl, (int32_t)k, U});
+                    cls[(size_t)k] = 0xffff;
+                    n_units += U;
+                    continue;
+                }
+                int b = cl > 1.0 ? (int)(std::log2(cl) * 8.0) : 0;
+                if (b >= NB) b = NB - 1;
+                cls[(size_t)k] = (uint16_t)(NB - 1 - b);  // descending size
+                cnt[NB - 1 - b + 1]++;
+            }
+            if (n_units <= 8ll * n_warp_slots) break;
+        }
+        for (int b = 0; b < NB; b++) cnt[b + 1] += cnt[b];
+        plan.n_large = plan.n_huge = 0;
+        plan.n_cpl = (int64_t)big.size();
+        plan.n_bulk = n - plan.n_cpl;
+        plan.total_cells = total;
+        plan.order.resize((size_t)n);
+        for (int64_t k = 0; k < n; k++)
+            if (cls[(size_t)k] != 0xffff) plan.order[(size_t)cnt[cls[(size_t)k]]++] = (int32_t)k;
+        std::sort(big.begin(), big.end(), [](const Big &x, const Big &y) { return x.neg_cells < y.neg_cells || (x.neg_cells == y.neg_cells && x.k < y.k); });
+        int32_t slot = 0;
+        for (size_t i = 0; i < big.size(); i++) {
+            plan.order[(size_t)plan.n_bulk + i] = big[i].k;
+            for (int32_t u = 0; u < big[i].U; u++) plan.units.push_back(CplUnit{big[i].k, u, big[i].U, slot});
+            slot += big[i].U;
+            plan.cpl_max_nx = std::max(plan.cpl_max_nx, c->sides[1].labels(pr[big[i].k].seg));
+        }
+        return;
     }
     double alpha = 0.5;
     if (const char *e = getenv("SA_COOP_ALPHA")) alpha = atof(e);
@@ -268,6 +347,28 @@ int check_unbanded_sizes(sa_ctx *ctx, const sa_mode *mode, const sa_problem *pr,
 
 int n_fill_ctas(const sa_ctx *ctx) { return ctx->n_sms * ctx->ctas_per_sm; }
 
+static std::string cpl_debug_text(const int32_t *e) {
+    std::string t;
+    if (e[12] == 0 && e[16] == 0) return t;
+    t = "; queue head " + std::to_string(e[12]) + "; ring progress (strip:column per unit):";
+    for (int k = 0; k < 16 && k < e[3]; k++)
+        t += e[16 + k] == 0 ? " unclaimed" : " " + std::to_string((e[16 + k] >> 12) & 0x3ffff) + ":" + std::to_string(e[16 + k] & 0xfff);
+    return t;
+}
+
+// after a stream synchronisation: did a coupled-unit handshake of the last fill time out (a unit's producer never ran)?
+int cpl_check(sa_ctx *ctx) {
+    if (!ctx->cpl_pending) return SA_OK;
+    ctx->cpl_pending = false;
+    const int32_t *e = ctx->h_cpl_err.as<int32_t>();
+    if (e[0] != 0)
+        return fail(ctx, SA_ECUDA, "fill kernel: a wavefront hand-over between coupled units timed out (problem " + std::to_string(e[1]) + " unit " +
+                                       std::to_string(e[2]) + "/" + std::to_string(e[3]) + " strip " + std::to_string(e[4]) + " column " + std::to_string(e[5]) +
+                                       ": expected tag " + std::to_string(e[6]) + ", saw " + std::to_string(e[7]) + "; " + std::to_string(e[8]) + " x " +
+                                       std::to_string(e[9]) + " labels, queue entry " + std::to_string(e[10]) + ", lane " + std::to_string(e[11]) + ")" + cpl_debug_text(e));
+    return SA_OK;
+}
+
 int prepare_fill(sa_ctx *ctx, FillParams &P, const sa_mode *mode) {
     if (!mode) return fail(ctx, SA_EINVAL, "mode is NULL");
     if (ctx->sides[0].n_maps == 0 || ctx->sides[1].n_maps == 0) return fail(ctx, SA_EINVAL, "maps not uploaded");
@@ -299,6 +400,37 @@ int launch_fill_classes(sa_ctx *ctx, FillParams P, const int32_t *d_order, const
     CU(cudaMemsetAsync(counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     P.stats = counters + 4;
     int launches = 0;
+    const int64_t n_units = (int64_t)plan.units.size();
+    if (n_units > 0) {  // coupled units go first (largest problems); they and the bulk kernel drain their queues side by side
+        const long long stride = (long long)std::max(plan.cpl_max_nx, 1) * 6;
+        CU(ctx->d_units.reserve(sizeof(CplUnit) * (size_t)n_units));
+        CU(ctx->d_mbox.reserve(sizeof(unsigned long long) * (size_t)(n_units * stride)));
+        CU(ctx->d_cpl_res.reserve(sizeof(CplRes) * (size_t)n_units));
+        CU(ctx->d_cpl_done.reserve(sizeof(int32_t) * (size_t)(2 * n_units + 64)));  // + the time-out flag and its description (+ debug progress marks)
+        CU(cpy(ctx, ctx->d_units.p, plan.units.data(), sizeof(CplUnit) * (size_t)n_units, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_mbox.p, 0, sizeof(unsigned long long) * (size_t)(n_units * stride), ctx->stream));  // tag 0 = empty
+        CU(cudaMemsetAsync(ctx->d_cpl_done.p, 0, sizeof(int32_t) * (size_t)(2 * n_units + 64), ctx->stream));
+        CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        FillParams C = P;
+        C.order = nullptr;
+        C.units = ctx->d_units.as<CplUnit>();
+        C.n_problems = n_units;
+        C.counter = counters + 1;
+        C.mbox = ctx->d_mbox.as<unsigned long long>();
+        C.mbox_stride = stride;
+        C.cpl_res = ctx->d_cpl_res.as<CplRes>();
+        C.cpl_done = ctx->d_cpl_done.as<int32_t>();
+        C.cpl_error = ctx->d_cpl_done.as<int32_t>() + n_units;
+        ctx->cpl_epoch = (ctx->cpl_epoch % 15u) + 1u;
+        C.cpl_epoch = ctx->cpl_epoch << 28;
+        int64_t cpl_ctas = std::min<int64_t>((n_units + FILL_WARPS - 1) / FILL_WARPS, n_fill_ctas(ctx));
+        if (const char *e = getenv("SA_CPL_MAX_CTAS")) cpl_ctas = std::max<int64_t>(8, std::min<int64_t>(cpl_ctas, atoll(e)));  // (testing aid)
+        launch_fill(C, store, swap, 3, (int)cpl_ctas, ctx->stream2);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
+        launches++;
+    }
     if (n_large > 0 || n_huge > 0) CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
     if (n_huge > 0) {  // longest first: clusters of CLUSTER_CTAS SMs
         CU(cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork, 0));
@@ -336,7 +468,12 @@ int launch_fill_classes(sa_ctx *ctx, FillParams P, const int32_t *d_order, const
         CU(cudaGetLastError());
         launches++;
     }
-    if (n_large > 0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    if (n_large > 0 || n_units > 0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    if (n_units > 0) {  // read by cpl_check() after the caller's next synchronisation of the stream
+        CU(ctx->h_cpl_err.reserve(64 * sizeof(int32_t)));
+        CU(cudaMemcpyAsync(ctx->h_cpl_err.p, ctx->d_cpl_done.as<int32_t>() + n_units, 64 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->cpl_pending = true;
+    }
     if (n_huge > 0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join3, 0));
     ctx->timing.n_launches += launches;
     return SA_OK;
@@ -405,9 +542,10 @@ void sa_ctx_destroy(sa_ctx *ctx) {
                       &ctx->d_path_s,   &ctx->d_tmp0,   &ctx->d_tmp1,     &ctx->d_tmp2,     &ctx->d_halo2,  &ctx->d_row_off, &ctx->d_rowmax_s,
                       &ctx->d_rowmax_q, &ctx->d_prev32, &ctx->d_halo3, &ctx->d_mail, &ctx->d_r_code, &ctx->d_r_halo, &ctx->d_r_col2,
                       &ctx->d_r_lastrow, &ctx->d_r_used, &ctx->d_r_path, &ctx->d_r_ps, &ctx->d_r_thr, &ctx->d_r_rounds, &ctx->d_r_nrounds,
-                      &ctx->d_r_pj, &ctx->d_r_pq, &ctx->d_r_psc, &ctx->d_r_ctl};
+                      &ctx->d_r_pj, &ctx->d_r_pq, &ctx->d_r_psc, &ctx->d_r_ctl,
+                      &ctx->d_units, &ctx->d_mbox, &ctx->d_cpl_res, &ctx->d_cpl_done};
     for (auto b : bufs) b->release();
-    HostBuf *hbufs[] = {&ctx->h_res, &ctx->h_start, &ctx->h_pj, &ctx->h_pq, &ctx->h_ps, &ctx->h_stage};
+    HostBuf *hbufs[] = {&ctx->h_res, &ctx->h_start, &ctx->h_pj, &ctx->h_pq, &ctx->h_ps, &ctx->h_stage, &ctx->h_cpl_err};
     for (auto b : hbufs) b->release();
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -526,13 +664,13 @@ int sa_plan_results(sa_ctx *ctx, sa_plan *pl, sa_result *results) {
     CU(cudaSetDevice(ctx->device));
     CU(cpy(ctx, results, pl->d_results.p, sizeof(sa_result) * (size_t)pl->n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    return SA_OK;
+    return cpl_check(ctx);
 }
 
 int sa_plan_info(const sa_plan *pl, int64_t *n_bulk, int64_t *n_large, double *total_cells) {
     if (!pl) return SA_EINVAL;
     if (n_bulk) *n_bulk = pl->plan.n_bulk;
-    if (n_large) *n_large = pl->plan.n_large + pl->plan.n_huge;
+    if (n_large) *n_large = pl->plan.n_large + pl->plan.n_huge + pl->plan.n_cpl;
     if (total_cells) *total_cells = pl->plan.total_cells;
     return SA_OK;
 }
@@ -670,6 +808,7 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
         int64_t n_path = 0;
         CU(cpy(ctx, &n_path, d_start + m, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        if (int e = cpl_check(ctx)) return e;
         // pass 2: write the paths packed
         CU(ctx->d_path_j.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(n_path, 1)));
         CU(ctx->d_path_q.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(n_path, 1)));
@@ -707,7 +846,7 @@ static int align_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *prob
         ctx->timing.n_launches += 2;
         if (getenv("SA_VERBOSE"))
             fprintf(stderr, "  sa_align_batch chunk: %lld problems, %.3e cells, fill %.2f ms (large %lld), traceback %.2f ms, %lld path entries, chunk wall %.1f ms\n",
-                    (long long)m, (double)cells, a, (long long)(plan.n_large * 1000 + plan.n_huge), b, (long long)n_path,
+                    (long long)m, (double)cells, a, (long long)(plan.n_large * 1000 + plan.n_huge + plan.n_cpl), b, (long long)n_path,
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
         k0 = k1;
     }
@@ -879,11 +1018,7 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
             Plan plan;
             build_plan(ctx, cp.data(), m, n_fill_ctas(ctx) * FILL_WARPS, plan);
             // one queue, largest first: the size classes of the plan in descending order (huge, large, bulk)
-            std::vector<int32_t> order;
-            order.reserve((size_t)m);
-            order.insert(order.end(), plan.order.begin() + plan.n_bulk + plan.n_large, plan.order.end());
-            order.insert(order.end(), plan.order.begin() + plan.n_bulk, plan.order.begin() + plan.n_bulk + plan.n_large);
-            order.insert(order.end(), plan.order.begin(), plan.order.begin() + plan.n_bulk);
+            const std::vector<int32_t> order = plan.big_first();
             CU(ctx->d_problems.reserve(sizeof(sa_problem) * (size_t)m));
             CU(ctx->d_order.reserve(sizeof(int32_t) * (size_t)m));
             CU(ctx->d_r_thr.reserve(sizeof(float) * (size_t)m));
@@ -1122,6 +1257,7 @@ int sa_detect_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
             CU(cpy(ctx, scores_out + scores_off[k0], ctx->d_path_s.p, sizeof(float) * (size_t)soff[(size_t)m], cudaMemcpyDeviceToHost, ctx->stream));
         CU(cpy(ctx, n_got + k0, ctx->d_path_q.p, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        if (int e = cpl_check(ctx)) return e;
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
@@ -1130,7 +1266,7 @@ int sa_detect_batch(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems
         ctx->timing.n_launches += 1;
         if (getenv("SA_VERBOSE"))
             fprintf(stderr, "  sa_detect_batch chunk: %lld problems, %.3e cells, fill %.2f ms (large %lld), harvest %.2f ms\n",
-                    (long long)m, (double)cells, a, (long long)(plan.n_large * 1000 + plan.n_huge), b);
+                    (long long)m, (double)cells, a, (long long)(plan.n_large * 1000 + plan.n_huge + plan.n_cpl), b);
         k0 = k1;
     }
     return SA_OK;
@@ -1217,7 +1353,7 @@ int sa_digest(sa_ctx *ctx, const char *seq, int64_t n, const char *motif, int32_
               int64_t *pos_out, int64_t *n_out) {
     if (!ctx || !seq || !motif || !n_out || n < 0 || cap < 0 || (cap > 0 && !pos_out)) return ctx ? fail(ctx, SA_EINVAL, "bad argument") : SA_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    const size_t padded = ((size_t)n + 31) / 32 * 32 + 64;  // the kernel reads whole 32-byte chunks plus 8 bytes of look-ahead
+    const size_t padded = ((size_t)n + 31) / 32 * 32 + 128;  // the kernel reads whole 32-byte chunks plus 8 bytes of look-ahead (and prefetches one chunk ahead)
     CU(ctx->d_S.reserve(padded));  // sequence bytes (the DP matrices are not live during a digestion)
     CU(ctx->d_tmp2.reserve(64));
     const int64_t dev_cap = std::max<int64_t>(cap, 1);

@@ -555,12 +555,22 @@ constexpr int STAGE_BYTES_PER_WARP = 32 * 9 * 4 + 32 * 12 + 16;
 // STORE_MODE 3 = "rounds" (NW == 1 only): the warp keeps its pair and runs the whole run_SA_aln loop on it (main.cpp:262-300):
 // codes go to per-worker scratch, every strip's bottom rows / the last row / the last two columns persist in HBM, and each
 // later round re-sweeps only the strips its predecessor's path can influence (see rounds_finish below).
-template <int STORE_MODE, bool SWAP, int NW, int MINB, int CS>
+// CPL ("coupled units", NW == 1): the way large problems are swept since round 2.  A problem is cut into U units; unit u owns
+//             the row strips u, u+U, ... and is processed by whichever warp pulls it from the queue (units of a problem are
+//             queued consecutively, largest problems first).  Strip s needs the bottom 6 rows of strip s-1 column by column:
+//             the producing warp writes them as 8-byte {value, tag} entries (tag = s * nx + q + 1, unique within a launch)
+//             into its unit's mailbox in L2, the consuming warp issues the load at the start of the step and only looks at
+//             it at the end, re-polling while the tag is not the expected one.  No barrier, no fence (an entry is one
+//             8-byte store, self-validating), no co-scheduling constraint beyond U <= resident warps: a straggler delays
+//             only its successor, and every warp runs the bulk code at the bulk rate.  Overwriting is safe because unit u
+//             reaches strip s+U only after the whole ring of units, including its consumer, has passed strip s.
+template <int STORE_MODE, bool SWAP, int NW, int MINB, int CS, bool CPL = false>
 __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_kernel(const FillParams P) {
     constexpr bool STORE = STORE_MODE != 0;
     constexpr bool STORE_S = STORE_MODE == 2;
     constexpr bool ROUNDS = STORE_MODE == 3;
     static_assert(!ROUNDS || (NW == 1 && CS == 1 && !SWAP), "the rounds variant is one warp per pair, semi-global, no swap");
+    static_assert(!CPL || (NW == 1 && CS == 1 && !ROUNDS), "coupled units are single warps");
     constexpr int WPC = (NW == 1) ? FILL_WARPS : NW;  // warps per CTA
     constexpr int NWT = NW * CS;                        // warps in the wavefront
     static_assert(CS == 1 || NW > 1, "clusters only for the cooperative shape");
@@ -621,7 +631,22 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
             t_idx = __ldcg(reinterpret_cast<const unsigned long long *>(cmail));
         }
         if (t_idx >= (unsigned long long)P.n_problems) break;
-        const long long pidx = P.order ? P.order[t_idx] : (long long)t_idx;
+        int cu = 0, cU = 1, cslot = 0;  // coupled: this warp's unit, the units of the problem, its first mailbox slot
+        long long pidx;
+        if (CPL) {
+            const CplUnit un = P.units[t_idx];
+            pidx = un.problem;
+            cu = un.u;
+            cU = un.U;
+            cslot = un.slot0;
+        } else {
+            pidx = P.order ? P.order[t_idx] : (long long)t_idx;
+        }
+#ifdef SA_CPL_DEBUG
+        if (CPL && lane == 0) P.cpl_done[P.n_problems + 64 + cslot + cu] = 0x40000000;  // claimed
+#endif
+        const unsigned long long *mb_in = CPL ? P.mbox + (long long)(cslot + (cu + cU - 1) % cU) * P.mbox_stride : nullptr;
+        unsigned long long *mb_out = CPL ? P.mbox + (long long)(cslot + cu) * P.mbox_stride : nullptr;
         const sa_problem pr = P.problems[pidx];
         const int64_t boff = P.contigs.pos_off[pr.contig];
         const int nb = (int)(P.contigs.pos_off[pr.contig + 1] - boff) - 1;
@@ -670,10 +695,11 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
             }
         }
         for (;;) {  // one pass, except in the rounds variant
-        const int T = ROUNDS ? (r_se - r_sb) * nx : rounds * R + (NWT - 1);  // < 2^31: check_problems() rejects problems with more than 2^35 cells
+        // < 2^31: check_problems() rejects problems with more than 2^35 cells
+        const int T = ROUNDS ? (r_se - r_sb) * nx : CPL ? ((nstrips - cu + cU - 1) / cU) * nx : rounds * R + (NWT - 1);
 
         // per-warp sweep state
-        int strip = ROUNDS ? r_sb : w;
+        int strip = ROUNDS ? r_sb : CPL ? cu : w;
         int q = 0;  // column within the current round (>= nx: idle tail of a short round)
         int j = 0, jc = 0;
         bool row_ok = false, row_used = false;
@@ -693,6 +719,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         for (int t = 0; t < T; t++) {
             const bool active = (NW == 1) ? true : ((t >= w) && (strip < nstrips) && (q < nx));  // NW==1: T = nstrips*nx
             float val = 0.0f, rv = 0.0f, hv = NEG_INF;
+            unsigned long long hv_cpl = 0;  // coupled: the mailbox entry as loaded at the start of the step
             int code = 0;
             if (active) {
                 if (q == 0) {  // strip set-up: row operands into registers, ring to -inf
@@ -738,7 +765,8 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                 }
                 // rows above the strip at column q (bottom rows of strip-1)
                 if (strip > 0 && lane < 6) {
-                    if (ROUNDS) hv = __ldcg(halo + ((long long)(strip - 1) * nx + q) * 8 + lane);
+                    if (CPL) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(hv_cpl) : "l"(mb_in + (long long)q * 6 + lane) : "memory");
+                    else if (ROUNDS) hv = __ldcg(halo + ((long long)(strip - 1) * nx + q) * 8 + lane);
                     else if (NW == 1 || w == 0) hv = __ldcg(halo + (long long)q * 8 + lane);
                     else if (CS > 1 && warp == 0) hv = __ldcg(cmail + 16 + ((crank - 1) * 2 + ((t - 1) & 1)) * 8 + lane);
                     else hv = s_xbuf[warp - 1][(t - 1) & 1][lane];
@@ -888,12 +916,46 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                 // publish column q: own row, the 6 rows above the strip, and our bottom rows for the strip below
                 sts_f32(pbase, rv);
                 sts_f32(pbase + LB * RING_W * 4, rv);
+#ifdef SA_CPL_DEBUG
+                if (CPL && lane == 0) *reinterpret_cast<volatile int32_t *>(P.cpl_done + P.n_problems + 64 + cslot + cu) = 0x40000000 | (strip << 12) | q;
+#endif
+                if (CPL && strip > 0 && lane < 6) {
+                    // the entry loaded at the start of the step is valid once it carries the tag of (strip - 1, q)
+                    const uint32_t want = P.cpl_epoch | ((uint32_t)(strip - 1) * (uint32_t)nx + (uint32_t)q + 1u);
+                    for (unsigned spin = 0; (uint32_t)(hv_cpl >> 32) != want; spin++) {
+                        // ~6 s without the producer's entry: it is not running (mis-launch).  Fail loudly on the host; once the
+                        // flag is up every other wait gives up at once, so the kernel drains instead of hanging.
+                        if (spin > (1u << 25) || ((spin & 1023u) == 1023u && *reinterpret_cast<volatile int32_t *>(P.cpl_error) != 0)) {
+                            if (atomicCAS(P.cpl_error, 0, 1) == 0) {  // first failure: leave a description for the host's error text
+                                P.cpl_error[1] = (int32_t)pidx, P.cpl_error[2] = cu, P.cpl_error[3] = cU, P.cpl_error[4] = strip;
+                                P.cpl_error[5] = q, P.cpl_error[6] = (int32_t)want, P.cpl_error[7] = (int32_t)(hv_cpl >> 32);
+                                P.cpl_error[8] = nb, P.cpl_error[9] = nx, P.cpl_error[10] = (int32_t)t_idx, P.cpl_error[11] = lane;
+#ifdef SA_CPL_DEBUG
+                                for (int k = 0; k < cU && k < 16; k++)
+                                    P.cpl_error[16 + k] = *reinterpret_cast<volatile int32_t *>(P.cpl_done + P.n_problems + 64 + cslot + k);
+                                P.cpl_error[12] = (int32_t)*reinterpret_cast<volatile unsigned long long *>(P.counter);
+#endif
+                            }
+                            break;
+                        }
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(hv_cpl) : "l"(mb_in + (long long)q * 6 + lane) : "memory");
+                    }
+                    hv = __uint_as_float((uint32_t)hv_cpl);
+                }
                 if (lane < 6) {
                     sts_f32(pbase - 24, hv);  // a_halo = a_my - 6 floats
                     sts_f32(pbase - 24 + LB * RING_W * 4, hv);
                 }
+                // Coupled units: this column may only be handed on AFTER the column above it has been taken over.  That order is
+                // what keeps a producer from overwriting a mailbox entry its consumer still needs (the ring argument above), and
+                // divergent lanes of a warp are not ordered by themselves: measured on B200, lanes 26..31 published while lanes
+                // 0..5 were still polling, a whole ring ran ahead on it and overwrote entries (hand-overs then never arrived).
+                if (CPL) __syncwarp();
                 if (lane >= 26) {
-                    if (ROUNDS) __stcg(halo + ((long long)strip * nx + q) * 8 + (lane - 26), rv);
+                    if (CPL) {
+                        const unsigned long long e = ((unsigned long long)(P.cpl_epoch | ((uint32_t)strip * (uint32_t)nx + (uint32_t)q + 1u)) << 32) | __float_as_uint(rv);
+                        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(mb_out + (long long)q * 6 + (lane - 26)), "l"(e) : "memory");
+                    } else if (ROUNDS) __stcg(halo + ((long long)strip * nx + q) * 8 + (lane - 26), rv);
                     else if (NW == 1 || w == NWT - 1) __stcg(halo + (long long)q * 8 + (lane - 26), rv);
                     else if (CS > 1 && warp == NW - 1) __stcg(cmail + 16 + (crank * 2 + (t & 1)) * 8 + (lane - 26), rv);
                     else s_xbuf[warp][t & 1][lane - 26] = rv;
@@ -973,7 +1035,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                 q++;
                 if (q == R) {
                     q = 0;
-                    strip += NWT;
+                    strip += CPL ? cU : NWT;
                 }
             }
         }
@@ -1056,6 +1118,34 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         if (P.stats) {
             const unsigned a = __reduce_add_sync(0xffffffffu, n_replay);
             if (lane == 0) atomicAdd(P.stats, (unsigned long long)a);
+        }
+        if (CPL) {
+            // every unit leaves its candidate; the unit that finishes last picks the winner (same rule as between lanes)
+            bool last = false;
+            if (lane == 0) {
+                CplRes r;
+                r.score = st_s, r.j = st_j, r.q = st_q, r.pad = 0, r.ord = st_ord;
+                P.cpl_res[cslot + cu] = r;
+                __threadfence();
+                last = atomicAdd(P.cpl_done + cslot, 1) == cU - 1;
+                if (last) {
+                    __threadfence();
+                    st_j = -1;
+                    for (int k = 0; k < cU; k++) {
+                        const CplRes *o = P.cpl_res + cslot + k;
+                        const float os = __ldcg(&o->score);
+                        const int oj = __ldcg(&o->j), oq = __ldcg(&o->q);
+                        const long long oo = __ldcg(&o->ord);
+                        if (oj >= 0 && (st_j < 0 || os > st_s || (os == st_s && oo < st_ord))) {
+                            st_s = os;
+                            st_j = oj;
+                            st_q = oq;
+                            st_ord = oo;
+                        }
+                    }
+                }
+            }
+            if (!__shfl_sync(0xffffffffu, (int)last, 0)) continue;  // the result is written by lane 0 of the last unit
         }
         if ((NW == 1 && lane == 0) || (NW > 1 && threadIdx.x == 0 && crank == 0)) {
             sa_result res;
@@ -1527,7 +1617,7 @@ static size_t fill_dyn_smem(int wpc, bool store = true) {
     return TAB_SMEM_BYTES + (size_t)wpc * (2 * LB * RING_W + 2 * LB * 32) * sizeof(float) +
            (store ? (size_t)wpc * STAGE_BYTES_PER_WARP : 0);
 }
-template <int NW, int MINB, int CS>
+template <int NW, int MINB, int CS, bool CPL = false>
 static void launch_fill_t(const FillParams &p, int store, bool swap, int n_ctas, cudaStream_t st) {
     const size_t sm = fill_dyn_smem(NW == 1 ? FILL_WARPS : NW, store != 0);
     cudaLaunchConfig_t cfg = {};
@@ -1544,11 +1634,11 @@ static void launch_fill_t(const FillParams &p, int store, bool swap, int n_ctas,
     cfg.numAttrs = (CS > 1) ? 1 : 0;
 #define SA_LAUNCH_FILL(S_, W_)                                                                                         \
     do {                                                                                                               \
-        cudaFuncSetAttribute(fill_kernel<S_, W_, NW, MINB, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-        cudaLaunchKernelEx(&cfg, fill_kernel<S_, W_, NW, MINB, CS>, p);                                                \
+        cudaFuncSetAttribute(fill_kernel<S_, W_, NW, MINB, CS, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        cudaLaunchKernelEx(&cfg, fill_kernel<S_, W_, NW, MINB, CS, CPL>, p);                                                \
     } while (0)
     if (store == 3) {  // the rounds variant exists for the bulk shape only (one warp per pair), semi-global, no swap
-        if constexpr (NW == 1 && CS == 1) SA_LAUNCH_FILL(3, false);
+        if constexpr (NW == 1 && CS == 1 && !CPL) SA_LAUNCH_FILL(3, false);
     } else if (store == 2) {
         if (swap) SA_LAUNCH_FILL(2, true);
         else SA_LAUNCH_FILL(2, false);
@@ -1563,7 +1653,8 @@ static void launch_fill_t(const FillParams &p, int store, bool swap, int n_ctas,
 }
 // shape: 0 = bulk (one warp per problem), 1 = cooperative CTA, 2 = cooperative cluster of CLUSTER_CTAS CTAs
 void launch_fill(const FillParams &p, int store, bool swap, int shape, int n_ctas, cudaStream_t st) {
-    if (shape == 2) launch_fill_t<CLUSTER_WARPS, 1, CLUSTER_CTAS>(p, store, swap, n_ctas, st);
+    if (shape == 3) launch_fill_t<1, FILL_MINB, 1, true>(p, store, swap, n_ctas, st);
+    else if (shape == 2) launch_fill_t<CLUSTER_WARPS, 1, CLUSTER_CTAS>(p, store, swap, n_ctas, st);
     else if (shape == 1) launch_fill_t<COOP_WARPS, COOP_MINB, 1>(p, store, swap, n_ctas, st);
     else launch_fill_t<1, FILL_MINB, 1>(p, store, swap, n_ctas, st);
 }

@@ -28,6 +28,19 @@ struct MapSetDev {
     int32_t max_labels;
 };
 
+// Wavefront units (see "coupled units" in sa_kernels.cu): a large problem is swept by U warps anywhere on the GPU; unit u owns
+// the row strips u, u+U, u+2U, ... and hands the bottom rows of each to unit (u+1) % U through a tagged mailbox in L2.
+struct CplUnit {
+    int32_t problem;  // index into FillParams::problems
+    int32_t u, U;
+    int32_t slot0;    // mailbox / result slot of the problem's unit 0 (its units occupy slot0 .. slot0 + U - 1)
+};
+struct CplRes {  // a unit's backtrack-start candidate
+    float score;
+    int32_t j, q, pad;
+    long long ord;
+};
+
 struct FillParams {
     MapSetDev contigs, segs;
     const sa_problem *problems;
@@ -49,6 +62,14 @@ struct FillParams {
     int32_t *rowmax_q;
     const int64_t *row_off;  // per problem offset into the rowmax arrays
     double pk[12];  // fp64 constants of the powf replay (kernel-parameter bank => direct DFMA operands)
+    // ---- coupled units (CPL variant): n_problems counts UNITS, `order` is unused
+    const CplUnit *units;
+    unsigned long long *mbox;  // [slots][mbox_stride] entries {fp32 value, tag}: 6 per column, tag = producing strip * nx + q + 1
+    long long mbox_stride;
+    CplRes *cpl_res;           // [slots]
+    int32_t *cpl_done;         // [slots] (entry slot0 of a problem counts its finished units)
+    int32_t *cpl_error;        // set when a handshake timed out (never, unless the kernel was mis-launched)
+    uint32_t cpl_epoch;        // launch number in the top 4 bits of every tag (the low 28 bits count the problem's steps)
     // ---- STORE_MODE 3 ("rounds", sa_align_rounds): the whole `while` loop of run_SA_aln (main.cpp:268-300) per pair on one
     // warp.  Per-worker scratch (one slot per resident warp) that persists across the rounds of a pair:
     uint8_t *r_code;        // [workers][r_cells]         predecessor codes of the pair's whole matrix
@@ -107,6 +128,7 @@ struct DetectParams {
 
 void launch_detect(const DetectParams &p, cudaStream_t st);
 // store: 0 = scoring (nothing per cell), 1 = predecessor codes, 2 = codes + scores (+ per-row maxima when requested)
+// shape: 0 = bulk (one warp per problem), 1 = cooperative CTA, 2 = cooperative cluster, 3 = coupled units (one warp per unit)
 void launch_fill(const FillParams &p, int store, bool swap, int shape, int n_ctas, cudaStream_t st);
 int max_clusters();
 void launch_fill_unbanded(const FillParams &p, int32_t *prev32, bool swap, int n_ctas, cudaStream_t st);

@@ -32,5 +32,7 @@ mode = ctx.mode(0, 1, 0, 6, 1)
 for rep in range(2):
     t0 = time.time(); sc, o, got = ctx.detect_batch(mode, pr, want); t1 = time.time()
     tm = ctx.timing()
-    print(f"rep{rep}: {pr.size} problems {cells:.3e} cells: fill {tm.fill_ms:.1f} ms ({cells/tm.fill_ms/1e6:.2f} GCUPS), harvest {tm.post_ms:.1f} ms, call {t1-t0:.3f} s")
+    import hashlib
+    h = hashlib.sha256(sc.tobytes() + got.tobytes()).hexdigest()[:16]
+    print(f"rep{rep}: [{h}] {pr.size} problems {cells:.3e} cells: fill {tm.fill_ms:.1f} ms ({cells/tm.fill_ms/1e6:.2f} GCUPS), harvest {tm.post_ms:.1f} ms, call {t1-t0:.3f} s")
 shutil.rmtree(tmp)

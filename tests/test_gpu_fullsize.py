@@ -32,19 +32,24 @@ def test_c2_shaped_batch_properties(ctx, oracle, monkeypatch):
     c_, s_ = np.meshgrid(np.arange(len(cid), dtype=np.int32), np.arange(len(fid), dtype=np.int32), indexing="ij")
     pr = ctx.problems(c_.ravel(), s_.ravel())
     mode = ctx.mode(capi.SA_INIT_SEMIGLOBAL, capi.SA_START_SEMIGLOBAL, 0, 6, 0)
-    monkeypatch.setenv("SA_COOP_ALPHA", "0.5")
     res = ctx.score_batch(mode, pr)
     again = ctx.score_batch(mode, pr)
     assert res.tobytes() == again.tobytes(), "scoring is not idempotent"
-    # the biggest problems through each cooperative shape, the rest through the bulk kernel
+    # the biggest problems one warp each, as coupled units (default for large problems; here: every one of them, cut as fine as
+    # the planner allows) and through each barrier-synchronised shape of round 1
     order = np.argsort(-(ctx.n_labels[0][pr["contig"]] * ctx.n_labels[1][pr["seg"]]))
     big = pr[order[:300]]
-    for alpha, no_cluster in (("0", "1"), ("1e-9", "1"), ("1e-9", "0")):
+    for shapes, cpl_alpha, alpha, no_cluster in (("coupled", "0", "0", "1"), ("coupled", "1e-9", "0", "1"), ("legacy", "0", "1e-9", "1"),
+                                                 ("legacy", "0", "1e-9", "0")):
+        monkeypatch.setenv("SA_SHAPES", shapes)
+        monkeypatch.setenv("SA_CPL_ALPHA", cpl_alpha)
         monkeypatch.setenv("SA_COOP_ALPHA", alpha)
         monkeypatch.setenv("SA_NO_CLUSTER", no_cluster)
         monkeypatch.setenv("SA_HUGE_MIN_CELLS", "0")
         r = ctx.score_batch(mode, big)
-        assert r.tobytes() == res[order[:300]].tobytes(), f"kernel shapes disagree (alpha={alpha}, no_cluster={no_cluster})"
+        assert r.tobytes() == res[order[:300]].tobytes(), f"kernel shapes disagree ({shapes}, cpl_alpha={cpl_alpha}, alpha={alpha}, no_cluster={no_cluster})"
+    for k in ("SA_SHAPES", "SA_CPL_ALPHA", "SA_COOP_ALPHA", "SA_NO_CLUSTER", "SA_HUGE_MIN_CELLS"):
+        monkeypatch.delenv(k)
     # seeded sample against the oracle
     rng = np.random.default_rng(42)
     full = capi.unflatten_maps(fid, foff, fpos)

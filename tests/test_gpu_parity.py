@@ -46,14 +46,20 @@ def upload(ctx, maps, probs, side):
     return ids
 
 
-@pytest.fixture(params=["bulk", "coop", "cluster"])
+@pytest.fixture(params=["bulk", "coupled", "coop", "cluster"])
 def kernel_class(request, monkeypatch):
-    """Run a parity case three times: through the one-warp-per-problem kernel, the cooperative 8-warp CTA wavefront and
-    the 8-CTA x 16-warp thread-block-cluster wavefront (forced by absurdly low size-class thresholds).  Requested only
-    by the tests whose result depends on the kernel shape (the powf / pruning-bound sweeps do not)."""
-    monkeypatch.setenv("SA_COOP_ALPHA", "0" if request.param == "bulk" else "1e-9")
-    monkeypatch.setenv("SA_NO_CLUSTER", "0" if request.param == "cluster" else "1")
-    monkeypatch.setenv("SA_HUGE_MIN_CELLS", "0")
+    """Run a parity case through every way a problem can be swept: one warp per problem, coupled units (several warps
+    anywhere on the GPU handing strip boundaries over through tagged mailboxes; the default for large problems), and the two
+    barrier-synchronised shapes of round 1 (8-warp CTA wavefront, 8-CTA x 16-warp cluster wavefront; SA_SHAPES=legacy).
+    Forced by absurdly low size thresholds.  Requested only by the tests whose result depends on the shape."""
+    if request.param == "coupled":
+        monkeypatch.setenv("SA_SHAPES", "coupled")
+        monkeypatch.setenv("SA_CPL_ALPHA", "1e-9")
+    else:
+        monkeypatch.setenv("SA_SHAPES", "legacy")
+        monkeypatch.setenv("SA_COOP_ALPHA", "0" if request.param == "bulk" else "1e-9")
+        monkeypatch.setenv("SA_NO_CLUSTER", "0" if request.param == "cluster" else "1")
+        monkeypatch.setenv("SA_HUGE_MIN_CELLS", "0")
     return request.param
 
 
