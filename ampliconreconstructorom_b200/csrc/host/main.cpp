@@ -24,6 +24,7 @@
 #include <thread>
 #include <unordered_map>
 #include <vector>
+#include <fcntl.h>
 #include <sched.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -709,7 +710,14 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open, Spmd &sp
         int asked = o.n_gpus;
         if (asked <= 0)
             if (const char *e = getenv("SA_NGPUS")) asked = atoi(e);
-        if (asked <= 0 && total_cells <= 2e10) sp.world = 1;
+        if (asked <= 0) {
+            // Nobody asked for a number of GPUs: a fixed-size job gains from another GPU only while its share of the work
+            // outweighs the start-up ladder (~0.8 s per additional GPU, driver-side; every rank must be up before the first
+            // exchange).  Whole run ~ cells / 25 GCUPS on one GPU; f(N) = 0.8 (N - 1) + t1 / N is smallest at sqrt(t1 / 0.8).
+            const double t1 = total_cells / 25e9;
+            const int best = (int)std::floor(std::sqrt(t1 / 0.8) + 0.5);
+            sp.world = std::max(1, std::min(sp.world, best));
+        }
         if (o.fitting_aln || segs.n_maps() == 0 || contigs.n_maps() == 0) sp.world = 1;
     }
     if (sp.rank >= sp.world) {
@@ -1004,6 +1012,17 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open, Spmd &sp
     }
     fflush(stdout);
     fflush(stderr);
+    if (sp.world > 1 && sp.rank > 0) {
+        // A worker rank is done once every rank has passed the last exchange: its files are written.  Tearing its context down
+        // (serialised by the driver across the processes of a box, ~0.4 s each) happens at process exit, in the background:
+        // give up the inherited stderr so that a caller reading our pipes does not wait for it.
+        const int dn = ::open("/dev/null", O_WRONLY);
+        if (dn >= 0) {
+            dup2(dn, 2);
+            ::close(dn);
+        }
+        return 0;
+    }
     if (!keep_open) eng.close();  // orderly teardown: abandoning the context only moves the cost to the next start
     pt.lap("close");
     return 0;
@@ -1371,9 +1390,18 @@ int main(int argc, char *argv[]) {
     fflush(stdout);
     fflush(stderr);
     if (sp.rank > 0) _exit(code);
-    for (pid_t k : sp.kids) {  // the run is over when every rank's files are written
+    if (const char *e = getenv("SA_FAST_EXIT"))  // (experiment: leave without the CUDA runtime's exit handlers)
+        if (atoi(e) != 0) _exit(code);
+    // The run is over when every rank's files are written.  After a successful run every rank has passed the last exchange, so
+    // the workers only have their CUDA teardown left: they are not waited for (they are reaped by init).  After a failure the
+    // workers are collected so that nothing of this run is left behind.
+    for (pid_t k : sp.kids) {
         int st = 0;
-        if (waitpid(k, &st, 0) == k && !(WIFEXITED(st) && WEXITSTATUS(st) == 0) && code == 0) code = 2;
+        if (code == 0 && sp.world > 1) {
+            if (waitpid(k, &st, WNOHANG) == k && !(WIFEXITED(st) && WEXITSTATUS(st) == 0)) code = 2;
+        } else if (waitpid(k, &st, 0) == k && !(WIFEXITED(st) && WEXITSTATUS(st) == 0) && code == 0 && sp.world > 1) {
+            code = 2;
+        }
     }
     return code;
 }

@@ -8,7 +8,8 @@
 // 18 fp64 operations, one final round to fp32.  It is NOT correctly rounded, so a generic pow cannot
 // substitute: the exact operation sequence (including which multiply-adds are fused) must be replayed.
 // The sequence below was read off the disassembly of __powf_fma in this image's libm.so.6 and is
-// checked exhaustively against the host powf in tests (tests/test_powf12.py, csrc/tools/powf_check.cu).
+// checked exhaustively against the host powf: the host-compiled replay in tests/test_powf12_host.py (csrc/tools/powf_check_host.cpp),
+// both device paths in tests/test_gpu_parity.py::test_powf12_device_exhaustive (every non-negative float).
 //
 // Compiles as host code (SA_HD empty, uses fma()) and as device code (DFMA is IEEE-754 fused).
 #pragma once

@@ -235,7 +235,7 @@ void build_plan(const sa_ctx *c, const sa_problem *pr, int64_t n, int n_warp_slo
                 const int nstrips = (nb + 31) / 32;
                 int U = 0;
                 if (a > 0 && cl > a * makespan && nstrips >= 2 && nx >= 4 && (double)nstrips * nx < 268435456.0)  // 28-bit step tags
-                    U = (int)std::min<double>(std::min<double>(std::ceil(cl / target), u_max), (double)std::min(nstrips, std::max(2, nx / 2)));
+                    U = (int)std::min<double>(std::min<double>(std::ceil(cl / target), u_max), (double)std::min(nstrips, std::max(2, nx / 4)));  // a ring of U units lags 3 U columns: keep it below nx
                 if (U >= 2) {
                     big.push_back(Big{-cl, (int32_t)k, U});
                     cls[(size_t)k] = 0xffff;

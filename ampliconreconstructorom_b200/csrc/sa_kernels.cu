@@ -535,6 +535,7 @@ __device__ __noinline__ bool rounds_finish(const FillParams &P, long long gunit,
 }
 
 constexpr int RING_W = 40;  // 6 halo rows + 32 lanes + 2 pad
+constexpr int CPL_LAG = 2;  // coupled units: columns a consumer stays behind its producer
 // STORE staging per warp: scores [32][9] floats + codes [32][12] bytes + the problem's cell offset (8 B, read back at every
 // flush from shared memory instead of living in registers or being re-fetched from global memory)
 constexpr int STAGE_BYTES_PER_WARP = 32 * 9 * 4 + 32 * 12 + 16;
@@ -723,6 +724,22 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
             int code = 0;
             if (active) {
                 if (q == 0) {  // strip set-up: row operands into registers, ring to -inf
+                    if (CPL && strip > 0) {
+                        // Start CPL_LAG columns behind the producer of the rows above: in steady state the entry for column q
+                        // is then already in L2 when the step begins and the poll at its end never spins (measured before:
+                        // 10 % of the warp time of the detection fill went into that spin, units running in lock-step).
+                        const int ql = nx - 1 < CPL_LAG ? nx - 1 : CPL_LAG;
+                        const uint32_t want = P.cpl_epoch | ((uint32_t)(strip - 1) * (uint32_t)nx + (uint32_t)ql + 1u);
+                        if (lane == 0) {
+                            unsigned long long e = 0;
+                            for (unsigned spin = 0; spin < (1u << 25); spin++) {
+                                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(e) : "l"(mb_in + (long long)ql * 6) : "memory");
+                                if ((uint32_t)(e >> 32) == want) break;
+                                if ((spin & 1023u) == 1023u && *reinterpret_cast<volatile int32_t *>(P.cpl_error) != 0) break;
+                            }
+                        }
+                        __syncwarp();
+                    }
                     j = (strip << 5) + lane;
                     row_ok = j < nb;
                     jc = row_ok ? j : nb - 1;

@@ -12,7 +12,7 @@ scores that must be identical for every N (strong scaling).
                resident in HBM), max over ranks; all cells of the batch / that time.
   e2e          THE DROP-IN BOUNDARY: the executable bin/SegAligner (what ARAlignDetect.py / OMPathFinder.py exec) on the
                full workload from CMAP files to output files -- CUDA start-up, parse, phase-1 scoring, thresholds,
-               alignment rounds, tip alignment, ~28 k *_aln.txt files -- on N GPUs (-ngpus=N, one process, one host thread
+               alignment rounds, tip alignment, ~28 k *_aln.txt files -- on N GPUs (-ngpus=N: one process
                and one context per GPU, problems sharded by index).  Same definition as the reference arm and
                cpu_baseline: phase-1 scoring cells / process wall time.  Host<->device bytes are the library's own counters.
   e2e_scoring  the scoring phase alone through the host-buffer C-ABI calls (sa_set_maps + sa_score_batch on this rank's
