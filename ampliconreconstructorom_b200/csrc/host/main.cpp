@@ -1390,8 +1390,6 @@ int main(int argc, char *argv[]) {
     fflush(stdout);
     fflush(stderr);
     if (sp.rank > 0) _exit(code);
-    if (const char *e = getenv("SA_FAST_EXIT"))  // (experiment: leave without the CUDA runtime's exit handlers)
-        if (atoi(e) != 0) _exit(code);
     // The run is over when every rank's files are written.  After a successful run every rank has passed the last exchange, so
     // the workers only have their CUDA teardown left: they are not waited for (they are reaped by init).  After a failure the
     // workers are collected so that nothing of this run is left behind.

@@ -338,6 +338,35 @@ __device__ __forceinline__ float delta_lo_approx(float d) {
     return e;
 }
 
+// Packed fp32 (sm_100 add/sub/fma .f32x2: two IEEE round-to-nearest operations per instruction, bit-identical to the scalar
+// ones).  The bound pass evaluates candidates in pairs; packing its five chain operations halves their issue slots, the
+// kernel's second ceiling next to the MUFU pipe.  SA_PACKED 0 keeps the scalar chain (A/B timing).
+#ifndef SA_PACKED
+#define SA_PACKED 1
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // powf(ax, 1.2f), inline fast path with the generic path behind a (rare) branch
 __device__ __forceinline__ float powf12_exact(float ax, const TabAddr ta, const double (&pk)[12]) {
     uint32_t u;
@@ -804,6 +833,22 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
 #pragma unroll
                     for (int dj = 1; dj <= LB; dj++) {
                         float hi[LB];
+#if SA_PACKED
+#pragma unroll
+                        for (int c = 0; c < LB; c += 2) {  // two candidates per chain: same operations, same order, packed
+                            const float sc0 = lds_f32(PC(c) - dj * 4), sc1 = lds_f32(PC(c + 1) - dj * 4);
+                            float a0, a1, e0, e1, t0, t1;
+                            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(a0) : "f"(fabsf(__fsub_rn(db[dj - 1], dx[c]))));
+                            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(a1) : "f"(fabsf(__fsub_rn(db[dj - 1], dx[c + 1]))));
+                            upk2(fma2(pk2(a0, a1), pk2(1.2f, 1.2f), pk2(-PRUNE_C, -PRUNE_C)), t0, t1);
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+                            f32x2 fnfp;  // fn_t + fp_t (SegAligner.cpp:89-91); 0 + fp_t == fp_t bit for bit (fp_t >= +0)
+                            if (!SWAP) fnfp = (dj == 1) ? pk2(fx[c], fx[c + 1]) : add2(pk2(5000.0f * (float)(dj - 1), 5000.0f * (float)(dj - 1)), pk2(fx[c], fx[c + 1]));
+                            else fnfp = add2(pk2(5000.0f * (float)c, 5000.0f * (float)(c + 1)), pk2(fb[dj - 1], fb[dj - 1]));
+                            upk2(add2(pk2(sc0, sc1), sub2(pk2(10000.0f, 10000.0f), add2(fnfp, pk2(e0, e1)))), hi[c], hi[c + 1]);
+                        }
+#else
 #pragma unroll
                         for (int c = 0; c < LB; c++) {
                             const float sc = lds_f32(PC(c) - dj * 4);
@@ -813,6 +858,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                             else fnfp = (c == 0) ? fb[dj - 1] : __fadd_rn(5000.0f * (float)c, fb[dj - 1]);
                             hi[c] = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, e)));
                         }
+#endif
 #pragma unroll
                         for (int c = 0; c < LB; c += 2) {
                             const float mx = fmaxf(hi[c], hi[c + 1]), mn = fminf(hi[c], hi[c + 1]);
