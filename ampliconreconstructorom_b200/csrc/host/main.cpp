@@ -896,8 +896,16 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open, Spmd &sp
         }
     }
     pt.lap("phase 1 scoring (GPU)");
-    if (sp.rank == 0) write_all_scores(rows, o.sample_prefix);
-    pt.lap("write all_scores");
+    // *_all_scores.txt (10^6..10^7 rows) is formatted and written beside the thresholds and the alignment passes, which only
+    // read `rows`; joined before the run reports its end
+    std::thread scores_writer;
+    struct ScoresJoiner {
+        std::thread &t;
+        ~ScoresJoiner() {
+            if (t.joinable()) t.join();
+        }
+    } scores_joiner{scores_writer};
+    if (sp.rank == 0) scores_writer = std::thread([&rows, &o]() { write_all_scores(rows, o.sample_prefix); });
 
     // ---------------- phase 2: thresholds (main.cpp:555-557); every rank computes the same values ---------------------
     std::vector<std::vector<std::pair<int, float>>> thr2;
@@ -1004,6 +1012,7 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open, Spmd &sp
             h2d = sp.ctl->h2d.load();
             d2h = sp.ctl->d2h.load();
         }
+        if (scores_writer.joinable()) scores_writer.join();
         printf("elapsed seconds for run %f\n", double(clock() - begin) / CLOCKS_PER_SEC);
         if (getenv("SA_VERBOSE") && sp.rank == 0) {
             fprintf(stderr, "SegAligner(b200): copied H2D %llu bytes, D2H %llu bytes\n", (unsigned long long)h2d, (unsigned long long)d2h);

@@ -186,6 +186,7 @@ struct Plan {
     int64_t n_bulk = 0, n_large = 0, n_huge = 0, n_cpl = 0;
     std::vector<CplUnit> units;  // coupled mode: the unit queue, largest problems first, units of a problem consecutive
     int cpl_max_nx = 0;
+    double cpl_max_unit_cells = 0;  // largest unit (a unit's warp may legitimately be waited for that long)
     double total_cells = 0;
     // every problem, largest classes first (one-warp-per-problem consumers: the rounds kernel)
     std::vector<int32_t> big_first() const {
@@ -213,6 +214,7 @@ void build_plan(const sa_ctx *c, const sa_problem *pr, int64_t n, int n_warp_slo
     plan.units.clear();
     plan.n_cpl = 0;
     plan.cpl_max_nx = 0;
+    plan.cpl_max_unit_cells = 0;
     if (!legacy) {
         double a = 0.25;
         if (const char *e = getenv("SA_CPL_ALPHA")) a = atof(e);
@@ -225,7 +227,8 @@ void build_plan(const sa_ctx *c, const sa_problem *pr, int64_t n, int n_warp_slo
         double unit_frac = 0.5, u_max = 64.0;  // a unit is this fraction of the coupling threshold; at most this many units
         if (const char *e = getenv("SA_CPL_UNIT")) unit_frac = atof(e);
         if (const char *e = getenv("SA_CPL_UMAX")) u_max = std::max(2.0, std::min(64.0, atof(e)));
-        for (double target = std::max(a * makespan * unit_frac, 2048.0);; target *= 2.0) {  // (the loop only bounds the mailbox memory)
+        // (a unit is at most ~1 s of one warp: waits on units that are not running yet stay short; the loop bounds the mailbox memory)
+        for (double target = std::min(std::max(a * makespan * unit_frac, 2048.0), 1.3e7);; target *= 2.0) {
             big.clear();
             std::fill(cnt.begin(), cnt.end(), 0);
             int64_t n_units = 0;
@@ -264,6 +267,7 @@ void build_plan(const sa_ctx *c, const sa_problem *pr, int64_t n, int n_warp_slo
             for (int32_t u = 0; u < big[i].U; u++) plan.units.push_back(CplUnit{big[i].k, u, big[i].U, slot});
             slot += big[i].U;
             plan.cpl_max_nx = std::max(plan.cpl_max_nx, c->sides[1].labels(pr[big[i].k].seg));
+            plan.cpl_max_unit_cells = std::max(plan.cpl_max_unit_cells, -big[i].neg_cells / big[i].U);
         }
         return;
     }
@@ -424,6 +428,9 @@ int launch_fill_classes(sa_ctx *ctx, FillParams P, const int32_t *d_order, const
         C.cpl_error = ctx->d_cpl_done.as<int32_t>() + n_units;
         ctx->cpl_epoch = (ctx->cpl_epoch % 15u) + 1u;
         C.cpl_epoch = ctx->cpl_epoch << 28;
+        // A warp may wait for a unit that no warp has pulled yet (the ring's last unit of a partially claimed problem): at most
+        // about one unit's duration (~1.3e7 cells/s per warp).  Ten of those, one poll ~0.2 us, at least 2^25 polls (~6 s).
+        C.cpl_spin_limit = (uint32_t)std::min(4.0e9, std::max(33554432.0, 10.0 * plan.cpl_max_unit_cells / 1.3e7 / 2.0e-7));
         int64_t cpl_ctas = std::min<int64_t>((n_units + FILL_WARPS - 1) / FILL_WARPS, n_fill_ctas(ctx));
         if (const char *e = getenv("SA_CPL_MAX_CTAS")) cpl_ctas = std::max<int64_t>(8, std::min<int64_t>(cpl_ctas, atoll(e)));  // (testing aid)
         launch_fill(C, store, swap, 3, (int)cpl_ctas, ctx->stream2);
@@ -520,8 +527,9 @@ int sa_ctx_create(int device, sa_ctx **out) {
     ctx->ctas_per_sm = fill_ctas_per_sm();
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    // stored matrices cost 5 bytes per cell; keep a chunk below a third of free memory
-    ctx->store_budget_cells = free_b / 3 / 5;
+    // stored matrices cost 5 bytes per cell; a chunk may take 45 % of free memory (the whole C3 detection sweep, 1.33 x 10^10
+    // cells = 67 GB, is then one chunk on a 180 GB B200; the rest holds maps, row maxima, mailboxes and the next allocations)
+    ctx->store_budget_cells = (size_t)((double)free_b * 0.45 / 5.0);
     if (const char *e = getenv("SA_STORE_BUDGET_CELLS")) ctx->store_budget_cells = (size_t)atoll(e);
     *out = ctx;
     return SA_OK;

@@ -761,7 +761,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                         const uint32_t want = P.cpl_epoch | ((uint32_t)(strip - 1) * (uint32_t)nx + (uint32_t)ql + 1u);
                         if (lane == 0) {
                             unsigned long long e = 0;
-                            for (unsigned spin = 0; spin < (1u << 25); spin++) {
+                            for (unsigned spin = 0; spin < P.cpl_spin_limit; spin++) {
                                 asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(e) : "l"(mb_in + (long long)ql * 6) : "memory");
                                 if ((uint32_t)(e >> 32) == want) break;
                                 if ((spin & 1023u) == 1023u && *reinterpret_cast<volatile int32_t *>(P.cpl_error) != 0) break;
@@ -986,9 +986,9 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     // the entry loaded at the start of the step is valid once it carries the tag of (strip - 1, q)
                     const uint32_t want = P.cpl_epoch | ((uint32_t)(strip - 1) * (uint32_t)nx + (uint32_t)q + 1u);
                     for (unsigned spin = 0; (uint32_t)(hv_cpl >> 32) != want; spin++) {
-                        // ~6 s without the producer's entry: it is not running (mis-launch).  Fail loudly on the host; once the
+                        // cpl_spin_limit polls (>= ~6 s, ten times the longest unit of the launch) without the producer's entry: it is not running.  Fail loudly on the host; once the
                         // flag is up every other wait gives up at once, so the kernel drains instead of hanging.
-                        if (spin > (1u << 25) || ((spin & 1023u) == 1023u && *reinterpret_cast<volatile int32_t *>(P.cpl_error) != 0)) {
+                        if (spin > P.cpl_spin_limit || ((spin & 1023u) == 1023u && *reinterpret_cast<volatile int32_t *>(P.cpl_error) != 0)) {
                             if (atomicCAS(P.cpl_error, 0, 1) == 0) {  // first failure: leave a description for the host's error text
                                 P.cpl_error[1] = (int32_t)pidx, P.cpl_error[2] = cu, P.cpl_error[3] = cU, P.cpl_error[4] = strip;
                                 P.cpl_error[5] = q, P.cpl_error[6] = (int32_t)want, P.cpl_error[7] = (int32_t)(hv_cpl >> 32);

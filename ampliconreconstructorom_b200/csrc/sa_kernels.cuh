@@ -70,6 +70,7 @@ struct FillParams {
     int32_t *cpl_done;         // [slots] (entry slot0 of a problem counts its finished units)
     int32_t *cpl_error;        // set when a handshake timed out (never, unless the kernel was mis-launched)
     uint32_t cpl_epoch;        // launch number in the top 4 bits of every tag (the low 28 bits count the problem's steps)
+    uint32_t cpl_spin_limit;   // polls after which a hand-over counts as lost (host: ~10 x the duration of the longest unit)
     // ---- STORE_MODE 3 ("rounds", sa_align_rounds): the whole `while` loop of run_SA_aln (main.cpp:268-300) per pair on one
     // warp.  Per-worker scratch (one slot per resident warp) that persists across the rounds of a pair:
     uint8_t *r_code;        // [workers][r_cells]         predecessor codes of the pair's whole matrix

@@ -7,8 +7,9 @@ import numpy as np
 
 def shard_problems(cells: np.ndarray, world: int, rank: int) -> np.ndarray:
     """Indices of the problems `rank` handles: problems sorted by size (largest first, stable) and dealt round-robin, so
-    every rank gets the same mix of sizes.  (The executable's multi-GPU engine, csrc/host/main.cpp Engine::shard, deals
-    round-robin within 1/4-octave size classes instead of a full sort -- same balance, O(n).)"""
+    every rank gets the same mix of sizes.  (The executable, csrc/host/main.cpp, deals its alignment passes round-robin within
+    1/4-octave size classes instead of a full sort (my_shard: same balance, O(n)) and hands phase 1 out dynamically in runs of
+    the same largest-first order, because its GPU processes come up one after the other.)"""
     order = np.argsort(-cells.astype(np.int64), kind="stable")
     return order[rank::world]
 
