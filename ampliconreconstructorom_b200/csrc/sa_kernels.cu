@@ -747,6 +747,45 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         int rm_q = -1;
 
         for (int t = 0; t < T; t++) {
+            if (ROUNDS && q == 0) {
+                // Strips whose 32 rows are ALL used labels are not swept: dp_align leaves a used row at its initial values with
+                // no predecessor (SegAligner.cpp:104-106), so the strip's outputs are known -- codes 0, and init_semiglobal_aln's
+                // values (row 0 and columns 0, 1: 0, else -inf) in the strip-boundary rows, the last two columns and the last row.
+                // A strip is one word of the pair's bitmap.  In the tip pass, where every contig label that an alignment of the
+                // standard pass took is used from the start (main.cpp:597-602), this is almost half of all strips on C2.
+                const uint32_t *ub = P.r_used + gunit * P.r_used_words;
+                bool done = false;
+                for (;;) {
+                    if (strip >= r_se) {
+                        done = true;
+                        break;
+                    }
+                    const int rows_here = nb - (strip << 5) < 32 ? nb - (strip << 5) : 32;
+                    const uint32_t valid = rows_here >= 32 ? 0xffffffffu : ((1u << rows_here) - 1u);
+                    if ((__ldcg(ub + strip) & valid) != valid) break;
+                    uint8_t *C = P.r_code + gunit * P.r_cells + (long long)(strip << 5) * nx;
+                    for (int i = lane; i < rows_here * nx; i += 32) C[i] = 0;
+                    if (rows_here == 32) {  // bottom rows for the strip below (rows 26..31 of this strip: never row 0)
+                        float *h = halo + (long long)strip * nx * 8;
+                        for (int i = lane; i < nx * 8; i += 32)
+                            if ((i & 7) < 6) __stcg(h + i, (i >> 3) < 2 ? 0.0f : NEG_INF);
+                    }
+                    const int jj = (strip << 5) + lane;
+                    if (jj < nb) {
+                        float *c2 = P.r_col2 + gunit * 2 * P.r_max_nb + 2 * jj;
+                        __stcg(c2, (jj == 0 || nx - 2 < 2) ? 0.0f : NEG_INF);
+                        __stcg(c2 + 1, (jj == 0 || nx - 1 < 2) ? 0.0f : NEG_INF);
+                    }
+                    if (nb - 1 >= (strip << 5) && nb - 1 < (strip << 5) + 32) {
+                        float *lr = P.r_lastrow + gunit * P.r_max_nx;
+                        for (int i = lane; i < nx; i += 32) __stcg(lr + i, (nb - 1 == 0 || i < 2) ? 0.0f : NEG_INF);
+                    }
+                    strip++;
+                    t += nx;
+                }
+                __syncwarp();
+                if (done) break;
+            }
             const bool active = (NW == 1) ? true : ((t >= w) && (strip < nstrips) && (q < nx));  // NW==1: T = nstrips*nx
             float val = 0.0f, rv = 0.0f, hv = NEG_INF;
             unsigned long long hv_cpl = 0;  // coupled: the mailbox entry as loaded at the start of the step

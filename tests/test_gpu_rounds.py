@@ -119,6 +119,32 @@ def test_rounds_match_full_matrix_reference_loop(ctx, oracle, gen):
     # tip-phase form: seed bitmaps (labels already taken), gen-2 standard cap of 12 rounds
     seeds = [sorted(set(rng.integers(0, len(contigs[cids[int(c)]]) - 1, size=int(rng.integers(0, 12))).tolist())) for c in pr["contig"]]
     check(ctx, oracle, contigs, segs, cids, sids, cp, sp, pr, thr, 12, seeds)
+    # whole runs of labels taken (what the tip pass inherits from the standard pass): 32-row strips that are entirely used are
+    # not swept by the kernel but filled in with their known values -- the first strip (row 0), the ragged last strip, runs
+    # that end one label short of a strip, and everything used
+    seeds = []
+    for k, c in enumerate(pr["contig"]):
+        nb = len(contigs[cids[int(c)]]) - 1
+        kind = k % 6
+        if kind == 0:
+            lo, hi = 0, min(nb, 32 * int(rng.integers(1, 4)))
+        elif kind == 1:
+            lo, hi = 32 * int(rng.integers(0, max(nb // 64, 1))), nb
+        elif kind == 2:
+            lo = 32 * int(rng.integers(0, max(nb // 32, 1)))
+            hi = min(nb, lo + 32 * int(rng.integers(1, 5)) - 1)
+        elif kind == 3:
+            lo, hi = 0, nb
+        elif kind == 4:
+            lo = int(rng.integers(0, nb))
+            hi = min(nb, lo + int(rng.integers(20, 200)))
+        else:
+            lo, hi = 32, min(nb, 64)
+        s = set(range(lo, hi))
+        if kind == 5:
+            s |= set(range(min(nb, 96), min(nb, 160)))
+        seeds.append(sorted(s))
+    check(ctx, oracle, contigs, segs, cids, sids, cp, sp, pr, thr, 12, seeds)
 
 
 def test_rounds_scratch_and_arena_limits(ctx, oracle, monkeypatch):
