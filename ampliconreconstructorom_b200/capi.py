@@ -41,7 +41,8 @@ class RoundsOut(C.Structure):
 
 class RoundsFilter(C.Structure):
     """sa_rounds_filter: which tracebacks sa_align_rounds_filtered returns (main.cpp:303-325)."""
-    _fields_ = [("tip", C.c_int32), ("min_len", C.c_int32), ("mean_min", C.c_float), ("mean_min_short", C.c_float)]
+    _fields_ = [("tip", C.c_int32), ("min_len", C.c_int32), ("mean_min", C.c_float), ("mean_min_short", C.c_float),
+                ("stop_below", C.c_float), ("tip_windows", C.c_int32)]
 
 
 round_dtype = np.dtype([("score", "<f4"), ("j", "<i4"), ("q", "<i4"), ("path_len", "<i4"), ("path_off", "<i8"), ("j_first", "<i4"), ("reserved", "<i4")])

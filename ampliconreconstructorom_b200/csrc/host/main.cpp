@@ -344,7 +344,7 @@ double wall_now();
 std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapSet &segs, const MapSet &contigs,
                                        const std::vector<std::pair<int, int>> &pairs /* (seg idx, contig idx) */,
                                        const std::vector<std::pair<int, float>> &thresholds /* by seg idx */,
-                                       const std::vector<Bitmap> *used_seed, bool tip_aln) {
+                                       const std::vector<Bitmap> *used_seed, bool tip_aln, float stop_score) {
     const int min_aln_labels = 6;
     const int min_tip_aln_labels = (o.inst_gen == 1) ? 3 : 5;
     std::vector<Bitmap> discovered((size_t)contigs.n_maps());
@@ -453,6 +453,10 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
         flt.min_len = tip_aln ? min_tip_aln_labels : std::max(min_aln_labels, min_tip_aln_labels);
         flt.mean_min = mean_thresh;
         flt.mean_min_short = 9400.0f;
+        // A round that scores below what a file needs ends the pair: later rounds cannot score higher, a round that cannot be
+        // written leaves nothing behind but its count, and the count only names files.  (stop_score: see can_write_a_file.)
+        flt.stop_below = getenv("SA_NO_EARLY_STOP") ? 0.0f : stop_score;
+        flt.tip_windows = (tip_aln && !getenv("SA_NO_TIP_WINDOWS")) ? 1 : 0;  // pairs no end-touching alignment of which can score that much: -2
         eng.align_rounds(mode, rp, rthr, max_alns, arena, flt, ro);
         const double t_r1 = wall_now();
         const size_t n_pairs = st.size();
@@ -468,6 +472,10 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
             for (size_t k = lo; k < hi; k++) {
                 PairState &p = st[k];
                 const int nr = ro.nr(k);
+                if (nr == -2) {  // certified: no round of this pair can write a tip alignment (sa_rounds_filter.tip_windows)
+                    p.live = false;
+                    continue;
+                }
                 if (nr < 0) continue;  // left to the batched rounds below
                 p.live = false;
                 bool more = p.curr_best >= p.exp_thresh && p.count < max_alns;  // main.cpp:268 (false for a NaN threshold)
@@ -489,7 +497,7 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
                     }
                     p.count += 1;
                     if (v.rec->path_off >= 0) emit(p, len, v.pj, v.pq, v.ps, aln, disc[(size_t)wi]);  // else: certified unwritable
-                    more = p.count < max_alns;
+                    more = p.count < max_alns && !(p.curr_best < flt.stop_below);  // the device stopped here too (stop_below)
                 }
                 if (more || r != nr) bad[(size_t)wi]++;  // the device loop and this replay must agree on the number of rounds
             }
@@ -507,6 +515,18 @@ std::vector<Bitmap> run_alignment_pass(Engine &eng, const Options &o, const MapS
             for (auto &e : disc[(size_t)wi]) bm_set(discovered[(size_t)e.first], e.second);
         }
         for (size_t k = 0; k < n_pairs; k++) n_fallback += st[k].live ? 1 : 0;
+        if (getenv("SA_VERBOSE")) {
+            long long n_rounds = 0, n_first_below = 0, n_hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (size_t k = 0; k < n_pairs; k++) {
+                const int nr = ro.nr(k);
+                if (nr <= 0) continue;
+                n_rounds += nr;
+                n_hist[std::min(nr, 7)]++;
+                n_first_below += ro.get(k, 0).rec->score < flt.stop_below;
+            }
+            fprintf(stderr, "  rounds: %lld in all (pairs by number of rounds 1..7+: %lld %lld %lld %lld %lld %lld %lld); first round already below %.0f: %lld pairs\n",
+                    n_rounds, n_hist[1], n_hist[2], n_hist[3], n_hist[4], n_hist[5], n_hist[6], n_hist[7], (double)flt.stop_below, n_first_below);
+        }
         if (getenv("SA_VERBOSE"))
             fprintf(stderr, "  device-resident alignment loop: %zu pairs, device call %.3f s, host replay + files %.3f s, %zu pairs left to batched rounds\n",
                     n_pairs, t_r1 - t_r0, wall_now() - t_r1, n_fallback);
@@ -965,7 +985,7 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open, Spmd &sp
     fflush(stdout);
     min_file_score = 0.99f * 35000.0f;  // standard pass: >= 6 labels, mean >= 7000 (main.cpp:218-222,249-255,310-325)
     std::vector<Bitmap> contig_used =
-        run_alignment_pass(eng, o, segs, contigs, my_pairs(can_write_a_file(uniq)), score_thresholds, nullptr, false);
+        run_alignment_pass(eng, o, segs, contigs, my_pairs(can_write_a_file(uniq)), score_thresholds, nullptr, false, phase1.empty() ? 0.0f : min_file_score);
     if (sp.world > 1) {  // exchange 2 (main.cpp:597-602): union of the labels of the written alignments
         size_t words = 0;
         for (auto &b : contig_used) words += b.size();
@@ -995,10 +1015,36 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open, Spmd &sp
         std::vector<std::pair<int, int>> tip_pairs;
         for (int s = 0; s < segs.n_maps(); s++)
             for (int c : tip_contigs) tip_pairs.emplace_back(s, c);  // every segment (+ and -) x every such contig
+        if (getenv("SA_VERBOSE") && sp.rank == 0) {  // how much of the tip pass's first sweep the used labels could save
+            long long rows = 0, used = 0, strips = 0, full = 0, blocks = 0;
+            for (int c : tip_contigs) {
+                const Bitmap &b = contig_used[(size_t)c];
+                const int nb = contigs.labels(c);
+                rows += nb;
+                strips += (nb + 31) / 32;
+                for (int s = 0; s * 32 < nb; s++) {
+                    const int r = std::min(32, nb - s * 32);
+                    const uint32_t valid = r >= 32 ? 0xffffffffu : ((1u << r) - 1u);
+                    full += (b[(size_t)s] & valid) == valid;
+                }
+                for (int j = 0; j < nb;) {
+                    if ((b[(size_t)(j >> 5)] >> (j & 31)) & 1u) {
+                        used++;
+                        j++;
+                        continue;
+                    }
+                    blocks++;
+                    for (int k = j; k < std::min(nb, j + 32); k++) used += (b[(size_t)(k >> 5)] >> (k & 31)) & 1u;
+                    j += 32;
+                }
+            }
+            fprintf(stderr, "  tip pass: %zu contigs, %lld labels, %lld used; %lld aligned strips, %lld of them entirely used; %lld blocks of 32 rows if a block starts at the next free label\n",
+                    tip_contigs.size(), rows, used, strips, full, blocks);
+        }
         printf("Performing alignments\n");
         fflush(stdout);
         min_file_score = 0.99f * ((o.inst_gen == 1) ? 2.0f * 9400.0f : 4.0f * 8750.0f);  // tip: >= 3 labels at 9400 / >= 5 at 8750
-        run_alignment_pass(eng, o, segs, contigs, my_pairs(can_write_a_file(tip_pairs)), tip_thresholds, &contig_used, true);
+        run_alignment_pass(eng, o, segs, contigs, my_pairs(can_write_a_file(tip_pairs)), tip_thresholds, &contig_used, true, phase1.empty() ? 0.0f : min_file_score);
         printf("Finished tip alignments.\n\n");
         pt.lap("phase 4 tip alignment");
     }

@@ -378,6 +378,7 @@ int prepare_fill(sa_ctx *ctx, FillParams &P, const sa_mode *mode) {
     if (ctx->sides[0].n_maps == 0 || ctx->sides[1].n_maps == 0) return fail(ctx, SA_EINVAL, "maps not uploaded");
     if (mode->lookback < LB) return fail(ctx, SA_EINVAL, "lookback must be 6 (banded kernels) or larger (-nl, unbanded)");
     memset(&P, 0, sizeof(P));
+    P.r_flt_stop_below = -INFINITY;  // rounds: never stop early unless a filter says so
     P.contigs = ctx->sides[0].dev();
     P.segs = ctx->sides[1].dev();
     P.init_mode = mode->init_mode;
@@ -940,6 +941,9 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
         P.used_words_per_slot = used_words_per_slot;
     }
     ctx->timing = {0, 0, 0, 0};
+    const bool verbose = getenv("SA_VERBOSE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_in = now();
     const int n_ctas = (int)std::min<int64_t>((n + FILL_WARPS - 1) / FILL_WARPS, n_fill_ctas(ctx));
     const long long workers = (long long)n_ctas * FILL_WARPS;
     size_t free_b = 0, total_b = 0;
@@ -970,6 +974,24 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
         P.r_flt_min_len = filter->min_len;
         P.r_flt_mean = filter->mean_min;
         P.r_flt_mean_short = filter->mean_min_short;
+        if (filter->stop_below > 0.0f) P.r_flt_stop_below = filter->stop_below;
+        if (filter->tip && filter->tip_windows) {
+            // A path that can be written has n >= min_len entries and score / (n - 1) >= m := 0.999 * min(mean_min, mean_min_short),
+            // i.e. penalties of at most c := 10000 - m per step on average.  Swept with a gain of G per step instead of 10000 it
+            // is worth >= (G - c)(n - 1) >= (G - c)(min_len - 1) =: W, and so is the cell it ends in (fp32 rounding of the two
+            // chains: < 2.1 each, partial sums stay below 2^19; the test value leaves 10).  G trades two kinds of chance paths
+            // off against each other: long ones with mediocre steps sink below zero as G falls towards c, short ones with
+            // near-perfect steps reach W as soon as (min_len - 2) G >= W.  G = 1.1 (min_len - 1) c keeps the latter just out.
+            const float m = 0.999f * std::min(filter->mean_min, filter->mean_min_short);
+            if (!(m > 0.0f && m < 10000.0f)) return fail(ctx, SA_EINVAL, "sa_align_rounds_filtered: tip_windows needs 0 < mean_min, mean_min_short < 10000");
+            const float c = 10000.0f - m;
+            P.r_flt_tipwin = 1;
+            P.r_win_gain = std::min(10000.0f, 1.1f * (float)(filter->min_len - 1) * c);
+            P.r_win_min = (P.r_win_gain - c) * (float)(filter->min_len - 1) - 10.0f;
+            // rows such a path can span per step: itself plus the labels it can afford to skip at 5000 each (fn_t); 0.1 % up
+            // for the rounding slack of the chain (2.1 in c (n - 1))
+            P.r_win_slope = (1.0f + c / 5000.0f) * 1.001f;
+        }
     }
     ctx->h_nr.assign((size_t)n, -1);
     if (ctx->h_rounds.size() < (size_t)n * (size_t)max_alns) ctx->h_rounds.resize((size_t)n * (size_t)max_alns);
@@ -1054,6 +1076,7 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
             P.r_pj = ctx->d_r_pj.as<int32_t>();
             P.r_pq = ctx->d_r_pq.as<int32_t>();
             P.r_psc = ctx->d_r_psc.as<float>();
+            const double t_launch = now();
             CU(cudaEventRecord(ctx->ev[0], ctx->stream));
             launch_fill(P, 3, false, 0, (int)std::min<int64_t>((m + FILL_WARPS - 1) / FILL_WARPS, n_ctas), ctx->stream);
             CU(cudaGetLastError());
@@ -1068,6 +1091,7 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
                 CU(ctx->h_pq.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(guess, 1), true));
                 CU(ctx->h_ps.reserve(sizeof(float) * (size_t)std::max<int64_t>(guess, 1), true));
             }
+            const double t_pinned = now();
             char *stage = ctx->h_stage.as<char>();
             unsigned long long *ctl = reinterpret_cast<unsigned long long *>(stage);
             const int32_t *nr = reinterpret_cast<const int32_t *>(stage + nr_at);
@@ -1076,6 +1100,7 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
             CU(cpy(ctx, stage + nr_at, ctx->d_r_nrounds.p, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cpy(ctx, stage + rr_at, ctx->d_r_rounds.p, sizeof(sa_round) * (size_t)m * (size_t)max_alns, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
+            const double t_records = now();
             if ((int32_t)ctl[1] != 0) return fail(ctx, SA_ECUDA, "sa_align_rounds: path arena overflow (internal sizing error)");
             const int64_t n_path = (int64_t)ctl[0];
             CU(ctx->h_pj.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(total + n_path, 1), true));
@@ -1087,6 +1112,7 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
                 CU(cpy(ctx, ctx->h_ps.as<float>() + total, ctx->d_r_psc.p, sizeof(float) * (size_t)n_path, cudaMemcpyDeviceToHost, ctx->stream));
             }
             CU(cudaStreamSynchronize(ctx->stream));
+            const double t_paths = now();
             for (int64_t i = 0; i < m; i++) {  // scatter the chunk's records to their problems, path offsets made global
                 const int64_t g = acc[k0 + (size_t)i];
                 h_nr[g] = nr[(size_t)i];
@@ -1101,10 +1127,13 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
             cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
             ctx->timing.fill_ms += a;
             ctx->timing.n_launches += 1;
-            if (getenv("SA_VERBOSE"))
+            if (verbose) {
                 fprintf(stderr, "  sa_align_rounds chunk: %lld pairs, kernel %.2f ms, %lld path entries, %d workers x %.1f MB scratch\n",
                         (long long)m, a, (long long)n_path, (int)workers,
                         ((double)max_cells + 4.0 * (double)max_halo + 8.0 * max_nb + 4.0 * max_nx + 4.0 * used_words + 12.0 * max_path) / 1e6);
+                fprintf(stderr, "    host side (ms since the call): launch at %.1f, pinned buffers ready at %.1f, records on the host at %.1f, paths at %.1f, scattered at %.1f\n",
+                        t_launch - t_in, t_pinned - t_in, t_records - t_in, t_paths - t_in, now() - t_in);
+            }
             k0 = k1;
         }
     }

@@ -387,7 +387,8 @@ struct CellRes {
 };
 __device__ __noinline__ CellRes cell_slow(bool swap, uint32_t a_row, float dx0, float dx1, float dx2, float dx3,
                                           float dx4, float dx5, float f0, float f1, float f2, float f3, float f4,
-                                          float f5, uint32_t pbase, uint32_t t2d, uint32_t exp, float best0, int code0) {
+                                          float f5, uint32_t pbase, uint32_t t2d, uint32_t exp, float best0, int code0,
+                                          float gain = 10000.0f) {
     const float dx[LB] = {dx0, dx1, dx2, dx3, dx4, dx5};
     const float f[LB] = {f0, f1, f2, f3, f4, f5};
     CellRes res;
@@ -403,11 +404,11 @@ __device__ __noinline__ CellRes cell_slow(bool swap, uint32_t a_row, float dx0, 
             const float fp = swap ? fbv : f[dq - 1];
             const float fnfp = __fadd_rn(fn, fp);
 #if SA_PRUNE
-            const float hi = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, delta_lo_approx(d))));
+            const float hi = __fadd_rn(sc, __fsub_rn(gain, __fadd_rn(fnfp, delta_lo_approx(d))));
             if (!(hi >= res.best)) continue;  // its exact score is <= hi < the running maximum
 #endif
             const float delta = powf12_any(fabsf(d), t2d, exp);
-            const float ns = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, delta)));
+            const float ns = __fadd_rn(sc, __fsub_rn(gain, __fadd_rn(fnfp, delta)));
             const int ck = 1 + (dj - 1) * LB + (dq - 1);
             if (ns > res.best || (ns == res.best && ck >= res.code)) {
                 res.best = ns;
@@ -544,7 +545,9 @@ __device__ __noinline__ bool rounds_finish(const FillParams &P, long long gunit,
                 const int jj = pj[t];
                 __stcg(ub + (jj >> 5), __ldcg(ub + (jj >> 5)) | (1u << (jj & 31)));
             }
-            if (n_count < P.r_max_alns) {  // main.cpp:268: another round, over the rows this path can influence
+            // main.cpp:268: another round, over the rows this path can influence -- unless the caller has declared rounds that
+            // score below r_flt_stop_below unobservable (later rounds cannot score higher than this one)
+            if (n_count < P.r_max_alns && !(st_s < P.r_flt_stop_below)) {
                 stop = 0;
                 const int j_lo = pj[n - 1], j_hi = pj[0];
                 const int nstrips = (nb + 31) >> 5;
@@ -561,6 +564,49 @@ __device__ __noinline__ bool rounds_finish(const FillParams &P, long long gunit,
     sb = __shfl_sync(0xffffffffu, n_sb, 0);
     se = __shfl_sync(0xffffffffu, n_se, 0);
     return stop != 0;
+}
+
+// Tip pass only (sa_rounds_filter.tip_windows): can ANY round of this pair write a tip alignment?  run_SA_aln writes one only if
+// its first label is <= 2 or its last label >= nb - 4 (main.cpp:303-308), it has >= min_len labels and its mean score per step
+// reaches a bar (main.cpp:310-325).  Three facts make a cheap, exact pre-check out of that:
+//  * A path takes one segment label per step and 1 + (skipped contig labels) rows; a skipped label costs 5000 (fn_t), and a path
+//    that passes the mean filter can afford c = 10000 - bar per step on average, so it spans at most (nx - 1)(1 + c / 5000)
+//    rows (win_span: 1.25 nx for the tip pass instead of the 6 nx a path could span at all).  One that starts in rows 0..2
+//    ends in rows <= 2 + span; one that ends in rows >= nb - 4 lies in rows >= nb - 4 - span.  The end of a round's path is
+//    its backtrack start: a cell of the last row or of the last two columns.  A window swept on its own (the rows above it
+//    taken as absent) gives every cell the best path into it that lies INSIDE the window, which is all the bound needs.
+//  * A cell's value is the best path into it, `val = max(init, best candidate)`, every operation monotone: masking more labels
+//    (later rounds) can only lower it, and so can closing start cells.  A path that starts in rows 0..2 starts in row 0 or in
+//    columns 0, 1 of rows 1, 2 (the cells init_semiglobal_aln sets to 0); the top strips are swept with the free starts of
+//    columns 0, 1 below row 2 closed, so that what reaches the last two columns there is the best path FROM THE CONTIG END --
+//    otherwise every ordinary alignment that merely ends inside the window keeps the pair alive (measured on C2: 26 % of the
+//    pairs survive a plain score bound over 6 nx rows, 16 % with the starts closed, 4.6 % with the gain below as well, 0.9 %
+//    with the windows cut to win_span; profiles/r2_c2_whole_run_tip_windows*.txt).
+//  * Both windows are swept with a per-step gain G < 10000 (r_win_gain, set by the host from the filter's mean bar): a path that
+//    passes the mean filter has penalties <= 10000 - bar per step on average and is worth >= (G - 10000 + bar)(n - 1) > 0 here,
+//    while chance alignments, whose penalties exceed G on most steps, sink below zero.  (A plain score bound cannot tell a
+//    40-label noise alignment of 45 000 from a 6-label tip alignment of 50 000.)
+// The maximum over the windows' backtrack-start cells is compared with r_win_min (a fraction of what the shortest writable path
+// is worth); below it, the pair is finished without ever having been aligned.  All 32 lanes call this.
+// contig labels a writable path can span beyond its first: one per step plus the labels it skips, and skipping costs 5000 each
+// (fn_t, SegAligner.cpp:89) out of a penalty budget of c per step, so at most (nx - 1)(1 + c / 5000) (r_win_slope); never more
+// than 6 per step
+__device__ __forceinline__ int win_span(const FillParams &P, int nx) {
+    return min((int)ceilf((float)(nx - 1) * P.r_win_slope) + 1, LB * (nx - 1));
+}
+__device__ __noinline__ float end_window_best(const FillParams &P, long long gunit, int nb, int nx) {
+    const int lane = threadIdx.x & 31;
+    const float *col2 = P.r_col2 + gunit * 2 * P.r_max_nb;
+    const float *lastrow = P.r_lastrow + gunit * P.r_max_nx;
+    float m = NEG_INF_F;
+    const int top = min(nb, 3 + win_span(P, nx));
+    for (int e = lane; e < 2 * top; e += 32) m = fmaxf(m, __ldcg(col2 + e));
+    const int bot = max(0, nb - 4);
+    for (int e = 2 * bot + lane; e < 2 * nb; e += 32) m = fmaxf(m, __ldcg(col2 + e));
+    for (int e = lane; e < nx; e += 32) m = fmaxf(m, __ldcg(lastrow + e));
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+    return m;
 }
 
 constexpr int RING_W = 40;  // 6 halo rows + 32 lanes + 2 pad
@@ -714,6 +760,17 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         const int rounds = (nstrips + NWT - 1) / NWT;
         // rounds variant: strips [r_sb, r_se) are swept in this pass; accepted alignments so far; pass number
         int r_sb = 0, r_se = nstrips, r_count = 0, r_round = 0;
+        // tip windows: 1 = sweeping the top strips, 2 = sweeping the bottom strips (started cold), 0 = the loop proper
+        int r_pre = 0;
+        if (ROUNDS && P.r_flt_tipwin) {
+            const int span = win_span(P, nx);
+            const int s_top = (3 + span + 31) >> 5;  // strips that hold rows 0 .. 2 + span
+            const int bot_row = nb - 4 - span;       // first row of a writable path that ends in rows >= nb - 4
+            if (bot_row > 0 && (bot_row >> 5) >= s_top) {      // the two windows are disjoint: worth a look before the full sweep
+                r_pre = 1;
+                r_se = s_top;
+            }
+        }
         if (ROUNDS) {
             uint32_t *ub = P.r_used + gunit * P.r_used_words;  // the pair's used labels: a copy of its seed bitmap (or none)
             for (int i = lane; i < ((nb + 31) >> 5); i += 32) __stcg(ub + i, used_off >= 0 ? P.used_bits[used_off + i] : 0u);
@@ -726,6 +783,9 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         }
         for (;;) {  // one pass, except in the rounds variant
         // < 2^31: check_problems() rejects problems with more than 2^35 cells
+        // what a step is worth before its penalties (score_f's 10000, SegAligner.cpp:92); the end windows of the tip pass are
+        // swept with a smaller value: see end_window_best
+        const float gain = (ROUNDS && r_pre != 0) ? P.r_win_gain : 10000.0f;
         const int T = ROUNDS ? (r_se - r_sb) * nx : CPL ? ((nstrips - cu + cU - 1) / cU) * nx : rounds * R + (NWT - 1);
 
         // per-warp sweep state
@@ -755,6 +815,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                 // standard pass took is used from the start (main.cpp:597-602), this is almost half of all strips on C2.
                 const uint32_t *ub = P.r_used + gunit * P.r_used_words;
                 bool done = false;
+                const bool open01 = r_pre != 1;  // columns 0, 1 are free starts in every row (not in the top end window)
                 for (;;) {
                     if (strip >= r_se) {
                         done = true;
@@ -768,17 +829,18 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                     if (rows_here == 32) {  // bottom rows for the strip below (rows 26..31 of this strip: never row 0)
                         float *h = halo + (long long)strip * nx * 8;
                         for (int i = lane; i < nx * 8; i += 32)
-                            if ((i & 7) < 6) __stcg(h + i, (i >> 3) < 2 ? 0.0f : NEG_INF);
+                            if ((i & 7) < 6) __stcg(h + i, ((i >> 3) < 2 && open01) ? 0.0f : NEG_INF);
                     }
                     const int jj = (strip << 5) + lane;
                     if (jj < nb) {
                         float *c2 = P.r_col2 + gunit * 2 * P.r_max_nb + 2 * jj;
-                        __stcg(c2, (jj == 0 || nx - 2 < 2) ? 0.0f : NEG_INF);
-                        __stcg(c2 + 1, (jj == 0 || nx - 1 < 2) ? 0.0f : NEG_INF);
+                        const bool o01 = open01 || jj <= 2;
+                        __stcg(c2, (jj == 0 || (nx - 2 < 2 && o01)) ? 0.0f : NEG_INF);
+                        __stcg(c2 + 1, (jj == 0 || (nx - 1 < 2 && o01)) ? 0.0f : NEG_INF);
                     }
                     if (nb - 1 >= (strip << 5) && nb - 1 < (strip << 5) + 32) {
                         float *lr = P.r_lastrow + gunit * P.r_max_nx;
-                        for (int i = lane; i < nx; i += 32) __stcg(lr + i, (nb - 1 == 0 || i < 2) ? 0.0f : NEG_INF);
+                        for (int i = lane; i < nx; i += 32) __stcg(lr + i, (nb - 1 == 0 || (i < 2 && (open01 || nb - 1 <= 2))) ? 0.0f : NEG_INF);
                     }
                     strip++;
                     t += nx;
@@ -851,14 +913,16 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                 // rows above the strip at column q (bottom rows of strip-1)
                 if (strip > 0 && lane < 6) {
                     if (CPL) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(hv_cpl) : "l"(mb_in + (long long)q * 6 + lane) : "memory");
-                    else if (ROUNDS) hv = __ldcg(halo + ((long long)(strip - 1) * nx + q) * 8 + lane);
+                    else if (ROUNDS) hv = (r_pre == 2 && strip == r_sb) ? NEG_INF : __ldcg(halo + ((long long)(strip - 1) * nx + q) * 8 + lane);
                     else if (NW == 1 || w == 0) hv = __ldcg(halo + (long long)q * 8 + lane);
                     else if (CS > 1 && warp == 0) hv = __ldcg(cmail + 16 + ((crank - 1) * 2 + ((t - 1) & 1)) * 8 + lane);
                     else hv = s_xbuf[warp - 1][(t - 1) & 1][lane];
                 }
 
                 float init;
-                if (P.init_mode == SA_INIT_SEMIGLOBAL) init = (j == 0 || q < 2) ? 0.0f : NEG_INF;
+                // (rounds, top end window: only paths that start in rows 0..2 count, i.e. the free starts of columns 0, 1 below
+                // row 2 are closed -- see end_window_best)
+                if (P.init_mode == SA_INIT_SEMIGLOBAL) init = (j == 0 || (q < 2 && (!ROUNDS || r_pre != 1 || j <= 2))) ? 0.0f : NEG_INF;
                 else if (P.init_mode == SA_INIT_LOCAL) init = 0.0f;
                 else init = (j == 0 || q == 0) ? 0.0f : NEG_INF;
 
@@ -885,7 +949,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                             f32x2 fnfp;  // fn_t + fp_t (SegAligner.cpp:89-91); 0 + fp_t == fp_t bit for bit (fp_t >= +0)
                             if (!SWAP) fnfp = (dj == 1) ? pk2(fx[c], fx[c + 1]) : add2(pk2(5000.0f * (float)(dj - 1), 5000.0f * (float)(dj - 1)), pk2(fx[c], fx[c + 1]));
                             else fnfp = add2(pk2(5000.0f * (float)c, 5000.0f * (float)(c + 1)), pk2(fb[dj - 1], fb[dj - 1]));
-                            upk2(add2(pk2(sc0, sc1), sub2(pk2(10000.0f, 10000.0f), add2(fnfp, pk2(e0, e1)))), hi[c], hi[c + 1]);
+                            upk2(add2(pk2(sc0, sc1), sub2(pk2(gain, gain), add2(fnfp, pk2(e0, e1)))), hi[c], hi[c + 1]);
                         }
 #else
 #pragma unroll
@@ -895,7 +959,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                             float fnfp;  // fn_t + fp_t (SegAligner.cpp:89-91); 0 + fp_t == fp_t bit for bit (fp_t >= +0)
                             if (!SWAP) fnfp = (dj == 1) ? fx[c] : __fadd_rn(5000.0f * (float)(dj - 1), fx[c]);
                             else fnfp = (c == 0) ? fb[dj - 1] : __fadd_rn(5000.0f * (float)c, fb[dj - 1]);
-                            hi[c] = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, e)));
+                            hi[c] = __fadd_rn(sc, __fsub_rn(gain, __fadd_rn(fnfp, e)));
                         }
 #endif
 #pragma unroll
@@ -923,7 +987,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                             const float fbv = lds_f32(a_row + (LB + djm) * 128);
                             fnfp = __fadd_rn(5000.0f * (float)c, fbv);
                         }
-                        best = __fadd_rn(sc, __fsub_rn(10000.0f, __fadd_rn(fnfp, delta)));
+                        best = __fadd_rn(sc, __fsub_rn(gain, __fadd_rn(fnfp, delta)));
                         code = 1 + k6;
                         n_replay++;
                         // step 3: every other candidate's exact score is <= its hi <= m2
@@ -932,7 +996,7 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
                             const CellRes cr = cell_slow(SWAP, a_row, dx[0], dx[1], dx[2], dx[3], dx[4], dx[5],
                                                          SWAP ? 0.0f : fx[0], SWAP ? 0.0f : fx[1], SWAP ? 0.0f : fx[2],
                                                          SWAP ? 0.0f : fx[3], SWAP ? 0.0f : fx[4], SWAP ? 0.0f : fx[5],
-                                                         pbase, a_tab.t2d, a_tab.exp, best, code);
+                                                         pbase, a_tab.t2d, a_tab.exp, best, code, gain);
                             best = cr.best;
                             code = cr.code;
                             if (P.stats) atomicAdd(P.stats + 1, 1ull);
@@ -1143,6 +1207,22 @@ __global__ void __launch_bounds__((NW == 1 ? FILL_WARPS : NW) * 32, MINB) fill_k
         }
         if (!ROUNDS) break;
         __syncwarp();
+        if (r_pre == 1) {  // top strips done: now the bottom strips, as if nothing lay above them
+            r_pre = 2;
+            r_sb = (nb - 4 - win_span(P, nx)) >> 5;
+            r_se = nstrips;
+            continue;
+        }
+        if (r_pre == 2) {
+            if (end_window_best(P, gunit, nb, nx) < P.r_win_min) {  // no round of this pair can write a tip alignment
+                if (lane == 0) P.r_n_rounds[pidx] = -2;
+                break;
+            }
+            r_pre = 0;  // round 1: the whole matrix (the top strips were swept with the starts below row 2 closed)
+            r_sb = 0;
+            r_se = nstrips;
+            continue;
+        }
         if (rounds_finish(P, gunit, pidx, pr.contig, nb, pr.seg, nx, P.r_thr[pidx], r_round, r_count, r_sb, r_se)) break;
         r_round++;
         }  // rounds

@@ -91,8 +91,9 @@ struct FillParams {
     float *r_psc;
     int32_t *r_overflow;    // set when the arena was too small (host-sized for the worst case, so never)
     // sa_align_rounds_filtered: only tracebacks that can still become a file leave the device (r_flt_on)
-    int r_flt_on, r_flt_tip, r_flt_min_len;
-    float r_flt_mean, r_flt_mean_short;
+    int r_flt_on, r_flt_tip, r_flt_min_len, r_flt_tipwin;
+    float r_flt_mean, r_flt_mean_short, r_flt_stop_below;  // stop_below: -inf = never
+    float r_win_gain, r_win_min, r_win_slope;  // tip end windows: per-step gain of the window sweeps, and the value a writable path reaches
 };
 
 struct TraceParams {

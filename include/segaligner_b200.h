@@ -148,6 +148,19 @@ typedef struct sa_rounds_filter {
     int32_t min_len;       /* fewer path entries cannot be written (main.cpp:310-312) */
     float mean_min;        /* score / (path_len - 1) below this cannot be written, paths of >= 5 entries (main.cpp:322) */
     float mean_min_short;  /* the same for paths of < 5 entries (main.cpp:318) */
+    float stop_below;      /* > 0: a pair's loop ends after the first round whose best score is below this value.  Every later
+                            * round's best score is <= it (masking labels only removes candidates; fp32 '+' and max are monotone),
+                            * so when no alignment scoring less can be written, the rounds left out are unobservable.  The round
+                            * that fell below is still reported; n_rounds counts up to it.  <= 0: run the loop to its own end. */
+    int32_t tip_windows;   /* 1 (with tip = 1): before a pair's first full sweep only the strips that an alignment touching a
+                            * contig end AND passing the filters can lie in are swept (rows 0 .. 2 + s, counting only paths that
+                            * start in rows 0..2, and rows >= nb - 4 - s, s = (nx - 1)(1 + c / 5000): a skipped label costs 5000
+                            * of a budget of c per step), with a per-step gain G = min(10000, 1.1 (min_len - 1) c) in place of
+                            * score_f's 10000, c = 10000 - 0.999 min(mean_min, mean_min_short): a path that passes
+                            * the length and mean-score filters is then worth >= (G - c)(min_len - 1), and masking labels only
+                            * lowers cell values, so if no backtrack start of the windows reaches that value, no round of the
+                            * pair can be written and the pair is reported with n_rounds = -2 without having been aligned.
+                            * Pairs whose two windows overlap (short contigs) are aligned as usual. */
 } sa_rounds_filter;
 typedef struct sa_rounds_out {
     int64_t n;

@@ -229,3 +229,102 @@ def test_filtered_rounds_return_exactly_the_writable_tracebacks(ctx, oracle, tip
             else:
                 dropped += 1
     assert kept > 5 and dropped > 5, (kept, dropped)
+
+
+def test_stop_below_truncates_the_loop_after_the_first_low_round(ctx, oracle):
+    """sa_rounds_filter.stop_below: the pair's loop ends after the first round that scores below it (that round is still
+    reported); everything up to there is the unfiltered loop's, and round scores never increase (what makes the cut exact)."""
+    rng = np.random.default_rng(4242)
+    contigs, segs = make_pairs(rng, 40, (40, 420), (4, 45))
+    cp, sp = oracle.probs(contigs, 2), oracle.probs(segs, 2)
+    cids = upload(ctx, contigs, cp, capi.SA_SIDE_CONTIG)
+    sids = upload(ctx, segs, sp, capi.SA_SIDE_SEG)
+    cc = np.repeat(np.arange(len(cids)), 3)
+    ss = (cc + np.tile([0, 5, 11], len(cids))) % len(sids)
+    pr = ctx.problems(cc, ss)
+    mode = ctx.mode(capi.SA_INIT_SEMIGLOBAL, capi.SA_START_SEMIGLOBAL, 0, 6, 0)
+    first = ctx.score_batch(mode, pr)["score"]
+    thr = (first * 0.05).astype(np.float32)
+    nr0, r0, pj0, pq0, ps0 = ctx.align_rounds(mode, pr, thr, 6)
+    scores = np.array([r0[k, r]["score"] for k in range(pr.size) for r in range(nr0[k])])
+    stop = float(np.median(scores))
+    flt = capi.RoundsFilter(0, 2, 0.0, 0.0, stop, 0)
+    nr1, r1, pj1, pq1, ps1 = ctx.align_rounds(mode, pr, thr, 6, flt=flt)
+    cut = 0
+    for k in range(pr.size):
+        sc = [float(r0[k, r]["score"]) for r in range(nr0[k])]
+        assert all(a >= b for a, b in zip(sc, sc[1:])), f"pair {k}: round scores increase {sc}"
+        below = [r for r, v in enumerate(sc) if v < stop]
+        want = min(nr0[k], below[0] + 1) if below else nr0[k]
+        assert nr1[k] == want, (k, sc, stop, nr1[k])
+        cut += want < nr0[k]
+        for r in range(want):
+            a, b = r0[k, r], r1[k, r]
+            assert (a["j"], a["q"], a["path_len"], a["j_first"]) == (b["j"], b["q"], b["path_len"], b["j_first"])
+            assert bits(a["score"]) == bits(b["score"])
+    assert cut > 10, cut
+
+
+def test_tip_windows_only_drop_pairs_that_cannot_write_a_tip_alignment(ctx, oracle):
+    """sa_rounds_filter.tip_windows: a pair reported with n_rounds = -2 has, in its complete loop, no round that touches a
+    contig end, is long enough and passes the mean-score filter (so nothing it could have written); every other pair's rounds
+    are the truncated loop's."""
+    rng = np.random.default_rng(8080)
+    g = synth.genome_positions(rng, 30_000)
+    contigs, segs = {}, {}
+    for k in range(48):
+        nb = int(rng.integers(220, 460))
+        nx = int(rng.integers(4, 15))
+        s0 = int(rng.integers(10, 29_000 - nb))
+        contigs[k + 1] = synth.noisy_contig(rng, g, s0, nb)
+        at = [0, nb - nx, int(rng.integers(0, nb - nx)), int(rng.integers(40, nb - nx - 40))][k % 4]  # top end, bottom end, anywhere, inside
+        segs[k + 1] = synth.window_map(g, s0 + at, nx)
+    cp, sp = oracle.probs(contigs, 2), oracle.probs(segs, 2)
+    cids = upload(ctx, contigs, cp, capi.SA_SIDE_CONTIG)
+    sids = upload(ctx, segs, sp, capi.SA_SIDE_SEG)
+    cc = np.repeat(np.arange(len(cids)), 3)
+    ss = (cc + np.tile([0, 5, 11], len(cids))) % len(sids)
+    pr = ctx.problems(cc, ss)
+    mode = ctx.mode(capi.SA_INIT_SEMIGLOBAL, capi.SA_START_SEMIGLOBAL, 0, 6, 0)
+    first = ctx.score_batch(mode, pr)["score"]
+    thr = (first * 0.05).astype(np.float32)
+    # seed bitmaps as the tip pass has them: a run of labels taken somewhere inside the contig
+    words = (max(len(contigs[c]) for c in cids) + 31) // 32
+    used_bits = np.zeros((pr.size, words), dtype=np.uint32)
+    for k in range(pr.size):
+        nb = len(contigs[cids[int(pr["contig"][k])]]) - 1
+        lo = int(rng.integers(0, nb - 30))
+        for j in range(lo, lo + int(rng.integers(0, 90))):
+            if j < nb and rng.random() < 0.8:
+                used_bits[k, j >> 5] |= np.uint32(1 << (j & 31))
+    pr = pr.copy()
+    pr["used_slot"] = np.arange(pr.size)
+    nr0, r0, pj0, pq0, ps0 = ctx.align_rounds(mode, pr, thr, 6, used_bits.ravel(), words)
+    min_len, mean_min, mean_short = 5, 7000.0, 8000.0
+    stop = 0.99 * (min_len - 1) * mean_min
+    flt = capi.RoundsFilter(1, min_len, mean_min, mean_short, stop, 1)
+    nr1, r1, pj1, pq1, ps1 = ctx.align_rounds(mode, pr, thr, 6, used_bits.ravel(), words, flt=flt)
+    dead = alive = could_write = 0
+    for k in range(pr.size):
+        nb = len(contigs[cids[int(pr["contig"][k])]]) - 1
+        touching = [(nb - 1 - int(r0[k, r]["j"]) <= 3 or int(r0[k, r]["j_first"]) <= 2) and int(r0[k, r]["path_len"]) >= min_len
+                    and float(r0[k, r]["score"]) / (int(r0[k, r]["path_len"]) - 1) >= 0.998 * mean_min for r in range(nr0[k])]
+        if nr1[k] == -2:
+            dead += 1
+            assert not any(touching), (k, [(float(r0[k, r]["score"]), int(r0[k, r]["j_first"]), int(r0[k, r]["j"])) for r in range(nr0[k])], nb)
+            continue
+        alive += 1
+        could_write += any(touching)
+        sc = [float(r0[k, r]["score"]) for r in range(nr0[k])]
+        below = [r for r, v in enumerate(sc) if v < stop]
+        want = min(nr0[k], below[0] + 1) if below else nr0[k]
+        assert nr1[k] == want, (k, sc, nr1[k])
+        for r in range(want):
+            a, b = r0[k, r], r1[k, r]
+            assert (a["j"], a["q"], a["path_len"], a["j_first"]) == (b["j"], b["q"], b["path_len"], b["j_first"])
+            assert bits(a["score"]) == bits(b["score"])
+            if int(b["path_off"]) >= 0:
+                L, o0, o1 = int(a["path_len"]), int(a["path_off"]), int(b["path_off"])
+                assert np.array_equal(pj1[o1:o1 + L], pj0[o0:o0 + L]) and np.array_equal(pq1[o1:o1 + L], pq0[o0:o0 + L])
+                assert np.array_equal(bits(ps1[o1:o1 + L]), bits(ps0[o0:o0 + L]))
+    assert dead > 10 and alive > 10 and could_write > 5, (dead, alive, could_write)
