@@ -36,7 +36,7 @@ class PackedPaths(C.Structure):
 class RoundsOut(C.Structure):
     _fields_ = [("n", C.c_int64), ("max_alns", C.c_int32), ("reserved", C.c_int32), ("total", C.c_int64),
                 ("n_rounds", C.c_void_p), ("rounds", C.c_void_p), ("path_j", C.c_void_p), ("path_q", C.c_void_p),
-                ("path_s", C.c_void_p)]
+                ("path_s", C.c_void_p), ("round_off", C.c_void_p)]
 
 
 class RoundsFilter(C.Structure):
@@ -55,7 +55,7 @@ class Timing(C.Structure):
 # every symbol include/segaligner_b200.h declares (tests check the library exports exactly these)
 EXPORTS = [
     "sa_device_count", "sa_ctx_create", "sa_ctx_destroy", "sa_last_error", "sa_set_maps", "sa_score_batch",
-    "sa_plan_create", "sa_plan_destroy", "sa_plan_score", "sa_plan_results", "sa_plan_info", "sa_sync", "sa_align_batch", "sa_align_batch_packed", "sa_align_rounds", "sa_align_rounds_filtered", "sa_detect_batch", "sa_fill_one", "sa_powf12",
+    "sa_plan_create", "sa_plan_destroy", "sa_plan_score", "sa_plan_results", "sa_plan_info", "sa_sync", "sa_align_batch", "sa_align_batch_packed", "sa_align_rounds", "sa_align_rounds_filtered", "sa_prepare_rounds", "sa_detect_batch", "sa_fill_one", "sa_powf12",
     "sa_powf12_range", "sa_check_prune_bound", "sa_get_timing", "sa_get_prune_stats", "sa_measure_fp64_peak", "sa_measure_mufu_peak", "sa_get_traffic", "sa_event_record", "sa_event_elapsed_ms",
     "sa_host_non_collapse_probs", "sa_host_make_reverse", "sa_host_parse_cmap", "sa_host_score_thresholds",
     "sa_host_format_float", "sa_digest",
@@ -93,6 +93,7 @@ def load_library() -> C.CDLL:
     lib.sa_align_batch_packed.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, i64, i64, C.POINTER(PackedPaths)]
     lib.sa_align_rounds.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, i32, vp, i64, i64, C.POINTER(RoundsOut)]
     lib.sa_align_rounds_filtered.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, i32, vp, i64, i64, C.POINTER(RoundsFilter), C.POINTER(RoundsOut)]
+    lib.sa_prepare_rounds.argtypes = [vp, i64, i32]
     lib.sa_detect_batch.argtypes = [vp, C.POINTER(Mode), vp, i64, vp, vp, vp, vp]
     lib.sa_fill_one.argtypes = [vp, C.POINTER(Mode), vp, vp, i64, vp, vp, vp]
     lib.sa_powf12.argtypes = [vp, vp, i64, vp, C.c_int]
@@ -370,8 +371,16 @@ class Context:
             buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(addr)
             return np.frombuffer(buf, dtype=dtype).copy()
 
-        return (view(ro.n_rounds, n, np.int32), view(ro.rounds, n * max_alns, round_dtype).reshape(n, max_alns),
-                view(ro.path_j, ro.total, np.int32), view(ro.path_q, ro.total, np.int32), view(ro.path_s, ro.total, np.float32))
+        # the library returns the records packed (pair k: rounds[round_off[k] .. + n_rounds[k])); callers here index [pair, round]
+        nr = view(ro.n_rounds, n, np.int32)
+        off = view(ro.round_off, n + 1, np.int64)
+        packed = view(ro.rounds, int(off[-1]) if n else 0, round_dtype)
+        assert np.array_equal(np.diff(off), np.maximum(nr, 0)), "round_off is not the prefix sum of the round counts"
+        dense = np.zeros((n, max_alns), dtype=round_dtype)
+        for r in range(max_alns):
+            has = nr > r
+            dense[has, r] = packed[off[:-1][has] + r]
+        return (nr, dense, view(ro.path_j, ro.total, np.int32), view(ro.path_q, ro.total, np.int32), view(ro.path_s, ro.total, np.float32))
 
     def detect_batch(self, mode: Mode, problems: np.ndarray, n_want: np.ndarray):
         problems = np.ascontiguousarray(problems, dtype=problem_dtype)

@@ -313,7 +313,7 @@ struct Engine {
             const float *ps;
         };
         View get(size_t k, int r) const {
-            const sa_round *rec = ro.rounds + k * (size_t)ro.max_alns + (size_t)r;
+            const sa_round *rec = ro.rounds + (size_t)ro.round_off[k] + (size_t)r;  // records are packed in pair order
             return View{rec, ro.path_j + rec->path_off, ro.path_q + rec->path_off, ro.path_s + rec->path_off};
         }
     };
@@ -865,6 +865,20 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open, Spmd &sp
                 for (int32_t t = 0; t < all_got[k]; t++)
                     rows.push_back(ScoreRow{segs.ids[(size_t)pr[k].seg], contigs.ids[(size_t)pr[k].contig], all_sc[off[k] + t]});
         } else {
+            // While the GPU scores, a helper thread pins the host buffers the alignment passes will read their results from:
+            // pinning costs 0.3 - 1 s per GB, and growing a pinned buffer later means freeing the old one, which waits for the
+            // device.  Sized for 60 % of this rank's pairs reaching the tip pass (C2: 58 %, C5: 38 %); more just grows later.
+            std::thread prewarm;
+            struct Joiner {
+                std::thread &t;
+                ~Joiner() {
+                    if (t.joinable()) t.join();
+                }
+            } prewarm_joiner{prewarm};
+            if (!o.local_aln && !o.swap_b_x && o.lookback == 6 && !getenv("SA_NO_ROUNDS"))
+                prewarm = std::thread([&eng, &o, n_hint = (int64_t)(0.6 * (double)mine.size()) + 1024]() {
+                    (void)sa_prepare_rounds(eng.ctx, n_hint, std::max(o.max_seg_contig_alns, 6));
+                });
             std::vector<float> own;
             float *all;
             if (sp.world > 1) all = sp.alloc<float>(pr.size());

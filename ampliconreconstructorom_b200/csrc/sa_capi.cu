@@ -113,7 +113,7 @@ struct sa_ctx {
         d_path_q, d_path_s, d_tmp0, d_tmp1, d_tmp2, d_halo2, d_row_off, d_rowmax_s, d_rowmax_q, d_prev32, d_halo3, d_mail;
     HostBuf h_res, h_start, h_pj, h_pq, h_ps;  // packed alignment output of the last sa_align_batch* call
     // sa_align_rounds: per-worker scratch that persists across the rounds of a pair, the packed path arena, its host mirrors
-    DevBuf d_r_code, d_r_halo, d_r_col2, d_r_lastrow, d_r_used, d_r_path, d_r_ps, d_r_thr, d_r_rounds, d_r_nrounds, d_r_pj, d_r_pq,
+    DevBuf d_r_code, d_r_halo, d_r_col2, d_r_lastrow, d_r_used, d_r_path, d_r_ps, d_r_thr, d_r_rounds, d_r_nrounds, d_r_roff, d_r_packed, d_r_pj, d_r_pq,
         d_r_psc, d_r_ctl;
     DevBuf d_units, d_mbox, d_cpl_res, d_cpl_done;  // coupled units: queue, mailboxes, per-unit start candidates, per-problem counters
     HostBuf h_cpl_err;                              // the handshake-timeout flag of the last coupled launch lands here
@@ -121,7 +121,8 @@ struct sa_ctx {
     uint32_t cpl_epoch = 0;
     HostBuf h_stage;                    // pinned D2H landing zone of a chunk's round records
     std::vector<int32_t> h_nr;          // what sa_rounds_out points at (scatter targets: pageable memory is enough)
-    std::vector<sa_round> h_rounds;
+    std::vector<sa_round> h_rounds;     // packed, pair order
+    std::vector<int64_t> h_roff;
     sa_timing timing = {0, 0, 0, 0};
     size_t store_budget_cells = 0;  // max cells of stored matrices per chunk
     uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes moved by this context since it was created (sa_get_traffic)
@@ -550,7 +551,7 @@ void sa_ctx_destroy(sa_ctx *ctx) {
                       &ctx->d_S,        &ctx->d_code,   &ctx->d_used,     &ctx->d_path_off, &ctx->d_path_j,  &ctx->d_path_q,
                       &ctx->d_path_s,   &ctx->d_tmp0,   &ctx->d_tmp1,     &ctx->d_tmp2,     &ctx->d_halo2,  &ctx->d_row_off, &ctx->d_rowmax_s,
                       &ctx->d_rowmax_q, &ctx->d_prev32, &ctx->d_halo3, &ctx->d_mail, &ctx->d_r_code, &ctx->d_r_halo, &ctx->d_r_col2,
-                      &ctx->d_r_lastrow, &ctx->d_r_used, &ctx->d_r_path, &ctx->d_r_ps, &ctx->d_r_thr, &ctx->d_r_rounds, &ctx->d_r_nrounds,
+                      &ctx->d_r_lastrow, &ctx->d_r_used, &ctx->d_r_path, &ctx->d_r_ps, &ctx->d_r_thr, &ctx->d_r_rounds, &ctx->d_r_nrounds, &ctx->d_r_roff, &ctx->d_r_packed,
                       &ctx->d_r_pj, &ctx->d_r_pq, &ctx->d_r_psc, &ctx->d_r_ctl,
                       &ctx->d_units, &ctx->d_mbox, &ctx->d_cpl_res, &ctx->d_cpl_done};
     for (auto b : bufs) b->release();
@@ -993,10 +994,14 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
             P.r_win_slope = (1.0f + c / 5000.0f) * 1.001f;
         }
     }
-    ctx->h_nr.assign((size_t)n, -1);
-    if (ctx->h_rounds.size() < (size_t)n * (size_t)max_alns) ctx->h_rounds.resize((size_t)n * (size_t)max_alns);
-    int32_t *h_nr = ctx->h_nr.data();
-    sa_round *h_rounds = ctx->h_rounds.data();
+    // Where the caller reads the records: normally straight from the pinned staging buffer (every pair accepted, one chunk: the
+    // common case, and at 10^7 pairs the scatter target alone would be gigabytes of page faults); otherwise scattered to
+    // per-problem slots in pageable memory, set up when the first chunk shows that it is needed.
+    int32_t *h_nr = nullptr;
+    const int32_t *direct_nr = nullptr;
+    const sa_round *direct_rounds = nullptr;
+    const double t_acc = now();
+    double t_reserved = t_acc, t_plan = t_acc;
     int64_t total = 0;
     if (!acc.empty()) {
         const int used_words = (max_nb + 31) / 32;
@@ -1045,10 +1050,18 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
                 k1++;
             }
             const int64_t m = (int64_t)(k1 - k0);
+            const bool direct = k0 == 0 && k1 == acc.size() && (int64_t)acc.size() == n;
+            if (!direct && !h_nr) {
+                ctx->h_nr.assign((size_t)n, -1);
+                ctx->h_rounds.clear();
+                h_nr = ctx->h_nr.data();
+            }
+            t_reserved = now();
             Plan plan;
             build_plan(ctx, cp.data(), m, n_fill_ctas(ctx) * FILL_WARPS, plan);
             // one queue, largest first: the size classes of the plan in descending order (huge, large, bulk)
             const std::vector<int32_t> order = plan.big_first();
+            t_plan = now();
             CU(ctx->d_problems.reserve(sizeof(sa_problem) * (size_t)m));
             CU(ctx->d_order.reserve(sizeof(int32_t) * (size_t)m));
             CU(ctx->d_r_thr.reserve(sizeof(float) * (size_t)m));
@@ -1081,28 +1094,51 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
             launch_fill(P, 3, false, 0, (int)std::min<int64_t>((m + FILL_WARPS - 1) / FILL_WARPS, n_ctas), ctx->stream);
             CU(cudaGetLastError());
             CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-            // records come back through a pinned staging buffer: [ctl (16 B)][n_rounds (m)][rounds (m * max_alns)]
-            const size_t nr_at = 16, rr_at = (nr_at + sizeof(int32_t) * (size_t)m + 15) & ~(size_t)15;
-            CU(ctx->h_stage.reserve(rr_at + sizeof(sa_round) * (size_t)m * (size_t)max_alns));
-            {   // pinned allocations cost ~0.3 s per GB: make them while the kernel runs, from a guess of the path volume
-                // (with a filter only the tracebacks that can become files come back: a few entries per pair at most)
+            // The round records leave the device PACKED (pair i: n_rounds[i] of them, in pair order): a count + prefix sum + gather
+            // behind the fill, then [ctl (16 B)][n_records (8 B)][n_rounds (m)][records] through a pinned staging buffer.
+            CU(ctx->d_r_roff.reserve(sizeof(int64_t) * (size_t)(m + 1)));
+            int64_t *d_roff = ctx->d_r_roff.as<int64_t>();
+            launch_rounds_count(P.r_n_rounds, d_roff, m, ctx->stream);
+            CU(cudaGetLastError());
+            {
+                size_t tmp_need = 0;
+                exclusive_scan_i64(d_roff, m + 1, nullptr, 0, &tmp_need, ctx->stream);
+                CU(ctx->d_tmp2.reserve(tmp_need + 16));
+                if (exclusive_scan_i64(d_roff, m + 1, ctx->d_tmp2.p, ctx->d_tmp2.cap, nullptr, ctx->stream))
+                    return fail(ctx, SA_ECUDA, "prefix sum of the round counts failed");
+            }
+            const size_t nrec_at = 16, nr_at = 32, rr_at = (nr_at + sizeof(int32_t) * (size_t)m + 15) & ~(size_t)15;
+            {   // pinned allocations cost 0.3 - 1 s per GB: make them while the kernel runs, from a guess of the volumes (most
+                // pairs of a large batch end after a round or two; with a filter only the tracebacks that can become files
+                // come back: a few entries per pair at most)
+                const int64_t rec_guess = std::min<int64_t>(m * (int64_t)max_alns, m + (1 << 20));
+                CU(ctx->h_stage.reserve(rr_at + sizeof(sa_round) * (size_t)rec_guess));
                 const int64_t guess = total + std::min<int64_t>((int64_t)std::min(worst, arena_cap), filter ? m * 4 + (1 << 20) : m * (int64_t)max_alns * 14);
                 CU(ctx->h_pj.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(guess, 1), true));
                 CU(ctx->h_pq.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(guess, 1), true));
                 CU(ctx->h_ps.reserve(sizeof(float) * (size_t)std::max<int64_t>(guess, 1), true));
             }
             const double t_pinned = now();
+            {
+                char *stage = ctx->h_stage.as<char>();
+                CU(cpy(ctx, stage, ctx->d_r_ctl.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cpy(ctx, stage + nrec_at, d_roff + m, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cpy(ctx, stage + nr_at, ctx->d_r_nrounds.p, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+            }
+            const int64_t n_rec = *reinterpret_cast<const int64_t *>(ctx->h_stage.as<char>() + nrec_at);
+            if ((int32_t)reinterpret_cast<const unsigned long long *>(ctx->h_stage.as<char>())[1] != 0)
+                return fail(ctx, SA_ECUDA, "sa_align_rounds: path arena overflow (internal sizing error)");
+            const int64_t n_path = (int64_t)reinterpret_cast<const unsigned long long *>(ctx->h_stage.as<char>())[0];
+            CU(ctx->d_r_packed.reserve(sizeof(sa_round) * (size_t)std::max<int64_t>(n_rec, 1)));
+            launch_rounds_gather(P.r_rounds, P.r_n_rounds, d_roff, ctx->d_r_packed.as<sa_round>(), m, max_alns, ctx->stream);
+            CU(cudaGetLastError());
+            CU(ctx->h_stage.reserve(rr_at + sizeof(sa_round) * (size_t)std::max<int64_t>(n_rec, 1), true));  // (keeps ctl and n_rounds)
             char *stage = ctx->h_stage.as<char>();
-            unsigned long long *ctl = reinterpret_cast<unsigned long long *>(stage);
             const int32_t *nr = reinterpret_cast<const int32_t *>(stage + nr_at);
             const sa_round *rr = reinterpret_cast<const sa_round *>(stage + rr_at);
-            CU(cpy(ctx, ctl, ctx->d_r_ctl.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cpy(ctx, stage + nr_at, ctx->d_r_nrounds.p, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cpy(ctx, stage + rr_at, ctx->d_r_rounds.p, sizeof(sa_round) * (size_t)m * (size_t)max_alns, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
+            if (n_rec > 0) CU(cpy(ctx, stage + rr_at, ctx->d_r_packed.p, sizeof(sa_round) * (size_t)n_rec, cudaMemcpyDeviceToHost, ctx->stream));
             const double t_records = now();
-            if ((int32_t)ctl[1] != 0) return fail(ctx, SA_ECUDA, "sa_align_rounds: path arena overflow (internal sizing error)");
-            const int64_t n_path = (int64_t)ctl[0];
             CU(ctx->h_pj.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(total + n_path, 1), true));
             CU(ctx->h_pq.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(total + n_path, 1), true));
             CU(ctx->h_ps.reserve(sizeof(float) * (size_t)std::max<int64_t>(total + n_path, 1), true));
@@ -1113,14 +1149,18 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
             }
             CU(cudaStreamSynchronize(ctx->stream));
             const double t_paths = now();
-            for (int64_t i = 0; i < m; i++) {  // scatter the chunk's records to their problems, path offsets made global
-                const int64_t g = acc[k0 + (size_t)i];
-                h_nr[g] = nr[(size_t)i];
-                for (int r = 0; r < nr[(size_t)i]; r++) {
-                    sa_round v = rr[(size_t)i * (size_t)max_alns + (size_t)r];
+            if (direct) {
+                direct_nr = nr;
+                direct_rounds = rr;
+            } else {  // append the chunk's records (pair order = problem order), path offsets made global; n_rounds to their problems
+                const size_t at = ctx->h_rounds.size();
+                ctx->h_rounds.resize(at + (size_t)n_rec);
+                for (int64_t r = 0; r < n_rec; r++) {
+                    sa_round v = rr[(size_t)r];
                     if (v.path_off >= 0) v.path_off += total;
-                    h_rounds[(size_t)g * (size_t)max_alns + (size_t)r] = v;
+                    ctx->h_rounds[at + (size_t)r] = v;
                 }
+                for (int64_t i = 0; i < m; i++) h_nr[acc[k0 + (size_t)i]] = nr[(size_t)i];
             }
             total += n_path;
             float a = 0;
@@ -1131,8 +1171,9 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
                 fprintf(stderr, "  sa_align_rounds chunk: %lld pairs, kernel %.2f ms, %lld path entries, %d workers x %.1f MB scratch\n",
                         (long long)m, a, (long long)n_path, (int)workers,
                         ((double)max_cells + 4.0 * (double)max_halo + 8.0 * max_nb + 4.0 * max_nx + 4.0 * used_words + 12.0 * max_path) / 1e6);
-                fprintf(stderr, "    host side (ms since the call): launch at %.1f, pinned buffers ready at %.1f, records on the host at %.1f, paths at %.1f, scattered at %.1f\n",
-                        t_launch - t_in, t_pinned - t_in, t_records - t_in, t_paths - t_in, now() - t_in);
+                fprintf(stderr, "    host side (ms since the call): pairs checked at %.1f, scratch reserved at %.1f, plan built at %.1f, launch at %.1f, pinned buffers ready at %.1f, records on the host at %.1f, paths at %.1f, %s at %.1f\n",
+                        t_acc - t_in, t_reserved - t_in, t_plan - t_in, t_launch - t_in, t_pinned - t_in, t_records - t_in, t_paths - t_in,
+                        direct ? "read in place" : "scattered", now() - t_in);
             }
             k0 = k1;
         }
@@ -1140,11 +1181,45 @@ int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem 
     out->n = n;
     out->max_alns = max_alns;
     out->total = total;
-    out->n_rounds = h_nr;
-    out->rounds = h_rounds;
+    if (!direct_nr && !h_nr) {  // nothing was accepted
+        ctx->h_nr.assign((size_t)n, -1);
+        ctx->h_rounds.clear();
+        h_nr = ctx->h_nr.data();
+    }
+    out->n_rounds = direct_nr ? direct_nr : h_nr;
+    out->rounds = direct_nr ? direct_rounds : ctx->h_rounds.data();
+    ctx->h_roff.resize((size_t)n + 1);  // where each pair's records start: the prefix sum of the round counts
+    {
+        int64_t at = 0;
+        for (int64_t k = 0; k < n; k++) {
+            ctx->h_roff[(size_t)k] = at;
+            at += out->n_rounds[k] > 0 ? out->n_rounds[k] : 0;
+        }
+        ctx->h_roff[(size_t)n] = at;
+    }
+    out->round_off = ctx->h_roff.data();
     out->path_j = ctx->h_pj.as<int32_t>();
     out->path_q = ctx->h_pq.as<int32_t>();
     out->path_s = ctx->h_ps.as<float>();
+    return SA_OK;
+}
+
+// Pinned host buffers of later sa_align_rounds* calls, reserved ahead of time (same sizes as the guesses made there).  Touches
+// only h_stage / h_pj / h_pq / h_ps, which no scoring call uses, and reports errors by return value only (ctx->err belongs to
+// the thread that drives the context).
+int sa_prepare_rounds(sa_ctx *ctx, int64_t n_pairs, int32_t max_alns) {
+    if (!ctx || n_pairs < 0 || max_alns < 1) return SA_EINVAL;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SA_ECUDA;
+    const size_t rr_at = (32 + sizeof(int32_t) * (size_t)n_pairs + 15) & ~(size_t)15;
+    const int64_t rec_guess = std::min<int64_t>(n_pairs * (int64_t)max_alns, n_pairs + (1 << 20));
+    const int64_t path_guess = n_pairs * 4 + (1 << 20);
+    if (ctx->h_stage.reserve(rr_at + sizeof(sa_round) * (size_t)rec_guess) != cudaSuccess ||
+        ctx->h_pj.reserve(sizeof(int32_t) * (size_t)path_guess, true) != cudaSuccess ||
+        ctx->h_pq.reserve(sizeof(int32_t) * (size_t)path_guess, true) != cudaSuccess ||
+        ctx->h_ps.reserve(sizeof(float) * (size_t)path_guess, true) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return SA_ENOMEM;
+    }
     return SA_OK;
 }
 

@@ -1859,6 +1859,29 @@ int exclusive_scan_i64(int64_t *d_vals, int64_t n_plus_1, void *d_tmp, size_t tm
     return cub::DeviceScan::ExclusiveSum(d_tmp, need, d_vals, d_vals, (int)n_plus_1, st) == cudaSuccess ? 0 : 2;
 }
 
+// sa_align_rounds: the round records leave the device packed (a pair has 0..max_alns of them; at 10^7 pairs the dense
+// [pair][max_alns] array would be gigabytes of pinned memory and PCIe traffic for mostly empty slots)
+__global__ void rounds_count_kernel(const int32_t *nr, int64_t *off, long long m) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) off[i] = nr[i] > 0 ? nr[i] : 0;
+    if (i == m) off[i] = 0;
+}
+__global__ void rounds_gather_kernel(const sa_round *rounds, const int32_t *nr, const int64_t *off, sa_round *packed, long long m, int max_alns) {
+    // one thread per 16-byte half record: consecutive threads write consecutive halves
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = t / (2 * max_alns);
+    const int h = (int)(t % (2 * max_alns));
+    if (i >= m || (h >> 1) >= nr[i]) return;
+    reinterpret_cast<uint4 *>(packed + off[i])[h] = reinterpret_cast<const uint4 *>(rounds + i * max_alns)[h];
+}
+void launch_rounds_count(const int32_t *nr, int64_t *off, long long m, cudaStream_t st) {
+    rounds_count_kernel<<<(unsigned)((m + 1 + 255) / 256), 256, 0, st>>>(nr, off, m);
+}
+void launch_rounds_gather(const sa_round *rounds, const int32_t *nr, const int64_t *off, sa_round *packed, long long m, int max_alns, cudaStream_t st) {
+    const long long threads = m * 2 * max_alns;
+    if (threads > 0) rounds_gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(rounds, nr, off, packed, m, max_alns);
+}
+
 void launch_traceback(const TraceParams &p, cudaStream_t st) {
     const int threads = 64;
     const long long blocks = (p.n_problems + threads - 1) / threads;

@@ -135,6 +135,8 @@ void launch_fill(const FillParams &p, int store, bool swap, int shape, int n_cta
 int max_clusters();
 void launch_fill_unbanded(const FillParams &p, int32_t *prev32, bool swap, int n_ctas, cudaStream_t st);
 void launch_traceback(const TraceParams &p, cudaStream_t st);
+void launch_rounds_count(const int32_t *nr, int64_t *off, long long m, cudaStream_t st);
+void launch_rounds_gather(const sa_round *rounds, const int32_t *nr, const int64_t *off, sa_round *packed, long long m, int max_alns, cudaStream_t st);
 // in-place exclusive prefix sum of n+1 int64 values (the last input value is ignored: out[n] = total)
 int exclusive_scan_i64(int64_t *d_vals, int64_t n_plus_1, void *d_tmp, size_t tmp_bytes, size_t *tmp_needed, cudaStream_t st);
 void launch_powf12(const float *x, long long n, float *out, int fast, cudaStream_t st);

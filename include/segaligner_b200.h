@@ -124,7 +124,9 @@ int sa_align_batch_packed(sa_ctx *ctx, const sa_mode *mode, const sa_problem *pr
  *   thr[k]        the segment's score threshold (start value of curr_best_score and exp_thresh, main.cpp:262,266)
  *   used_slot     seed bitmap of the pair (tip phase: labels already taken on the contig) or -1; the seed is not modified
  * Output (pinned host memory owned by the context, valid until the next sa_align* call): n_rounds[k] rounds per pair
- * (0 when thr is NaN) in rounds[k * max_alns ...]; round r's traceback (end -> start, like aln_list) is
+ * (0 when thr is NaN), packed in pair order: pair k's records are rounds[round_off[k] .. round_off[k] + n_rounds[k]) (a
+ * batch of 10^7 pairs, most of which end after a round or two, returns megabytes instead of gigabytes); round r's traceback
+ * (end -> start, like aln_list) is
  * path_j/q/s[path_off .. path_off + path_len).  The last round of a pair is the one that failed `best > exp_thresh`
  * (or the max_alns-th accepted one).  Semi-global mode, lookback 6, no swap_b_x, every segment >= 2 labels; a pair whose
  * matrix exceeds the per-worker scratch gets n_rounds = -1 (the caller falls back to sa_align_batch_packed rounds).
@@ -167,16 +169,22 @@ typedef struct sa_rounds_out {
     int32_t max_alns;
     int32_t reserved;
     int64_t total;             /* packed path entries */
-    const int32_t *n_rounds;   /* n */
-    const sa_round *rounds;    /* n * max_alns */
+    const int32_t *n_rounds;   /* n (-1: not aligned, too large for the scratch; -2: certified unwritable, see tip_windows) */
+    const sa_round *rounds;    /* packed: sum over k of max(n_rounds[k], 0) records */
     const int32_t *path_j, *path_q;
     const float *path_s;
+    const int64_t *round_off;  /* n + 1: where pair k's records start in rounds */
 } sa_rounds_out;
 int sa_align_rounds(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const float *thr, int32_t max_alns,
                     const uint32_t *used_bits, int64_t used_words_per_slot, int64_t n_used_slots, sa_rounds_out *out);
 int sa_align_rounds_filtered(sa_ctx *ctx, const sa_mode *mode, const sa_problem *problems, int64_t n, const float *thr,
                              int32_t max_alns, const uint32_t *used_bits, int64_t used_words_per_slot, int64_t n_used_slots,
                              const sa_rounds_filter *filter, sa_rounds_out *out);
+/* Optional: pins the host buffers that sa_align_rounds* calls of up to n_pairs pairs return their results in, ahead of time
+ * (pinning costs 0.3 - 1 s per GB; growing a pinned buffer inside a call waits for the device).  The one call that may be
+ * made from ANOTHER host thread while sa_score_batch / sa_detect_batch runs on the context -- run_SA_score is when the host
+ * has nothing else to do (main.cpp:531-551) -- but not beside any sa_align* call. */
+int sa_prepare_rounds(sa_ctx *ctx, int64_t n_pairs, int32_t max_alns);
 
 /* Detection-mode scoring (run_SA_score with detection=true, main.cpp:155-159): semiglobal init, dp_align,
  * then multi_backtrack_scores (SegAligner.cpp:208-233) harvesting n_want[k] path scores per problem in the
