@@ -732,10 +732,20 @@ static int run_job(int argc, char *argv[], Engine &eng, bool keep_open, Spmd &sp
             if (const char *e = getenv("SA_NGPUS")) asked = atoi(e);
         if (asked <= 0) {
             // Nobody asked for a number of GPUs: a fixed-size job gains from another GPU only while its share of the work
-            // outweighs the start-up ladder (~0.8 s per additional GPU, driver-side; every rank must be up before the first
-            // exchange).  Whole run ~ cells / 25 GCUPS on one GPU; f(N) = 0.8 (N - 1) + t1 / N is smallest at sqrt(t1 / 0.8).
-            const double t1 = total_cells / 25e9;
-            const int best = (int)std::floor(std::sqrt(t1 / 0.8) + 0.5);
+            // outweighs the start-up ladder (0.8 - 2 s per additional GPU, driver-side and box-dependent; every rank must be
+            // up before the first exchange, and a rank that is already scoring stalls in its driver calls while the others
+            // come up).  Whole run ~ cells / 38 GCUPS on one GPU; f(N) = 1.2 (N - 1) + t1 / N; the smallest N within 5 % of the
+            // minimum (the curve is flat there, and fewer processes is the safer side of a start-up cost that varies).
+            const double t1 = total_cells / 38e9;
+            auto f = [&](int n) { return 1.2 * (n - 1) + t1 / n; };
+            int best = 1;
+            for (int n = 2; n <= sp.world; n++)
+                if (f(n) < f(best)) best = n;
+            for (int n = 1; n < best; n++)
+                if (f(n) <= 1.05 * f(best)) {
+                    best = n;
+                    break;
+                }
             sp.world = std::max(1, std::min(sp.world, best));
         }
         if (o.fitting_aln || segs.n_maps() == 0 || contigs.n_maps() == 0) sp.world = 1;
