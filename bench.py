@@ -15,6 +15,9 @@ scores that must be identical for every N (strong scaling).
                alignment rounds, tip alignment, ~28 k *_aln.txt files -- on N GPUs (-ngpus=N: one process
                and one context per GPU, problems sharded by index).  Same definition as the reference arm and
                cpu_baseline: phase-1 scoring cells / process wall time.  Host<->device bytes are the library's own counters.
+  whole_run_default_ngpus  (N > 1 lines) the same executable run without -ngpus: the executable's own choice of how many of
+               the N visible GPUs a job of this size is worth (CUDA start-up of every extra process against its share of the
+               work); e2e stays the forced -ngpus=N run.
   e2e_scoring  the scoring phase alone through the host-buffer C-ABI calls (sa_set_maps + sa_score_batch on this rank's
                shard, pinned host buffers, H2D/D2H inside) plus the gather of all results to rank 0.
   roofline     the binding resource of the executed work, the XU (MUFU) pipe: 2 MUFU per predecessor candidate (fp32 score
@@ -249,9 +252,32 @@ def run_reference_arm(args, rank):
 
 
 # ---- the drop-in executable, whole process -----------------------------------------------------------------------------
+def parse_verbose(err: str):
+    """SA_VERBOSE=1 stderr of bin/SegAligner -> (phase seconds by name, H2D bytes, D2H bytes, GPUs the run used or None)."""
+    phases, h2d, d2h, used = {}, 0, 0, None
+    for line in err.splitlines():
+        if line.startswith("SegAligner(b200): copied H2D"):
+            t = line.split()
+            h2d, d2h = int(t[3]), int(t[6])
+        elif line.startswith("SegAligner(b200): wall") and line.rstrip().endswith("GPU(s)"):
+            try:
+                used = int(line.split()[-2])
+            except ValueError:
+                pass
+        elif line.startswith("SegAligner(b200):") and line.rstrip().endswith(" s"):
+            name = line[len("SegAligner(b200):"):].rsplit(None, 2)[0].strip()
+            try:
+                phases[name] = float(line.split()[-2])
+            except ValueError:
+                pass
+    return phases, h2d, d2h, used
+
+
 def time_executable(segs, contigs, n_gpus: int, reps: int = 1):
-    """bin/SegAligner on the given maps, whole process (every phase, every output file); returns the JSON block."""
+    """bin/SegAligner on the given maps, whole process (every phase, every output file); returns the JSON block.
+    n_gpus = 0: no -ngpus flag, the executable picks the number of GPUs from the job size (its default behaviour)."""
     cells = scoring_cells(segs, contigs)
+    ng_flag = [f"-ngpus={n_gpus}"] if n_gpus > 0 else []
     env = dict(os.environ, SA_VERBOSE="1")
     with tempfile.TemporaryDirectory() as d:
         d = Path(d)
@@ -260,27 +286,17 @@ def time_executable(segs, contigs, n_gpus: int, reps: int = 1):
         wsegs = {i: segs[i] for i in sorted(segs)[:4]}
         wcont = {i: contigs[i] for i in sorted(contigs)[:40]}
         wf = write_inputs(d / "warm", wsegs, wcont)
-        run_binary(NEW_BIN, wf[0], wf[1], f"{d}/warm/SA", C2_FLAGS + ["-nthreads=8", f"-ngpus={n_gpus}"], env=env, capture=True)
+        run_binary(NEW_BIN, wf[0], wf[1], f"{d}/warm/SA", C2_FLAGS + ["-nthreads=8"] + ng_flag, env=env, capture=True)
         best, err = None, ""
         for rep in range(reps):
             (d / f"r{rep}").mkdir()
-            dt, e = run_binary(NEW_BIN, sf, cf, f"{d}/r{rep}/SA", C2_FLAGS + [f"-nthreads={os.cpu_count() or 1}", f"-ngpus={n_gpus}"],
+            dt, e = run_binary(NEW_BIN, sf, cf, f"{d}/r{rep}/SA", C2_FLAGS + [f"-nthreads={os.cpu_count() or 1}"] + ng_flag,
                                env=env, capture=True)
             if best is None or dt < best:
                 best, err = dt, e
         n_files = len([f for f in (d / "r0").iterdir() if f.name.endswith("_aln.txt")])
-    phases, h2d, d2h = {}, 0, 0
-    for line in err.splitlines():
-        if line.startswith("SegAligner(b200): copied H2D"):
-            t = line.split()
-            h2d, d2h = int(t[3]), int(t[6])
-        elif line.startswith("SegAligner(b200):") and line.rstrip().endswith(" s"):
-            name = line[len("SegAligner(b200):"):].rsplit(None, 2)[0].strip()
-            try:
-                phases[name] = float(line.split()[-2])
-            except ValueError:
-                pass
-    return {"value": cells / best / 1e9, "unit": UNIT, "wall_s": best, "scoring_cells": cells, "n_gpus": n_gpus,
+    phases, h2d, d2h, used = parse_verbose(err)
+    return {"value": cells / best / 1e9, "unit": UNIT, "wall_s": best, "scoring_cells": cells, "n_gpus": n_gpus if n_gpus > 0 else used,
             "alignment_files": n_files, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "phases_s": phases,
             "what": "bin/SegAligner whole process from CMAP files to output files (CUDA start-up, parse, phase-1 scoring, thresholds, "
                     "alignment rounds, tip alignment, all *_aln.txt files); value = phase-1 scoring cells / process wall time"}
@@ -529,7 +545,7 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- the drop-in boundary: the executable on the whole workload, rank 0 drives all N GPUs (-ngpus=N)
-    exe = None
+    exe = exe_auto = None
     if not args.no_extras:
         if world > 1:
             dist.barrier(group=gloo)  # host-side wait: an NCCL barrier would keep a kernel spinning on the idle ranks' GPUs
@@ -539,6 +555,15 @@ def main():
                 exe = time_executable(segs_all, contigs_all, world, reps=1 if args.steps < 3 else 2)
             except RuntimeError as e:
                 exe = {"value": None, "unit": UNIT, "error": str(e)[-400:]}
+            if world > 1:
+                # beside the forced -ngpus=N run: what the executable does when nobody tells it how many GPUs to use (it weighs
+                # the CUDA start-up of every additional process against its share of the work)
+                try:
+                    log("whole executable on the full workload, no -ngpus flag (the executable's own choice) ...")
+                    exe_auto = time_executable(segs_all, contigs_all, 0, reps=1)
+                    exe_auto["what"] = "the same run without -ngpus: the executable picks the number of GPUs from the job size"
+                except Exception as e:  # noqa: BLE001 -- an optional key must not cost the line
+                    exe_auto = {"value": None, "unit": UNIT, "error": str(e)[-400:]}
         if world > 1:
             dist.barrier(group=gloo)
 
@@ -596,6 +621,8 @@ def main():
                           "d2h_bytes_per_step": exe.get("d2h_bytes_per_step", 0), "steps": 1, **{k: v for k, v in exe.items()
                                                                                                    if k not in ("value", "unit")}}
             out["whole_run" if world == 1 else "whole_run_ngpus"] = exe
+            if exe_auto is not None:
+                out["whole_run_default_ngpus"] = exe_auto
         else:
             out["e2e"] = dict(out["e2e_scoring"], note="--no-extras: the whole-executable run was skipped; this is e2e_scoring")
         if world == 1 and not args.no_extras:
